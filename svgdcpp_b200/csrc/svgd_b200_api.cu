@@ -1,0 +1,1000 @@
+// svgd_b200_api.cu — context, host orchestration and the C ABI of include/svgd_b200.h.
+//
+// One SVGD::Step (reference SVGD.hpp:373-400) is, on the device:
+//   r = |x|^2  ->  [median bandwidth a]  ->  G = grad log p(X_local)  ->  V = G - 2aX  [all-gather V]
+//   ->  fused pair interaction + optimizer + clamp -> X_next(local rows)  [all-gather X_next]  -> swap
+// There is no CPU fallback anywhere in this file: every numerical result comes from a kernel.
+#include "../../include/svgd_b200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels_f64.cuh"
+#include "select.cuh"
+#ifdef SVGDB_WITH_TC32
+#include "kernels_tc32.cuh"
+#endif
+
+using namespace svgdb;
+
+namespace {
+
+enum { MODEL_UNSET = 0, MODEL_MVN_SUM = 1, MODEL_HOOK = 2 };
+constexpr uint64_t KEY_END = 0x7FF0000000000001ull; // one past the bit pattern of +inf
+
+struct HostScratch { // pinned
+    unsigned long long below, max_below, cand_count;
+    unsigned long long hist[HIST_BINS];
+    MedianResult med;
+};
+
+} // namespace
+
+struct svgdb_ctx {
+    int device = 0;
+    int64_t N = 0;
+    int d = 0;
+    int precision = SVGDB_PRECISION_F64;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int sm_count = 148;
+
+    // sharding
+    int world = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    int64_t rows_per_rank = 0, row0 = 0, n_rows = 0, n_pad = 0;
+
+    // device state
+    double *X[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *V = nullptr, *G = nullptr, *r = nullptr, *s1 = nullptr, *s2 = nullptr, *a_dev = nullptr;
+    double *lb = nullptr, *ub = nullptr;
+    double *phi_dbg = nullptr;
+
+    // model
+    int model_kind = MODEL_UNSET;
+    int C = 0;
+    double *means_dev = nullptr, *prec_dev = nullptr;
+    svgdb_grad_fn hook = nullptr;
+    void *hook_user = nullptr;
+
+    // kernel
+    bool kernel_set = false;
+    int scale_method = SVGDB_SCALE_MEDIAN;
+    double fixed_a = 0.0;
+
+    // optimizer
+    bool opt_set = false;
+    OptParams opt{};
+    uint64_t counter = 0;
+    bool initialized = false;
+
+    // median machinery
+    unsigned long long *below = nullptr, *max_below = nullptr, *hist = nullptr, *cand = nullptr, *cand_count = nullptr;
+    uint64_t capacity = 1ull << 24;
+    SelectState *sel = nullptr;
+    MedianResult *medres = nullptr;
+    HostScratch *hs = nullptr;
+    bool have_pred = false;
+    double pred_d2_lo = 0.0, pred_d2_hi = 0.0, delta = 0.0;
+    int skip_pred = 0, miss_streak = 0;
+
+    // measurement
+    svgdb_stats stats{};
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    std::string err;
+};
+
+namespace {
+
+int fail(svgdb_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, SVGDB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess)                                                                           \
+            return fail(ctx, SVGDB_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));        \
+    } while (0)
+
+#define TRY(call)                                                                                        \
+    do {                                                                                                 \
+        int rc_ = (call);                                                                                \
+        if (rc_ != SVGDB_OK) return rc_;                                                                 \
+    } while (0)
+
+#define KERNEL_CHECK()                                                                                   \
+    do {                                                                                                 \
+        ++ctx->stats.kernel_launches;                                                                    \
+        CU(cudaGetLastError());                                                                          \
+    } while (0)
+
+// Gauss-Jordan inverse with partial pivoting (double).  A is d x d; returns false if singular.
+bool invert_matrix(const double *A, int d, std::vector<double> &inv)
+{
+    std::vector<double> w((size_t)d * 2 * d, 0.0);
+    for (int r = 0; r < d; ++r) {
+        for (int c = 0; c < d; ++c) w[(size_t)r * 2 * d + c] = A[(size_t)r * d + c];
+        w[(size_t)r * 2 * d + d + r] = 1.0;
+    }
+    for (int col = 0; col < d; ++col) {
+        int piv = col;
+        double best = std::fabs(w[(size_t)col * 2 * d + col]);
+        for (int r = col + 1; r < d; ++r) {
+            double v = std::fabs(w[(size_t)r * 2 * d + col]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (!(best > 0.0) || !std::isfinite(best)) return false;
+        if (piv != col)
+            for (int c = 0; c < 2 * d; ++c) std::swap(w[(size_t)col * 2 * d + c], w[(size_t)piv * 2 * d + c]);
+        double pv = w[(size_t)col * 2 * d + col];
+        for (int c = 0; c < 2 * d; ++c) w[(size_t)col * 2 * d + c] /= pv;
+        for (int r = 0; r < d; ++r) {
+            if (r == col) continue;
+            double f = w[(size_t)r * 2 * d + col];
+            if (f == 0.0) continue;
+            for (int c = 0; c < 2 * d; ++c) w[(size_t)r * 2 * d + c] -= f * w[(size_t)col * 2 * d + c];
+        }
+    }
+    inv.assign((size_t)d * d, 0.0);
+    for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c) inv[(size_t)r * d + c] = w[(size_t)r * 2 * d + d + c];
+    // d/dx of -1/2 x^T P x is -1/2 (P + P^T) x: the symmetric part is what the reference's AD sees
+    for (int r = 0; r < d; ++r)
+        for (int c = r + 1; c < d; ++c) {
+            double s = 0.5 * (inv[(size_t)r * d + c] + inv[(size_t)c * d + r]);
+            inv[(size_t)r * d + c] = inv[(size_t)c * d + r] = s;
+        }
+    return true;
+}
+
+inline uint64_t key_of(double v)
+{
+    uint64_t k;
+    std::memcpy(&k, &v, 8);
+    return k;
+}
+
+int free_sharded(svgdb_ctx *ctx)
+{
+    cudaFree(ctx->X[0]); cudaFree(ctx->X[1]); cudaFree(ctx->V); cudaFree(ctx->G); cudaFree(ctx->r);
+    cudaFree(ctx->s1); cudaFree(ctx->s2); cudaFree(ctx->phi_dbg);
+    ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
+    return SVGDB_OK;
+}
+
+int alloc_sharded(svgdb_ctx *ctx)
+{
+    free_sharded(ctx);
+    ctx->rows_per_rank = (ctx->N + ctx->world - 1) / ctx->world;
+    ctx->n_pad = ctx->rows_per_rank * ctx->world;
+    ctx->row0 = ctx->rows_per_rank * ctx->rank;
+    ctx->n_rows = std::max<int64_t>(0, std::min<int64_t>(ctx->rows_per_rank, ctx->N - ctx->row0));
+    size_t full = (size_t)ctx->n_pad * ctx->d * sizeof(double);
+    size_t local = (size_t)ctx->rows_per_rank * ctx->d * sizeof(double);
+    CU(cudaMalloc(&ctx->X[0], full));
+    CU(cudaMalloc(&ctx->X[1], full));
+    CU(cudaMalloc(&ctx->V, full));
+    CU(cudaMalloc(&ctx->r, (size_t)ctx->n_pad * sizeof(double)));
+    CU(cudaMalloc(&ctx->G, local));
+    CU(cudaMalloc(&ctx->s1, local));
+    CU(cudaMalloc(&ctx->s2, local));
+    CU(cudaMalloc(&ctx->phi_dbg, local));
+    CU(cudaMemsetAsync(ctx->X[0], 0, full, ctx->stream));
+    CU(cudaMemsetAsync(ctx->X[1], 0, full, ctx->stream));
+    CU(cudaMemsetAsync(ctx->V, 0, full, ctx->stream));
+    CU(cudaMemsetAsync(ctx->s1, 0, local, ctx->stream));
+    CU(cudaMemsetAsync(ctx->s2, 0, local, ctx->stream));
+    ctx->cur = 0;
+    return SVGDB_OK;
+}
+
+// ---- collectives (no-ops at world == 1) ------------------------------------------------------
+int allreduce_u64(svgdb_ctx *ctx, unsigned long long *buf, size_t count, ncclRedOp_t op)
+{
+    if (ctx->world == 1) return SVGDB_OK;
+    NC(ncclAllReduce(buf, buf, count, ncclUint64, op, ctx->comm, ctx->stream));
+    return SVGDB_OK;
+}
+
+int allgather_rows(svgdb_ctx *ctx, double *buf, int64_t elems_per_row)
+{
+    if (ctx->world == 1) return SVGDB_OK;
+    size_t chunk = (size_t)ctx->rows_per_rank * elems_per_row;
+    NC(ncclAllGather(buf + (size_t)ctx->rank * chunk, buf, chunk, ncclDouble, ctx->comm, ctx->stream));
+    return SVGDB_OK;
+}
+
+// ---- phases ------------------------------------------------------------------------------------
+int launch_rownorm(svgdb_ctx *ctx)
+{
+    const int wpb = 8;
+    int64_t blocks = (ctx->N + wpb - 1) / wpb;
+    rownorm_f64_kernel<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->r);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+size_t dist_smem_bytes(int d, bool hist)
+{
+    int kc = d < 64 ? ((d + 3) & ~3) : 64;
+    int ldx = ((kc + 15) & ~15) + 4;
+    return (size_t)(2 * 64 * ldx + 128) * sizeof(double) + (hist ? HIST_BINS * sizeof(unsigned int) : 0);
+}
+
+int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
+{
+    DistArgs a{};
+    a.X = ctx->X[ctx->cur];
+    a.r = ctx->r;
+    a.n_total = ctx->N;
+    a.d = ctx->d;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.sym = ctx->world == 1 ? 1 : 0;
+    a.n_tiles_j = (ctx->N + 63) / 64;
+    a.n_tiles_i = (ctx->n_rows + 63) / 64;
+    a.n_work = a.sym ? a.n_tiles_j * (a.n_tiles_j + 1) / 2 : a.n_tiles_i * a.n_tiles_j;
+    a.lo = lo;
+    a.hi = hi;
+    a.shift = shift;
+    a.below = ctx->below;
+    a.max_below = ctx->max_below;
+    a.hist = ctx->hist;
+    a.cand = ctx->cand;
+    a.cand_count = ctx->cand_count;
+    a.capacity = ctx->capacity;
+    CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
+    if (a.n_work > 0) {
+        unsigned grid = (unsigned)std::min<int64_t>(a.n_work, (int64_t)ctx->sm_count * 4);
+        if (mode == MODE_HIST) {
+            CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
+            dist_pass_f64_kernel<MODE_HIST><<<grid, 128, dist_smem_bytes(ctx->d, true), ctx->stream>>>(a);
+        } else {
+            CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
+            dist_pass_f64_kernel<MODE_COLLECT><<<grid, 128, dist_smem_bytes(ctx->d, false), ctx->stream>>>(a);
+        }
+        KERNEL_CHECK();
+    }
+    ++ctx->stats.median_passes;
+    TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
+    TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
+    if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
+    return SVGDB_OK;
+}
+
+// Reads below / max_below / (hist | cand_count) back to the pinned mirror.  In the multi-rank case
+// `cand_count` stays local; hs->below etc. are global.  mid_total gets the global in-bracket count.
+int read_pass_results(svgdb_ctx *ctx, int mode, uint64_t *mid_total)
+{
+    CU(cudaMemcpyAsync(&ctx->hs->below, ctx->below, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->hs->max_below, ctx->max_below, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == MODE_HIST) {
+        CU(cudaMemcpyAsync(ctx->hs->hist, ctx->hist, HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CU(cudaMemcpyAsync(&ctx->hs->cand_count, ctx->cand_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint64_t total = ctx->hs->cand_count;
+        if (ctx->world > 1) {
+            // global in-bracket count: reuse `below` as a scratch word after it has been read
+            CU(cudaMemcpyAsync(ctx->below, ctx->cand_count, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
+            unsigned long long tmp = 0;
+            CU(cudaMemcpyAsync(&tmp, ctx->below, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            total = tmp;
+        }
+        if (mid_total) *mid_total = total;
+    }
+    return SVGDB_OK;
+}
+
+// Radix select of rank kk among this rank's candidates (hist all-reduced across ranks), then a.
+int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n)
+{
+    uint64_t m_local = std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
+    // digits above the highest differing bit of [lo, hi) are common to every candidate
+    uint64_t diff = lo ^ (hi - 1);
+    uint64_t prefix = 0, mask = 0;
+    int first_shift = 56;
+    while (first_shift >= 0 && ((diff >> first_shift) & 255ull) == 0ull) {
+        prefix |= lo & (255ull << first_shift);
+        mask |= 255ull << first_shift;
+        first_shift -= 8;
+    }
+    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, prefix, mask, kk);
+    KERNEL_CHECK();
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m_local + 2047) / 2048, (uint64_t)ctx->sm_count * 8));
+    for (int shift = first_shift; shift >= 0; shift -= 8) {
+        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, ctx->sel);
+        KERNEL_CHECK();
+        TRY(allreduce_u64(ctx, ctx->sel->hist, 256, ncclSum));
+        select_pick_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, shift);
+        KERNEL_CHECK();
+    }
+    if (even) {
+        select_max_less_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, ctx->sel);
+        KERNEL_CHECK();
+        TRY(allreduce_u64(ctx, &ctx->sel->max_less, 1, ncclMax));
+    }
+    median_finalize_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, kk, even ? 1 : 0, ctx->max_below, 0, 0ull, log_n,
+                                                      ctx->medres, ctx->a_dev);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+// GaussianRBFKernel::ComputeScale, Median branch (Kernel/GaussianRBFKernel.hpp:168-188), exact.
+int median_scale(svgdb_ctx *ctx)
+{
+    const long double totald = (long double)ctx->N * (long double)ctx->N;
+    if (totald > 1.8e19L) return fail(ctx, SVGDB_ERR_INVALID, "n^2 overflows 64 bits");
+    const uint64_t total = (uint64_t)ctx->N * (uint64_t)ctx->N;
+    const bool even = (total % 2ull) == 0ull;
+    const uint64_t k_hi = total / 2ull; // 0-based rank of the upper middle (the middle when odd)
+    const double log_n = std::log((double)ctx->N);
+
+    uint64_t lo = 0, hi = KEY_END, below_known = 0, in_range = total;
+    bool collected = false;
+    uint64_t mid = 0;
+
+    // 1) predicted bracket around the previous iteration's median (one pass when it holds)
+    if (ctx->have_pred && ctx->skip_pred == 0 && total > ctx->capacity) {
+        double plo = ctx->pred_d2_lo * (1.0 - ctx->delta), phi = ctx->pred_d2_hi * (1.0 + ctx->delta);
+        uint64_t klo = key_of(std::max(plo, 0.0)), khi = key_of(phi) + 1;
+        TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
+        TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
+        uint64_t b = ctx->hs->below;
+        bool hit = (b <= k_hi) && (k_hi < b + mid) && (mid <= ctx->capacity) && (!even || k_hi >= 1);
+        if (hit) {
+            lo = klo; hi = khi; below_known = b; collected = true;
+            ++ctx->stats.median_bracket_hits;
+            ctx->miss_streak = 0;
+            // proportional control: aim for capacity/4 candidates
+            double target = (double)ctx->capacity / 4.0;
+            ctx->delta = std::min(0.0625, std::max(1e-9, ctx->delta * target / (double)std::max<uint64_t>(mid, 1)));
+        } else {
+            ++ctx->miss_streak;
+            ctx->skip_pred = std::min(64, 1 << std::min(ctx->miss_streak, 6)) - 1;
+            if (mid <= ctx->capacity) ctx->delta = std::min(0.0625, ctx->delta * 4.0);
+            else ctx->delta *= 0.25;
+        }
+    } else if (ctx->skip_pred > 0) {
+        --ctx->skip_pred;
+    }
+
+    // 2) radix narrowing on the key bits until the bracket fits the candidate buffer
+    if (!collected) {
+        while (in_range > ctx->capacity && hi - lo > 1) {
+            uint64_t span = hi - lo - 1;
+            int bits = 0;
+            while (bits < 64 && (span >> bits) != 0ull) ++bits;
+            int shift = std::max(0, bits - 12);
+            TRY(launch_dist_pass(ctx, MODE_HIST, lo, hi, shift));
+            TRY(read_pass_results(ctx, MODE_HIST, nullptr));
+            uint64_t cum = ctx->hs->below;
+            int b = 0;
+            for (; b < HIST_BINS; ++b) {
+                if (k_hi < cum + ctx->hs->hist[b]) break;
+                cum += ctx->hs->hist[b];
+            }
+            if (b == HIST_BINS) return fail(ctx, SVGDB_ERR_NUMERIC, "median select: rank not found (non-finite particles?)");
+            uint64_t nlo = lo + ((uint64_t)b << shift);
+            uint64_t nhi = std::min<uint64_t>(hi, nlo + (1ull << shift));
+            lo = nlo; hi = nhi; below_known = cum; in_range = ctx->hs->hist[b];
+        }
+        TRY(launch_dist_pass(ctx, MODE_COLLECT, lo, hi, 0));
+        TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
+        below_known = ctx->hs->below;
+        if (!(below_known <= k_hi && k_hi < below_known + mid))
+            return fail(ctx, SVGDB_ERR_NUMERIC, "median select: bracket lost the rank (non-finite particles?)");
+    }
+
+    const uint64_t kk = k_hi - below_known;
+    if (mid > ctx->capacity) {
+        // only reachable when hi - lo == 1: more than `capacity` identical distances
+        median_finalize_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, kk, even ? 1 : 0, ctx->max_below, 1, lo, log_n,
+                                                          ctx->medres, ctx->a_dev);
+        KERNEL_CHECK();
+    } else {
+        TRY(run_select(ctx, lo, hi, kk, even, log_n));
+    }
+    CU(cudaMemcpyAsync(&ctx->hs->med, ctx->medres, sizeof(MedianResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.last_scale = ctx->hs->med.scale;
+    ctx->pred_d2_lo = ctx->hs->med.d2_lo;
+    ctx->pred_d2_hi = ctx->hs->med.d2_hi;
+    if (!ctx->have_pred) {
+        ctx->have_pred = true;
+        ctx->delta = std::min(0.0625, std::max(1e-9, (double)ctx->capacity / (40.0 * (double)total)));
+    }
+    return SVGDB_OK;
+}
+
+int compute_scale_dev(svgdb_ctx *ctx)
+{
+    if (ctx->scale_method == SVGDB_SCALE_MEDIAN) return median_scale(ctx);
+    if (ctx->scale_method == SVGDB_SCALE_FIXED) {
+        CU(cudaMemcpyAsync(ctx->a_dev, &ctx->fixed_a, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.last_scale = ctx->fixed_a;
+        return SVGDB_OK;
+    }
+    return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is not implemented on the device path yet");
+}
+
+int launch_grad(svgdb_ctx *ctx)
+{
+    if (ctx->n_rows <= 0) return SVGDB_OK;
+    if (ctx->model_kind == MODEL_HOOK) {
+        int rc = ctx->hook(ctx->X[ctx->cur], ctx->G, ctx->N, ctx->d, ctx->row0, ctx->n_rows, (void *)ctx->stream, ctx->hook_user);
+        if (rc != 0) return fail(ctx, SVGDB_ERR_INVALID, "device gradient hook returned " + std::to_string(rc));
+        return SVGDB_OK;
+    }
+    constexpr int PT = 16;
+    size_t smem = ((size_t)3 * PT * ctx->d + 5 * PT) * sizeof(double);
+    unsigned blocks = (unsigned)((ctx->n_rows + PT - 1) / PT);
+    mvn_sum_grad_f64_kernel<PT><<<blocks, 128, smem, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->row0, ctx->n_rows,
+                                                                     ctx->C, ctx->means_dev, ctx->prec_dev, ctx->G);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+size_t phi_smem_bytes(int d, int dc)
+{
+    int kc = d < 64 ? ((d + 3) & ~3) : 64;
+    int ldx = ((kc + 15) & ~15) + 4;
+    return (size_t)(2 * 64 * ldx + 64 * (dc + 2) + 64) * sizeof(double);
+}
+
+template <int DC>
+int launch_phi_dc(svgdb_ctx *ctx, const PhiArgs &a)
+{
+    dim3 grid((unsigned)((ctx->n_rows + 63) / 64), (unsigned)((ctx->d + DC - 1) / DC));
+    phi_f64_kernel<DC><<<grid, 128, phi_smem_bytes(ctx->d, DC), ctx->stream>>>(a);
+    KERNEL_CHECK();
+    ++ctx->stats.phi_launches;
+    return SVGDB_OK;
+}
+
+int launch_phi(svgdb_ctx *ctx, bool debug_phi)
+{
+    if (ctx->n_rows <= 0) return SVGDB_OK;
+    PhiArgs a{};
+    a.X = ctx->X[ctx->cur];
+    a.V = ctx->V;
+    a.r = ctx->r;
+    a.a_ptr = ctx->a_dev;
+    a.n_total = ctx->N;
+    a.d = ctx->d;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.opt = ctx->opt;
+    a.s1 = ctx->s1;
+    a.s2 = ctx->s2;
+    a.lb = ctx->lb;
+    a.ub = ctx->ub;
+    a.X_out = ctx->X[ctx->cur ^ 1];
+    a.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+    if (ctx->d <= 8) return launch_phi_dc<8>(ctx, a);
+    if (ctx->d <= 16) return launch_phi_dc<16>(ctx, a);
+    if (ctx->d <= 32) return launch_phi_dc<32>(ctx, a);
+    return launch_phi_dc<64>(ctx, a);
+}
+
+int launch_make_v(svgdb_ctx *ctx)
+{
+    if (ctx->n_rows > 0) {
+        int64_t cnt = ctx->n_rows * ctx->d;
+        make_v_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->G, ctx->a_dev, ctx->row0,
+                                                                                   ctx->n_rows, ctx->d, ctx->V);
+        KERNEL_CHECK();
+    }
+    return allgather_rows(ctx, ctx->V, ctx->d);
+}
+
+int check_ready(svgdb_ctx *ctx)
+{
+    if (ctx->model_kind == MODEL_UNSET) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
+    if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
+    return SVGDB_OK;
+}
+
+void prof_mark(svgdb_ctx *ctx, int i)
+{
+    if (ctx->profiling) cudaEventRecord(ctx->ev[i], ctx->stream);
+}
+
+// phi (and everything it needs) for the current X; leaves V, r, a on the device
+int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
+{
+    prof_mark(ctx, 0);
+    TRY(launch_rownorm(ctx));
+    TRY(compute_scale_dev(ctx));
+    prof_mark(ctx, 1);
+    TRY(launch_grad(ctx));
+    prof_mark(ctx, 2);
+    TRY(launch_make_v(ctx));
+    prof_mark(ctx, 3);
+    TRY(launch_phi(ctx, debug_phi));
+    prof_mark(ctx, 4);
+    return SVGDB_OK;
+}
+
+int one_step(svgdb_ctx *ctx)
+{
+    ++ctx->counter; // Adam increments its counter before the bias correction (Adam.hpp:80-82)
+    if (ctx->opt.kind == OPT_ADAM) {
+        ctx->opt.bias1 = 1.0 - std::pow(ctx->opt.beta1, (double)ctx->counter);
+        ctx->opt.bias2 = 1.0 - std::pow(ctx->opt.beta2, (double)ctx->counter);
+    }
+    TRY(prepare_and_phi(ctx, false));
+    TRY(allgather_rows(ctx, ctx->X[ctx->cur ^ 1], ctx->d));
+    ctx->cur ^= 1;
+    ++ctx->stats.iterations;
+    if (ctx->profiling) {
+        cudaEvent_t end;
+        CU(cudaEventCreate(&end));
+        CU(cudaEventRecord(end, ctx->stream));
+        CU(cudaEventSynchronize(end));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.ms_median += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_grad += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_comm += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_phi += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[4], end); ctx->stats.ms_comm += ms;
+        cudaEventDestroy(end);
+    }
+    return SVGDB_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *svgdb_version(void) { return "svgd_b200 0.1 (sm_100a)"; }
+
+const char *svgdb_last_error(const svgdb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int precision_mode)
+{
+    if (!out) return SVGDB_ERR_INVALID;
+    *out = nullptr;
+    if (n_total < 1 || d < 1) return SVGDB_ERR_DIMENSION;
+    svgdb_ctx *ctx = new (std::nothrow) svgdb_ctx();
+    if (!ctx) return SVGDB_ERR_NOMEM;
+    *out = ctx; // returned even on failure so the caller can read svgdb_last_error, then destroy
+    ctx->device = device;
+    ctx->N = n_total;
+    ctx->d = d;
+    ctx->precision = precision_mode;
+    if (precision_mode != SVGDB_PRECISION_F64 && precision_mode != SVGDB_PRECISION_TC32)
+        return fail(ctx, SVGDB_ERR_INVALID, "unknown precision mode");
+#ifndef SVGDB_WITH_TC32
+    if (precision_mode == SVGDB_PRECISION_TC32)
+        return fail(ctx, SVGDB_ERR_INVALID, "this build has no TC32 (tcgen05) path");
+#endif
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, SVGDB_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                             " (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ctx, SVGDB_ERR_CUDA, "built for sm_100a (B200); found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
+    if (const char *s = std::getenv("SVGDB_CAND_CAPACITY")) {
+        long long v = std::atoll(s);
+        if (v >= 64) ctx->capacity = (uint64_t)v;
+    }
+    // opt-in to large dynamic shared memory for every instantiation we launch
+    CU(cudaFuncSetAttribute(phi_f64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phi_smem_bytes(d, 8)));
+    CU(cudaFuncSetAttribute(phi_f64_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phi_smem_bytes(d, 16)));
+    CU(cudaFuncSetAttribute(phi_f64_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phi_smem_bytes(d, 32)));
+    CU(cudaFuncSetAttribute(phi_f64_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phi_smem_bytes(d, 64)));
+    CU(cudaFuncSetAttribute(dist_pass_f64_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dist_smem_bytes(d, true)));
+    CU(cudaFuncSetAttribute(dist_pass_f64_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dist_smem_bytes(d, false)));
+    {
+        size_t gsm = ((size_t)3 * 16 * d + 5 * 16) * sizeof(double);
+        if (gsm > (size_t)prop.sharedMemPerBlockOptin)
+            return fail(ctx, SVGDB_ERR_DIMENSION, "dimension too large for the built-in Gaussian gradient kernel (d <= 590)");
+        CU(cudaFuncSetAttribute(mvn_sum_grad_f64_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    }
+    CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
+    CU(cudaMalloc(&ctx->below, 8));
+    CU(cudaMalloc(&ctx->max_below, 8));
+    CU(cudaMalloc(&ctx->cand_count, 8));
+    CU(cudaMalloc(&ctx->hist, HIST_BINS * 8));
+    CU(cudaMalloc(&ctx->sel, sizeof(SelectState)));
+    CU(cudaMalloc(&ctx->medres, sizeof(MedianResult)));
+    CU(cudaMallocHost(&ctx->hs, sizeof(HostScratch)));
+    {
+        // the candidate buffer never needs more than n^2 entries
+        long double tot = (long double)n_total * (long double)n_total;
+        if (tot < (long double)ctx->capacity) ctx->capacity = std::max<uint64_t>(64, (uint64_t)tot);
+        CU(cudaMalloc(&ctx->cand, ctx->capacity * 8));
+    }
+    TRY(alloc_sharded(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+void svgdb_destroy(svgdb_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    free_sharded(ctx);
+    cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
+    cudaFree(ctx->below); cudaFree(ctx->max_below); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
+    cudaFree(ctx->sel); cudaFree(ctx->medres);
+    if (ctx->hs) cudaFreeHost(ctx->hs);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int svgdb_set_stream(svgdb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SVGDB_OK;
+}
+
+int svgdb_nccl_unique_id(void *out_id, size_t bytes)
+{
+    if (!out_id || bytes < sizeof(ncclUniqueId)) return SVGDB_ERR_INVALID;
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return SVGDB_ERR_NCCL;
+    std::memcpy(out_id, &id, sizeof(id));
+    return SVGDB_OK;
+}
+
+int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique_id, size_t bytes)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SVGDB_ERR_INVALID, "bad world/rank");
+    if (world > ctx->N) return fail(ctx, SVGDB_ERR_DIMENSION, "more ranks than particles");
+    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (world > 1) {
+        if (!nccl_unique_id || bytes < sizeof(ncclUniqueId)) return fail(ctx, SVGDB_ERR_INVALID, "missing ncclUniqueId");
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id, sizeof(id));
+        CU(cudaSetDevice(ctx->device));
+        NC(ncclCommInitRank(&ctx->comm, world, id, rank));
+    }
+    ctx->world = world;
+    ctx->rank = rank;
+    ctx->have_pred = false;
+    TRY(alloc_sharded(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+int svgdb_set_particles(svgdb_ctx *ctx, const double *X)
+{
+    if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
+    CU(cudaMemcpyAsync(ctx->X[ctx->cur], X, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_pred = false;
+    return SVGDB_OK;
+}
+
+int svgdb_get_particles(svgdb_ctx *ctx, double *X)
+{
+    if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
+    CU(cudaMemcpyAsync(X, ctx->X[ctx->cur], (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+int svgdb_set_model_mvn_sum(svgdb_ctx *ctx, int32_t C, const double *means, const double *covs)
+{
+    if (!ctx || !means || !covs) return fail(ctx, SVGDB_ERR_INVALID, "null model parameters");
+    if (C < 1) return fail(ctx, SVGDB_ERR_INVALID, "a mixture needs at least one component");
+    const int d = ctx->d;
+    std::vector<double> prec((size_t)C * d * d), inv;
+    for (int c = 0; c < C; ++c) {
+        if (!invert_matrix(covs + (size_t)c * d * d, d, inv))
+            return fail(ctx, SVGDB_ERR_NUMERIC, "covariance of component " + std::to_string(c) + " is singular");
+        std::copy(inv.begin(), inv.end(), prec.begin() + (size_t)c * d * d);
+    }
+    cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
+    ctx->means_dev = ctx->prec_dev = nullptr;
+    CU(cudaMalloc(&ctx->means_dev, (size_t)C * d * sizeof(double)));
+    CU(cudaMalloc(&ctx->prec_dev, prec.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->means_dev, means, (size_t)C * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->prec_dev, prec.data(), prec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // prec is a local
+    ctx->C = C;
+    ctx->model_kind = MODEL_MVN_SUM;
+    return SVGDB_OK;
+}
+
+int svgdb_set_model_mvn(svgdb_ctx *ctx, const double *mean, const double *cov)
+{
+    return svgdb_set_model_mvn_sum(ctx, 1, mean, cov);
+}
+
+int svgdb_set_model_device_hook(svgdb_ctx *ctx, svgdb_grad_fn fn, void *user)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (!fn) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
+    ctx->hook = fn;
+    ctx->hook_user = user;
+    ctx->model_kind = MODEL_HOOK;
+    return SVGDB_OK;
+}
+
+int svgdb_set_kernel_rbf(svgdb_ctx *ctx, int scale_method, double fixed_a)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (scale_method != SVGDB_SCALE_MEDIAN && scale_method != SVGDB_SCALE_FIXED && scale_method != SVGDB_SCALE_HESSIAN)
+        return fail(ctx, SVGDB_ERR_INVALID, "[Argument error] Invalid scale method Enum provided.");
+    if (scale_method == SVGDB_SCALE_HESSIAN)
+        return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is not implemented on the device path yet");
+    if (scale_method == SVGDB_SCALE_FIXED && !(fixed_a > 0.0) ) return fail(ctx, SVGDB_ERR_INVALID, "fixed kernel scale must be positive");
+    ctx->scale_method = scale_method;
+    ctx->fixed_a = fixed_a;
+    ctx->kernel_set = true;
+    return SVGDB_OK;
+}
+
+int svgdb_set_optimizer(svgdb_ctx *ctx, int kind, double lr, double beta1, double beta2, double eps)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (kind == SVGDB_OPT_ADAM) {
+        if (beta1 >= 1.0 || beta1 < 0.0 || beta2 >= 1.0 || beta2 < 0.0)
+            return fail(ctx, SVGDB_ERR_INVALID, "[Argument Error] Invalid value for decay parameter beta.");
+    } else if (kind == SVGDB_OPT_RMSPROP) {
+        if (beta1 > 1.0 || beta1 < 0.0) return fail(ctx, SVGDB_ERR_INVALID, "[Argument Error] Invalid value for decay parameter beta.");
+    } else if (kind != SVGDB_OPT_ADAGRAD) {
+        return fail(ctx, SVGDB_ERR_INVALID, "unknown optimizer kind");
+    }
+    ctx->opt.kind = kind;
+    ctx->opt.lr = lr;
+    ctx->opt.beta1 = beta1;
+    ctx->opt.beta2 = beta2;
+    ctx->opt.eps = eps;
+    ctx->opt.bias1 = ctx->opt.bias2 = 1.0;
+    ctx->opt_set = true;
+    return SVGDB_OK;
+}
+
+int svgdb_set_bounds(svgdb_ctx *ctx, const double *lb, const double *ub, int32_t n_bound)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    cudaFree(ctx->lb); cudaFree(ctx->ub);
+    ctx->lb = ctx->ub = nullptr;
+    if (!lb && !ub) return SVGDB_OK;
+    if (!lb || !ub) return fail(ctx, SVGDB_ERR_INVALID, "both bounds are required");
+    if (n_bound != 1 && n_bound != ctx->d) return fail(ctx, SVGDB_ERR_DIMENSION, "The provided bounds have incorrect dimensions.");
+    std::vector<double> l(ctx->d), u(ctx->d);
+    for (int k = 0; k < ctx->d; ++k) { l[k] = lb[n_bound == 1 ? 0 : k]; u[k] = ub[n_bound == 1 ? 0 : k]; }
+    CU(cudaMalloc(&ctx->lb, ctx->d * sizeof(double)));
+    CU(cudaMalloc(&ctx->ub, ctx->d * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->lb, l.data(), ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->ub, u.data(), ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+int svgdb_initialize(svgdb_ctx *ctx)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    TRY(check_ready(ctx));
+    if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
+    size_t local = (size_t)ctx->rows_per_rank * ctx->d * sizeof(double);
+    CU(cudaMemsetAsync(ctx->s1, 0, local, ctx->stream));
+    CU(cudaMemsetAsync(ctx->s2, 0, local, ctx->stream));
+    ctx->counter = 0;
+    ctx->initialized = true;
+    return SVGDB_OK;
+}
+
+int svgdb_step(svgdb_ctx *ctx, int64_t iters)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    TRY(check_ready(ctx));
+    if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
+    CU(cudaSetDevice(ctx->device));
+    for (int64_t it = 0; it < iters; ++it) TRY(one_step(ctx));
+    return SVGDB_OK;
+}
+
+int svgdb_compute_phi(svgdb_ctx *ctx, double *phi, double *scale_out)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    TRY(check_ready(ctx));
+    CU(cudaSetDevice(ctx->device));
+    TRY(prepare_and_phi(ctx, true));
+    if (phi) {
+        // gather the local rows of every rank through V's storage (phi is debug output)
+        double *tmp = ctx->V;
+        if (ctx->n_rows > 0)
+            CU(cudaMemcpyAsync(tmp + (size_t)ctx->row0 * ctx->d, ctx->phi_dbg, (size_t)ctx->n_rows * ctx->d * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(allgather_rows(ctx, tmp, ctx->d));
+        CU(cudaMemcpyAsync(phi, tmp, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    double a = 0.0;
+    CU(cudaMemcpyAsync(&a, ctx->a_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (scale_out) *scale_out = a;
+    return SVGDB_OK;
+}
+
+int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
+    CU(cudaSetDevice(ctx->device));
+    TRY(launch_rownorm(ctx));
+    TRY(compute_scale_dev(ctx));
+    double a = 0.0;
+    CU(cudaMemcpyAsync(&a, ctx->a_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (scale_out) *scale_out = a;
+    return SVGDB_OK;
+}
+
+int svgdb_compute_log_model_grad(svgdb_ctx *ctx, double *G)
+{
+    if (!ctx || !G) return fail(ctx, SVGDB_ERR_INVALID, "null output");
+    if (ctx->model_kind == MODEL_UNSET) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
+    CU(cudaSetDevice(ctx->device));
+    TRY(launch_grad(ctx));
+    double *tmp = ctx->V;
+    if (ctx->n_rows > 0)
+        CU(cudaMemcpyAsync(tmp + (size_t)ctx->row0 * ctx->d, ctx->G, (size_t)ctx->n_rows * ctx->d * sizeof(double),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(allgather_rows(ctx, tmp, ctx->d));
+    CU(cudaMemcpyAsync(G, tmp, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+int svgdb_get_opt_state(svgdb_ctx *ctx, double *s1, double *s2, uint64_t *counter)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    // optimizer state is row-sharded; gather through V's storage one array at a time
+    double *src[2] = {ctx->s1, ctx->s2};
+    double *dst[2] = {s1, s2};
+    for (int k = 0; k < 2; ++k) {
+        if (!dst[k]) continue;
+        if (ctx->n_rows > 0)
+            CU(cudaMemcpyAsync(ctx->V + (size_t)ctx->row0 * ctx->d, src[k], (size_t)ctx->n_rows * ctx->d * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(allgather_rows(ctx, ctx->V, ctx->d));
+        CU(cudaMemcpyAsync(dst[k], ctx->V, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (counter) *counter = ctx->counter;
+    return SVGDB_OK;
+}
+
+int svgdb_set_opt_state(svgdb_ctx *ctx, const double *s1, const double *s2, uint64_t counter)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    size_t bytes = (size_t)std::max<int64_t>(ctx->n_rows, 0) * ctx->d * sizeof(double);
+    if (s1 && bytes) CU(cudaMemcpyAsync(ctx->s1, s1 + (size_t)ctx->row0 * ctx->d, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (s2 && bytes) CU(cudaMemcpyAsync(ctx->s2, s2 + (size_t)ctx->row0 * ctx->d, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->counter = counter;
+    return SVGDB_OK;
+}
+
+int svgdb_sync(svgdb_ctx *ctx)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
+int svgdb_set_profiling(svgdb_ctx *ctx, int enabled)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    ctx->profiling = enabled != 0;
+    return SVGDB_OK;
+}
+
+int svgdb_get_stats(svgdb_ctx *ctx, svgdb_stats *out)
+{
+    if (!ctx || !out) return SVGDB_ERR_INVALID;
+    *out = ctx->stats;
+    return SVGDB_OK;
+}
+
+int svgdb_reset_stats(svgdb_ctx *ctx)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    double last = ctx->stats.last_scale;
+    ctx->stats = svgdb_stats{};
+    ctx->stats.last_scale = last;
+    return SVGDB_OK;
+}
+
+int svgdb_time_steps(svgdb_ctx *ctx, int64_t iters, float *ms_out)
+{
+    if (!ctx || !ms_out) return SVGDB_ERR_INVALID;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(e0, ctx->stream));
+    int rc = svgdb_step(ctx, iters);
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int svgdb_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return SVGDB_ERR_INVALID;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? SVGDB_OK : SVGDB_ERR_NOMEM;
+}
+
+int svgdb_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SVGDB_OK : SVGDB_ERR_CUDA; }
+
+int svgdb_probe_peak(int device, int what, double *out)
+{
+    if (!out || what != 0) return SVGDB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SVGDB_ERR_CUDA;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SVGDB_ERR_CUDA;
+    double *sink = nullptr;
+    if (cudaMalloc(&sink, sizeof(double)) != cudaSuccess) return SVGDB_ERR_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, blocks = prop.multiProcessorCount * 4, threads = 256;
+    dmma_probe_kernel<<<blocks, threads>>>(iters, sink); // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dmma_probe_kernel<<<blocks, threads>>>(iters, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); return SVGDB_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // per warp and iteration: 16 independent DMMAs of 8*8*4 MACs
+        double flops = 2.0 * 256.0 * 16.0 * iters * (double)blocks * (threads / 32);
+        best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *out = best;
+    return SVGDB_OK;
+}
+
+} // extern "C"

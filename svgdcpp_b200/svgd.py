@@ -1,0 +1,358 @@
+"""Host-side mirror of the SVGDCpp interface for the accelerated path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference classes so that parity tests read
+like the reference's own programs (examples/multivariate_normal/mvn_example.cpp):
+
+    x0 = 3 * eigen_random(dim, n)                      # dim x n, like Eigen::MatrixXd
+    model = MultivariateNormal(mean, cov)              # Model/MultivariateNormal.hpp:39
+    kernel = GaussianRBFKernel(x0, ScaleMethod.Median, model)   # Kernel/GaussianRBFKernel.hpp:47
+    opt = AdaGrad(dim, n, 1e-1)                        # Optimizer/AdaGrad.hpp:31
+    svgd = SVGD(dim, iters, x0, kernel, model, opt)    # SVGD.hpp:118
+    svgd.Initialize(); svgd.Run()                      # x0 is updated in place (SVGD.hpp:393)
+
+All numerics run in libsvgd_b200.so on the GPU; nothing here computes.  The C++ facade with the
+identical API lives in include/SVGDCpp/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+
+import numpy as np
+
+from . import _capi
+
+_dp = C.POINTER(C.c_double)
+
+
+class DimensionMismatchException(Exception):  # Exceptions.hpp:23-35
+    def __init__(self, message):
+        super().__init__("SVGDCpp: [Dimension Error] " + message)
+
+
+class UnsetException(Exception):  # Exceptions.hpp:38-50
+    def __init__(self, message):
+        super().__init__("SVGDCpp: [Unset Error] " + message)
+
+
+def _raise_for(code, ctx_handle):
+    if code == _capi.OK:
+        return
+    msg = _capi.load().svgdb_last_error(ctx_handle)
+    msg = msg.decode() if msg else "error %d" % code
+    if code == _capi.ERR_DIMENSION:
+        raise DimensionMismatchException(msg)
+    if code == _capi.ERR_UNSET:
+        raise UnsetException(msg)
+    if code == _capi.ERR_INVALID:
+        raise ValueError("SVGDCpp: " + msg)  # std::invalid_argument
+    raise RuntimeError("SVGDCpp: [Runtime Error] " + msg)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+# ---- models -------------------------------------------------------------------------------------
+class Model:
+    """Model base (Model/Model.hpp).  Only sums of MultivariateNormal objects (operator+,
+    Model.hpp:55-92) and device-gradient hooks have a device implementation; an arbitrary taped
+    lambda has none and raises UnsetException at SVGD construction (no CPU fallback)."""
+
+    def __init__(self, dim):
+        self.dimension_ = int(dim)
+        self._components = []   # list of (mean, cov)
+        self._hook = None       # (ctypes callback, user pointer)
+
+    def __add__(self, other):
+        if self.dimension_ != other.dimension_:
+            raise DimensionMismatchException("Only models with the same variable dimensions can be added.")
+        if (not self._components and self._hook is None) or (not other._components and other._hook is None):
+            raise UnsetException("One of the model functions is unset; functional composition requires both model functions to be set.")
+        if self._hook is not None or other._hook is not None:
+            raise UnsetException("device-gradient hooks cannot be composed; only sums of MultivariateNormal are supported on the device")
+        out = Model(self.dimension_)
+        out._components = list(self._components) + list(other._components)
+        return out
+
+    def SetDeviceGradient(self, fn, user=None):
+        """Device hook replacing Model::EvaluateLogModelGrad (Model.hpp:335-338); `fn` is a
+        _capi.GRAD_FN (or a raw function pointer) enqueuing work on the given stream."""
+        self._hook = (fn, user)
+        self._components = []
+
+    def GetParameters(self):
+        out = []
+        for mean, cov in self._components:
+            out += [mean.copy().reshape(-1, 1), cov.copy()]
+        return out
+
+    def Initialize(self):
+        pass
+
+    def Step(self):
+        pass
+
+
+class MultivariateNormal(Model):
+    def __init__(self, mean, covariance):
+        mean = np.asarray(mean, dtype=np.float64).reshape(-1)
+        covariance = np.asarray(covariance, dtype=np.float64)
+        super().__init__(mean.shape[0])
+        if covariance.ndim != 2 or covariance.shape[0] != mean.shape[0] or covariance.shape[1] != mean.shape[0]:
+            raise DimensionMismatchException("Dimensions of parameter vectors/matrices do not match.")
+        self._components = [(mean.copy(), covariance.copy())]
+        self._compute_norm_const()
+
+    def UpdateParameters(self, params):  # MultivariateNormal.hpp:94-115
+        mean = np.asarray(params[0], dtype=np.float64).reshape(-1)
+        covariance = np.asarray(params[1], dtype=np.float64)
+        if covariance.ndim != 2 or covariance.shape[0] != mean.shape[0] or covariance.shape[1] != mean.shape[0]:
+            raise DimensionMismatchException("Dimensions of parameter vectors/matrices do not match each other (# of rows must be equal).")
+        if mean.shape[0] != self.dimension_:
+            raise DimensionMismatchException("Dimensions of parameter vectors/matrices do not match original dimension.")
+        self._components = [(mean.copy(), covariance.copy())]
+        self._compute_norm_const()
+
+    def _compute_norm_const(self):  # MultivariateNormal.hpp:182-186
+        cov = self._components[0][1]
+        with np.errstate(all="ignore"):
+            det = np.float64(np.linalg.det(cov))
+            self.norm_const_ = float(np.float64(1.0) / (np.float64(math.pow(2.0 * math.pi, self.dimension_ / 2.0)) * np.sqrt(det)))
+
+    def GetNormalizationConstant(self):
+        return self.norm_const_
+
+
+# ---- kernel -------------------------------------------------------------------------------------
+class ScaleMethod(enum.IntEnum):  # GaussianRBFKernel.hpp:25-30 (+ a constant scale)
+    Median = 0
+    Hessian = 1
+    Fixed = 2
+
+
+class GaussianRBFKernel:
+    ScaleMethod = ScaleMethod
+
+    def __init__(self, coord_mat, method=ScaleMethod.Median, model=None, fixed_scale=0.0):
+        if method == ScaleMethod.Hessian and model is None:
+            raise UnsetException("Hessian-based scale requires a model.")
+        self.coord_matrix_ = coord_mat
+        self.dimension_ = int(np.asarray(coord_mat).shape[0])
+        self.scale_method_ = ScaleMethod(method)
+        self.fixed_scale_ = float(fixed_scale)
+        self.target_model_ = model
+
+
+# ---- optimizers ---------------------------------------------------------------------------------
+class Optimizer:
+    def __init__(self, lr, epsilon=1.0e-8):
+        self.learning_rate_ = float(lr)
+        self.stabilizer_ = float(epsilon)
+
+
+class Adam(Optimizer):  # Optimizer/Adam.hpp:33-49
+    kind = _capi.OPT_ADAM
+
+    def __init__(self, dimension, num_particles, lr, beta1, beta2, epsilon=1.0e-8):
+        super().__init__(lr, epsilon)
+        if beta1 >= 1.0 or beta1 < 0.0 or beta2 >= 1.0 or beta2 < 0.0:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid value for decay parameter beta.")
+        self.dimension_, self.num_particles_ = int(dimension), int(num_particles)
+        self.decay_rate_1_, self.decay_rate_2_ = float(beta1), float(beta2)
+
+
+class AdaGrad(Optimizer):  # Optimizer/AdaGrad.hpp:31-37
+    kind = _capi.OPT_ADAGRAD
+
+    def __init__(self, dimension, num_particles, lr, epsilon=1.0e-8):
+        super().__init__(lr, epsilon)
+        self.dimension_, self.num_particles_ = int(dimension), int(num_particles)
+        self.decay_rate_1_ = self.decay_rate_2_ = 0.0
+
+
+class RMSProp(Optimizer):  # Optimizer/RMSProp.hpp:33-46
+    kind = _capi.OPT_RMSPROP
+
+    def __init__(self, dimension, num_particles, lr, beta, epsilon=1.0e-8):
+        super().__init__(lr, epsilon)
+        if beta > 1.0 or beta < 0.0:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid value for decay parameter beta.")
+        self.dimension_, self.num_particles_ = int(dimension), int(num_particles)
+        self.decay_rate_1_, self.decay_rate_2_ = float(beta), 0.0
+
+
+# ---- driver -------------------------------------------------------------------------------------
+class SVGDOptions:  # SVGD.hpp:27-52 (+ device / precision / sharding fields with defaults)
+    def __init__(self):
+        self.Dimension = 0
+        self.NumIterations = 0
+        self.CoordinateMatrixPtr = None
+        self.KernelPtr = None
+        self.ModelPtr = None
+        self.OptimizerPtr = None
+        self.LowerBound = np.array([-np.inf])
+        self.UpperBound = np.array([np.inf])
+        self.IntermediateMatricesOutputPath = "log.txt"
+        self.Parallel = False
+        self.LogIntermediateMatrices = False
+        self.Device = 0
+        self.Precision = _capi.PRECISION_F64
+
+
+class SVGD:
+    """SVGD driver (SVGD.hpp:84-511).  `coord_mat` is the dim x n particle matrix, updated in place
+    by Run()/Step() exactly like the reference's shared Eigen::MatrixXd."""
+
+    def __init__(self, dim, iter=None, coord_mat=None, kernel=None, model=None, optimizer=None,
+                 bound_lower=None, bound_upper=None, parallel=False, log_intermediate_matrices=False,
+                 intermediate_matrices_output_path="log.txt", device=0, precision=_capi.PRECISION_F64):
+        if isinstance(dim, SVGDOptions):
+            o = dim
+            dim, iter, coord_mat, kernel, model, optimizer = (o.Dimension, o.NumIterations, o.CoordinateMatrixPtr,
+                                                              o.KernelPtr, o.ModelPtr, o.OptimizerPtr)
+            bound_lower, bound_upper, parallel = o.LowerBound, o.UpperBound, o.Parallel
+            log_intermediate_matrices, intermediate_matrices_output_path = o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath
+            device, precision = o.Device, o.Precision
+        self._lib = _capi.load()
+        self._ctx = C.c_void_p()
+        if coord_mat is None:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid coordinate matrix pointer.")
+        self.coord_matrix_ = coord_mat
+        self.dimension_ = int(coord_mat.shape[0])
+        self.num_particles_ = int(coord_mat.shape[1])
+        self.num_iterations_ = int(iter)
+        self.parallel_ = bool(parallel)  # accepted for source compatibility; the GPU path is always parallel
+        if self.dimension_ != int(dim):
+            raise DimensionMismatchException("Specified dimension does not match the particle coordinate matrix.")
+        lb = np.asarray(bound_lower if bound_lower is not None else [-np.inf], dtype=np.float64).reshape(-1)
+        ub = np.asarray(bound_upper if bound_upper is not None else [np.inf], dtype=np.float64).reshape(-1)
+        self.check_bounds_ = not (lb.size == 1 and ub.size == 1 and lb[0] == -np.inf and ub[0] == np.inf)
+        if self.check_bounds_:
+            if lb.size not in (1, self.dimension_):
+                raise DimensionMismatchException("The provided lower bounds have incorrect dimensions.")
+            if ub.size not in (1, self.dimension_):
+                raise DimensionMismatchException("The provided upper bounds have incorrect dimensions.")
+        if kernel is None:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid Kernel object pointer.")
+        if model is None:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid Model object pointer.")
+        if optimizer is None:
+            raise ValueError("SVGDCpp: [Argument Error] Invalid Optimizer object pointer.")
+        if log_intermediate_matrices:
+            raise NotImplementedError("LogIntermediateMatrices: K and grad K are never materialised on the device path")
+        self.kernel_, self.model_, self.optimizer_ = kernel, model, optimizer
+
+        rc = self._lib.svgdb_create(C.byref(self._ctx), int(device), self.num_particles_, self.dimension_, int(precision))
+        self._check(rc)
+        if self.check_bounds_:
+            lbf = np.ascontiguousarray(np.broadcast_to(lb, (self.dimension_,)) if lb.size == 1 else lb)
+            ubf = np.ascontiguousarray(np.broadcast_to(ub, (self.dimension_,)) if ub.size == 1 else ub)
+            self._check(self._lib.svgdb_set_bounds(self._ctx, _ptr(lbf), _ptr(ubf), self.dimension_))
+        self._push_model()
+        self._push_kernel()
+        o = optimizer
+        self._check(self._lib.svgdb_set_optimizer(self._ctx, o.kind, o.learning_rate_, o.decay_rate_1_, o.decay_rate_2_, o.stabilizer_))
+        self._host = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
+        self._dirty_host = True
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != _capi.OK:
+            try:
+                _raise_for(rc, self._ctx)
+            finally:
+                pass
+
+    def _push_model(self):
+        m = self.model_
+        if m._hook is not None:
+            fn, user = m._hook
+            self._hook_keepalive = fn
+            self._check(self._lib.svgdb_set_model_device_hook(self._ctx, C.cast(fn, C.c_void_p), user))
+            return
+        if not m._components:
+            raise UnsetException("Model function is unset.")
+        means = np.ascontiguousarray(np.stack([c[0] for c in m._components]))          # C x d
+        covs = np.ascontiguousarray(np.stack([c[1] for c in m._components]))           # C x d x d
+        if means.shape[1] != self.dimension_:
+            raise DimensionMismatchException("Model dimension does not match the particle coordinate matrix.")
+        self._check(self._lib.svgdb_set_model_mvn_sum(self._ctx, means.shape[0], _ptr(means), _ptr(covs)))
+
+    def _push_kernel(self):
+        k = self.kernel_
+        if k.dimension_ != self.dimension_:
+            raise DimensionMismatchException("Kernel dimension does not match the particle coordinate matrix.")
+        self._check(self._lib.svgdb_set_kernel_rbf(self._ctx, int(k.scale_method_), k.fixed_scale_))
+
+    def _upload(self):
+        self._host[...] = np.asarray(self.coord_matrix_, dtype=np.float64).T
+        self._check(self._lib.svgdb_set_particles(self._ctx, _ptr(self._host)))
+
+    def _download(self):
+        self._check(self._lib.svgdb_get_particles(self._ctx, _ptr(self._host)))
+        self.coord_matrix_[...] = self._host.T
+
+    # -- reference API ---------------------------------------------------------------------------
+    def Initialize(self):  # SVGD.hpp:268-296
+        self.model_.Initialize()
+        self._check(self._lib.svgdb_initialize(self._ctx))
+
+    def UpdateKernelParameters(self, params):  # SVGD.hpp:304-321: params[0] = A = a I
+        A = np.asarray(params[0], dtype=np.float64)
+        self.kernel_.scale_method_ = ScaleMethod.Fixed
+        self.kernel_.fixed_scale_ = float(A[0, 0]) if A.ndim == 2 else float(A)
+        self._push_kernel()
+
+    def UpdateModelParameters(self, params):  # SVGD.hpp:328-332
+        self.model_.UpdateParameters(params)
+        self._push_model()
+
+    def Step(self, iters=1):  # SVGD.hpp:373-400 (protected there; public here)
+        self._upload()
+        self._check(self._lib.svgdb_step(self._ctx, int(iters)))
+        self._download()
+
+    def Run(self):  # SVGD.hpp:338-366
+        self.Step(self.num_iterations_)
+
+    # -- extras used by tests / bench ---------------------------------------------------------------
+    def ComputePhi(self):
+        """SVGD::ComputePhi (SVGD.hpp:407-454) on the current coordinates: (phi as dim x n, scale a)."""
+        self._upload()
+        phi = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
+        a = C.c_double(0.0)
+        self._check(self._lib.svgdb_compute_phi(self._ctx, _ptr(phi), C.byref(a)))
+        return phi.T.copy(), a.value
+
+    def ComputeScale(self):
+        self._upload()
+        a = C.c_double(0.0)
+        self._check(self._lib.svgdb_compute_scale(self._ctx, C.byref(a)))
+        return a.value
+
+    def EvaluateLogModelGrad(self):
+        self._upload()
+        G = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
+        self._check(self._lib.svgdb_compute_log_model_grad(self._ctx, _ptr(G)))
+        return G.T.copy()
+
+    def Stats(self):
+        st = _capi.Stats()
+        self._check(self._lib.svgdb_get_stats(self._ctx, C.byref(st)))
+        return {name: getattr(st, name) for name, _ in st._fields_}
+
+    def context(self):
+        return self._ctx
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.svgdb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

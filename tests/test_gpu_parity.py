@@ -1,0 +1,269 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the CPU oracle on identical seeded inputs, plus the reference's published example outputs.
+
+Tolerances (FP64 mode): per-step phi and kernel scale <= 1e-11 relative; final particles after the
+configured iteration count within 1e-9 of max|X|."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_matches_printed, load_golden
+
+pytestmark = pytest.mark.gpu
+
+PHI_RTOL = 1e-11
+FINAL_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def sv():
+    import svgdcpp_b200
+
+    svgdcpp_b200._capi.load()  # fails loudly if the CUDA extension is missing
+    return svgdcpp_b200
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _example(sv, oracle, g, precision=0):
+    n, d = g["num_particles"], g["dim"]
+    x0 = oracle.eigen_random(d, n, g["x0_scale"], reseed=True, seed=1).T.copy()  # dim x n
+    model = None
+    for mu, cov in zip(g["means"], g["covs"]):
+        m = sv.MultivariateNormal(mu, cov)
+        model = m if model is None else model + m
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+    o = g["optimizer"]
+    opt = sv.AdaGrad(d, n, o["lr"]) if o["kind"] == "adagrad" else sv.Adam(d, n, o["lr"], o["beta1"], o["beta2"])
+    svgd = sv.SVGD(d, g["num_iterations"], x0, kernel, model, opt, precision=precision)
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    return x0
+
+
+@pytest.mark.parametrize("name", ["mvn_example", "gmm_example"])
+def test_reference_examples_reproduced_on_gpu(sv, oracle, name):
+    """mvn_example.cpp / gmm_example.cpp through the mirrored API: every printed digit of the
+    reference's published final coordinates, and 1e-9 agreement with the oracle."""
+    g = load_golden(name)
+    xf = _example(sv, oracle, g)
+    assert_matches_printed(xf.T, g["final"])
+    x0 = oracle.eigen_random(g["dim"], g["num_particles"], g["x0_scale"], reseed=True, seed=1)
+    o = g["optimizer"]
+    kind = oracle.OPT_ADAGRAD if o["kind"] == "adagrad" else oracle.OPT_ADAM
+    ref = oracle.svgd_run(x0, g["num_iterations"], g["means"], g["covs"], opt_kind=kind, lr=o["lr"],
+                          beta1=o.get("beta1", 0.0), beta2=o.get("beta2", 0.0), eps=o["eps"])
+    assert _rel(xf.T, ref) < FINAL_RTOL
+
+
+def _mvn_setup(sv, n, d, seed=0, opt="adam", iters=1, **kw):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + 0.5 * np.eye(d)
+    mu = rng.standard_normal(d)
+    x0 = np.asfortranarray(2.0 * rng.standard_normal((d, n)))
+    model = sv.MultivariateNormal(mu, cov)
+    kernel = sv.GaussianRBFKernel(x0, kw.pop("scale", sv.ScaleMethod.Median), model, fixed_scale=kw.pop("fixed_scale", 0.0))
+    optimizer = {"adam": lambda: sv.Adam(d, n, 0.1, 0.9, 0.999), "adagrad": lambda: sv.AdaGrad(d, n, 0.1),
+                 "rmsprop": lambda: sv.RMSProp(d, n, 0.05, 0.9)}[opt]()
+    svgd = sv.SVGD(d, iters, x0, kernel, model, optimizer, **kw)
+    return svgd, x0, mu[None], cov[None]
+
+
+@pytest.mark.parametrize("n,d", [(1, 3), (2, 2), (10, 2), (63, 1), (64, 8), (65, 5), (200, 17), (300, 64), (257, 100), (130, 130), (96, 200)])
+def test_phi_scale_and_grad_match_oracle(sv, oracle, n, d):
+    """One ComputePhi (SVGD.hpp:407-454) on ragged / tiny / multi-chunk shapes."""
+    svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=n * 1000 + d)
+    X = np.ascontiguousarray(x0.T)
+    G = svgd.EvaluateLogModelGrad().T
+    G_ref = oracle.mvn_sum_logp_grad(X, mu, cov)
+    assert _rel(G, G_ref) < 1e-12
+    if n == 1:
+        svgd.close()
+        return  # median of a single zero distance: a = log(1)/0 -> NaN in the reference as well
+    phi, a = svgd.ComputePhi()
+    a_ref = oracle.rbf_median_scale(X)
+    assert abs(a - a_ref) <= 1e-12 * a_ref
+    phi_ref = oracle.phi(X, G_ref, a_ref)
+    assert _rel(phi.T, phi_ref) < PHI_RTOL
+    svgd.close()
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "rmsprop"])
+def test_trajectory_matches_oracle(sv, oracle, opt):
+    n, d, iters = 256, 64, 25
+    svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=7, opt=opt, iters=iters)
+    X0 = np.ascontiguousarray(x0.T)
+    svgd.Initialize()
+    svgd.Run()
+    kind = {"adam": oracle.OPT_ADAM, "adagrad": oracle.OPT_ADAGRAD, "rmsprop": oracle.OPT_RMSPROP}[opt]
+    lr = 0.05 if opt == "rmsprop" else 0.1
+    ref = oracle.svgd_run(X0, iters, mu, cov, opt_kind=kind, lr=lr, beta1=0.9, beta2=0.999 if opt == "adam" else 0.0)
+    assert _rel(x0.T, ref) < FINAL_RTOL
+    st = svgd.Stats()
+    assert st["iterations"] == iters and st["kernel_launches"] > 0
+    svgd.close()
+
+
+def test_run_is_resumable_and_in_place(sv, oracle):
+    """Two Run() calls of k iterations equal one of 2k (state stays on the device between calls,
+    x0 is updated in place like the reference's shared coordinate matrix, SVGD.hpp:393)."""
+    n, d = 100, 6
+    svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=11, iters=5)
+    X0 = np.ascontiguousarray(x0.T)
+    svgd.Initialize()
+    svgd.Run()
+    svgd.Run()
+    ref = oracle.svgd_run(X0, 10, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
+    assert _rel(x0.T, ref) < FINAL_RTOL
+    svgd.Initialize()  # zeroes the optimizer state again (Adam.hpp:61-67)
+    X1 = np.ascontiguousarray(x0.T)
+    svgd.Run()
+    ref2 = oracle.svgd_run(X1, 5, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
+    assert _rel(x0.T, ref2) < FINAL_RTOL
+    svgd.close()
+
+
+def test_bounds_and_fixed_scale(sv, oracle):
+    """Fixed-bandwidth kernel + box clamp (the tests/test_svgd.cpp configuration, with an MVN target)."""
+    n, d, iters = 40, 2, 15
+    svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=3, iters=iters, scale=sv.ScaleMethod.Fixed, fixed_scale=1.0,
+                                   bound_lower=[-1.0, -0.5], bound_upper=[1.0, 0.75])
+    X0 = np.ascontiguousarray(x0.T)
+    svgd.Initialize()
+    svgd.Run()
+    ref = oracle.svgd_run(X0, iters, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1, scale_method=oracle.SCALE_FIXED, fixed_a=1.0,
+                          lb=[-1.0, -0.5], ub=[1.0, 0.75])
+    assert np.max(x0[0]) <= 1.0 and np.min(x0[0]) >= -1.0 and np.max(x0[1]) <= 0.75 and np.min(x0[1]) >= -0.5
+    assert np.sum(x0[0] == 1.0) + np.sum(x0[0] == -1.0) > 0  # the clamp is active
+    assert _rel(x0.T, ref) < FINAL_RTOL
+    svgd.close()
+
+
+def test_mixture_gradient_log_sum_exp(sv, oracle):
+    """16-D, 5-component sum of Gaussians incl. far-away components (config-4 style)."""
+    from svgdcpp_b200 import synth
+
+    n, d, C = 333, 16, 5
+    x0, means, covs = synth.gmm_problem(n, d, C)
+    model = None
+    for k in range(C):
+        m = sv.MultivariateNormal(means[k], covs[k])
+        model = m if model is None else model + m
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+    svgd = sv.SVGD(d, 10, x0, kernel, model, sv.AdaGrad(d, n, 0.1))
+    X0 = np.ascontiguousarray(x0.T)
+    G = svgd.EvaluateLogModelGrad().T
+    G_ref = oracle.mvn_sum_logp_grad(X0, means, covs, lse=True)
+    assert _rel(G, G_ref) < 1e-12
+    svgd.Initialize()
+    svgd.Run()
+    ref = oracle.svgd_run(X0, 10, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+    assert _rel(x0.T, ref) < FINAL_RTOL
+    svgd.close()
+
+
+def test_mixture_finite_where_reference_underflows(sv):
+    """Every exp(-q/2) underflows in double: the reference's log(sum exp) is NaN;
+    the device path evaluates the same gradient through log-sum-exp and stays finite."""
+    d = 4
+    x0 = np.asfortranarray(np.full((d, 8), 60.0) + np.arange(8)[None, :])
+    model = sv.MultivariateNormal(np.zeros(d), np.eye(d)) + sv.MultivariateNormal(np.ones(d), np.eye(d))
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+    svgd = sv.SVGD(d, 1, x0, kernel, model, sv.AdaGrad(d, 8, 0.1))
+    G = svgd.EvaluateLogModelGrad()
+    assert np.all(np.isfinite(G))
+    # dominated by the nearer component (mean 1): grad ~ -(x - 1)
+    assert np.allclose(G, -(x0 - 1.0), rtol=1e-9)
+    svgd.close()
+
+
+@pytest.mark.parametrize("capacity", [64, 1000])
+def test_median_select_narrowing_paths(sv, oracle, capacity, monkeypatch):
+    """Tiny candidate buffers force the histogram-narrowing passes, the bracket prediction and the
+    tie handling of the exact on-device select (GaussianRBFKernel.hpp:222-254 semantics)."""
+    monkeypatch.setenv("SVGDB_CAND_CAPACITY", str(capacity))
+    rng = np.random.default_rng(5)
+    for n, d in [(90, 3), (151, 64), (64, 2)]:
+        svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=n)
+        X = np.ascontiguousarray(x0.T)
+        a = svgd.ComputeScale()
+        a_ref = oracle.rbf_median_scale(X)
+        assert abs(a - a_ref) <= 1e-12 * a_ref, (n, d)
+        # several steps: the predicted-bracket path must keep agreeing with the oracle
+        svgd.Initialize()
+        svgd.Step(6)
+        ref = oracle.svgd_run(X, 6, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
+        assert _rel(x0.T, ref) < FINAL_RTOL
+        assert svgd.Stats()["median_passes"] >= 6
+        svgd.close()
+    # heavy ties: many duplicated particles (more equal distances than the buffer holds)
+    n, d = 80, 3
+    base = rng.standard_normal((4, d))
+    X = np.ascontiguousarray(base[rng.integers(0, 4, n)])
+    x0 = np.asfortranarray(X.T)
+    model = sv.MultivariateNormal(np.zeros(d), np.eye(d))
+    svgd = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1))
+    D = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1))
+    med = np.median(D.ravel())
+    a = svgd.ComputeScale()
+    if med > 0:
+        assert abs(a - np.log(n) / med ** 2) <= 1e-10 * a
+    else:
+        assert np.isinf(a)
+    svgd.close()
+
+
+def test_error_mapping(sv):
+    x0 = np.zeros((3, 5), order="F")
+    model = sv.MultivariateNormal(np.zeros(3), np.eye(3))
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+    with pytest.raises(sv.DimensionMismatchException):
+        sv.SVGD(2, 1, x0, kernel, model, sv.AdaGrad(3, 5, 0.1))
+    with pytest.raises(sv.DimensionMismatchException):
+        sv.SVGD(3, 1, x0, kernel, model, sv.AdaGrad(3, 5, 0.1), bound_lower=[0.0, 0.0], bound_upper=[1.0, 1.0])
+    with pytest.raises(ValueError):
+        sv.SVGD(3, 1, x0, None, model, sv.AdaGrad(3, 5, 0.1))
+    with pytest.raises(ValueError):
+        sv.Adam(3, 5, 0.1, 1.0, 0.999)
+    with pytest.raises(sv.UnsetException):
+        sv.SVGD(3, 1, x0, kernel, sv.Model(3), sv.AdaGrad(3, 5, 0.1))
+    with pytest.raises(RuntimeError):  # singular covariance
+        sv.SVGD(3, 1, x0, kernel, sv.MultivariateNormal(np.zeros(3), np.zeros((3, 3))), sv.AdaGrad(3, 5, 0.1))
+
+
+def test_full_size_properties(sv):
+    """BASELINE config 3 (N=65,536, d=64): size-independent checks where the oracle cannot run.
+    (1) sampled rows of phi recomputed in O(N d) on the host from the device's own scale;
+    (2) the scale is log(N)/med^2 with about half of sampled distances below med."""
+    from svgdcpp_b200 import synth
+
+    n, d = 65536, 64
+    x0, means, covs = synth.mvn_problem(n, d)
+    model = sv.MultivariateNormal(means[0], covs[0])
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+    svgd = sv.SVGD(d, 1, x0, kernel, model, sv.Adam(d, n, 0.1, 0.9, 0.999))
+    X = np.ascontiguousarray(x0.T)
+    phi, a = svgd.ComputePhi()
+    G = -(X - means[0]) @ np.linalg.inv(covs[0])
+    rows = np.random.default_rng(0).integers(0, n, 12)
+    frac = []
+    med = np.sqrt(np.log(n) / a)
+    for i in rows:
+        d2 = ((X - X[i]) ** 2).sum(1)
+        k = np.exp(-a * d2)
+        ref = (k @ G + (-2 * a * (X - X[i]) * k[:, None]).sum(0)) / n
+        assert np.max(np.abs(phi[:, i] - ref)) <= 1e-10 * np.max(np.abs(ref))
+        frac.append(np.mean(np.sqrt(d2) < med))
+    assert abs(np.mean(frac) - 0.5) < 0.05
+    # one full step moves every particle by at most lr (Adam's first step is lr * sign(phi))
+    before = x0.copy()
+    svgd.Initialize()
+    svgd.Step(1)
+    step = np.abs(x0 - before)
+    assert np.all(np.isfinite(x0)) and np.max(step) <= 0.1 * (1 + 1e-6) and np.mean(step) > 0.05
+    svgd.close()
