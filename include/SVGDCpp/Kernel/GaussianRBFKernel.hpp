@@ -1,0 +1,51 @@
+/* GaussianRBFKernel.hpp — k(x, x') = exp(-(x-x')^T A (x-x')), A = a I
+ * (reference Kernel/GaussianRBFKernel.hpp:47-88).  ScaleMethod::Median recomputes
+ * a = log(n) / median(|x_i - x_j|)^2 from the current particles at every Step (:141-188); on the
+ * device that is an exact radix select over all n^2 distances (svgdcpp_b200/csrc/select.cuh). */
+#ifndef SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
+#define SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
+
+#include "../Model/Model.hpp"
+#include "Kernel.hpp"
+
+class GaussianRBFKernel : public Kernel {
+public:
+    enum class ScaleMethod {
+        Median = 0,
+        Hessian = 1,
+        Constant = 2 /* the reference's "TODO: constant scale"; value given by UpdateParameters({A}) */
+    };
+
+    GaussianRBFKernel() {}
+    GaussianRBFKernel(const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const ScaleMethod &method = ScaleMethod::Median,
+                      const std::shared_ptr<Model> &model_ptr = nullptr)
+        : Kernel(static_cast<size_t>(coord_mat_ptr->rows())), scale_method_(method), coord_matrix_ptr_(coord_mat_ptr), target_model_ptr_(model_ptr)
+    {
+        if (scale_method_ == ScaleMethod::Hessian && !model_ptr) throw UnsetException("Hessian-based scale requires a model.");
+    }
+
+    /* UpdateParameters({A}) fixes the scale to A(0,0) (A = a I), like SVGD::UpdateKernelParameters. */
+    void UpdateParameters(const std::vector<Eigen::MatrixXd> &params) override
+    {
+        Kernel::UpdateParameters(params);
+        if (!params.empty() && params[0].size() > 0) {
+            fixed_scale_ = params[0](0, 0);
+            scale_method_ = ScaleMethod::Constant;
+        }
+    }
+
+    std::unique_ptr<Kernel> CloneUniquePointer() const override { return std::make_unique<GaussianRBFKernel>(*this); }
+    std::shared_ptr<Kernel> CloneSharedPointer() const override { return std::make_shared<GaussianRBFKernel>(*this); }
+
+    void Upload(svgdb_ctx *ctx) const override
+    {
+        svgdcpp_b200::ThrowOnError(svgdb_set_kernel_rbf(ctx, static_cast<int>(scale_method_), fixed_scale_), svgdb_last_error(ctx));
+    }
+
+protected:
+    ScaleMethod scale_method_ = ScaleMethod::Median;
+    double fixed_scale_ = 0.0;
+    std::shared_ptr<Eigen::MatrixXd> coord_matrix_ptr_;
+    std::shared_ptr<Model> target_model_ptr_;
+};
+#endif

@@ -1,0 +1,166 @@
+/* SVGD.hpp — the SVGD driver of the facade (reference SVGD.hpp:27-52 SVGDOptions, :84-511 SVGD).
+ *
+ * Same constructors, Initialize(), Run(), UpdateKernelParameters(), UpdateModelParameters(); Step()
+ * is public here (protected in the reference, :368-373).  The body of Step() is one call into the
+ * C ABI: median bandwidth, grad log p, the N x N interaction, the optimizer update and the bound
+ * clamp all run on the GPU; the shared coordinate matrix is refreshed in place when Run()/Step()
+ * return, keeping the reference's in-place contract (:393). */
+#ifndef SVGDCPP_B200_SVGD_HPP
+#define SVGDCPP_B200_SVGD_HPP
+
+#include <cmath>
+
+#include "Core.hpp"
+#include "Kernel/Kernel.hpp"
+#include "Model/Model.hpp"
+#include "Optimizer/Optimizer.hpp"
+
+struct SVGDOptions {
+    size_t Dimension = 0;
+    size_t NumIterations = 0;
+    std::shared_ptr<Eigen::MatrixXd> CoordinateMatrixPtr = nullptr;
+    std::shared_ptr<Kernel> KernelPtr = nullptr;
+    std::shared_ptr<Model> ModelPtr = nullptr;
+    std::shared_ptr<Optimizer> OptimizerPtr = nullptr;
+    Eigen::VectorXd LowerBound = Eigen::VectorXd::Constant(1, -INFINITY);
+    Eigen::VectorXd UpperBound = Eigen::VectorXd::Constant(1, INFINITY);
+    std::string IntermediateMatricesOutputPath = "log.txt";
+    bool Parallel = false;               /* accepted; the device path is always parallel */
+    bool LogIntermediateMatrices = false; /* K and grad K are never materialised: not supported */
+    int Device = 0;                                  /* CUDA device ordinal */
+    int PrecisionMode = SVGDB_PRECISION_F64;         /* svgdb_precision */
+    SVGDOptions() {}
+};
+
+class SVGD {
+public:
+    SVGD(const SVGDOptions &o)
+        : SVGD(o.Dimension, o.NumIterations, o.CoordinateMatrixPtr, o.KernelPtr, o.ModelPtr, o.OptimizerPtr, o.LowerBound, o.UpperBound,
+               o.Parallel, o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath, o.Device, o.PrecisionMode) {}
+
+    SVGD(const size_t &dim, const size_t &iter, const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const std::shared_ptr<Kernel> &kernel_ptr,
+         const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const bool &parallel = false)
+        : SVGD(dim, iter, coord_mat_ptr, kernel_ptr, model_ptr, optimizer_ptr, Eigen::VectorXd::Constant(1, -INFINITY),
+               Eigen::VectorXd::Constant(1, INFINITY), parallel) {}
+
+    SVGD(const size_t &dim, const size_t &iter, const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const std::shared_ptr<Kernel> &kernel_ptr,
+         const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const Eigen::VectorXd &bound_lower,
+         const Eigen::VectorXd &bound_upper, const bool &parallel = false, const bool &log_intermediate_matrices = false,
+         const std::string &intermediate_matrices_output_path = "log.txt", int device = 0, int precision_mode = SVGDB_PRECISION_F64)
+        : num_iterations_(iter), parallel_(parallel)
+    {
+        (void)intermediate_matrices_output_path;
+        if (!coord_mat_ptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid coordinate matrix pointer.");
+        dimension_ = static_cast<int>(coord_mat_ptr->rows());
+        if (dimension_ != static_cast<int>(dim))
+            throw DimensionMismatchException("Specified dimension does not match the particle coordinate matrix.");
+        coord_matrix_ptr_ = coord_mat_ptr;
+
+        const bool default_bounds = bound_lower.rows() == 1 && bound_upper.rows() == 1 && bound_lower(0) == -INFINITY && bound_upper(0) == INFINITY;
+        check_bounds_ = !default_bounds;
+        if (check_bounds_) {
+            if (bound_lower.rows() != dimension_ && bound_lower.rows() != 1)
+                throw DimensionMismatchException("The provided lower bounds have incorrect dimensions.");
+            std::cout << SVGDCPP_LOG_PREFIX + "Bound checking enabled, lower bound set to " << bound_lower.transpose() << "." << std::endl;
+            if (bound_upper.rows() != dimension_ && bound_upper.rows() != 1)
+                throw DimensionMismatchException("The provided upper bounds have incorrect dimensions.");
+            std::cout << SVGDCPP_LOG_PREFIX + "Bound checking enabled, upper bound set to " << bound_upper.transpose() << "." << std::endl;
+        }
+        kernel_ptr_ = kernel_ptr;
+        model_ptr_ = model_ptr;
+        optimizer_ptr_ = optimizer_ptr;
+        if (kernel_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Kernel object pointer.");
+        if (model_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Model object pointer.");
+        if (optimizer_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Optimizer object pointer.");
+        if (log_intermediate_matrices)
+            throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] LogIntermediateMatrices needs the n x n kernel matrices, which the device path never forms.");
+
+        int rc = svgdb_create(&ctx_, device, static_cast<int64_t>(coord_matrix_ptr_->cols()), dimension_, precision_mode);
+        if (rc != SVGDB_OK) {
+            std::string msg = ctx_ ? svgdb_last_error(ctx_) : "svgdb_create failed";
+            svgdb_destroy(ctx_);
+            ctx_ = nullptr;
+            svgdcpp_b200::ThrowOnError(rc, msg.c_str());
+        }
+        try {
+            if (check_bounds_) {
+                // a 1-row bound is replicated over every coordinate (reference replicate(1, n), :203,215)
+                const int nb_l = static_cast<int>(bound_lower.rows()), nb_u = static_cast<int>(bound_upper.rows());
+                std::vector<double> lb(dimension_), ub(dimension_);
+                for (int k = 0; k < dimension_; ++k) { lb[k] = bound_lower(nb_l == 1 ? 0 : k); ub[k] = bound_upper(nb_u == 1 ? 0 : k); }
+                Check(svgdb_set_bounds(ctx_, lb.data(), ub.data(), dimension_));
+            }
+            if (model_ptr_->Dimension() != dimension_) throw DimensionMismatchException("Model dimension does not match the particle coordinate matrix.");
+            model_ptr_->Upload(ctx_);
+            kernel_ptr_->Upload(ctx_);
+            optimizer_ptr_->Upload(ctx_);
+        } catch (...) {
+            svgdb_destroy(ctx_);
+            ctx_ = nullptr;
+            throw;
+        }
+        if (parallel_) std::cout << SVGDCPP_LOG_PREFIX << "device path: all particle pairs run in parallel on the GPU." << std::endl;
+    }
+
+    SVGD(const SVGD &) = delete;
+    SVGD &operator=(const SVGD &) = delete;
+    ~SVGD() { svgdb_destroy(ctx_); }
+
+    void Initialize()
+    {
+        model_ptr_->Initialize();
+        kernel_ptr_->Initialize();
+        optimizer_ptr_->Initialize();
+        Check(svgdb_initialize(ctx_));
+    }
+
+    void UpdateKernelParameters(const std::vector<Eigen::MatrixXd> &params)
+    {
+        kernel_ptr_->UpdateParameters(params);
+        kernel_ptr_->Initialize();
+        kernel_ptr_->Upload(ctx_);
+    }
+
+    void UpdateModelParameters(const std::vector<Eigen::MatrixXd> &params)
+    {
+        model_ptr_->UpdateParameters(params);
+        model_ptr_->Initialize();
+        model_ptr_->Upload(ctx_);
+    }
+
+    void Run() { Step(num_iterations_); }
+
+    /* `iters` SVGD steps on the device; the coordinate matrix is read before and written after. */
+    void Step(size_t iters = 1)
+    {
+        model_ptr_->Step();
+        Check(svgdb_set_particles(ctx_, coord_matrix_ptr_->data()));
+        Check(svgdb_step(ctx_, static_cast<int64_t>(iters)));
+        Check(svgdb_get_particles(ctx_, coord_matrix_ptr_->data()));
+    }
+
+    /* ComputePhi of the reference (:407-454) for inspection: phi is dim x n. */
+    Eigen::MatrixXd ComputePhi(double *scale_out = nullptr)
+    {
+        Eigen::MatrixXd phi(dimension_, coord_matrix_ptr_->cols());
+        Check(svgdb_set_particles(ctx_, coord_matrix_ptr_->data()));
+        Check(svgdb_compute_phi(ctx_, phi.data(), scale_out));
+        return phi;
+    }
+
+    svgdb_ctx *Context() { return ctx_; }
+
+protected:
+    void Check(int rc) { svgdcpp_b200::ThrowOnError(rc, svgdb_last_error(ctx_)); }
+
+    int dimension_ = -1;
+    size_t num_iterations_;
+    const bool parallel_ = false;
+    bool check_bounds_ = false;
+    std::shared_ptr<Kernel> kernel_ptr_;
+    std::shared_ptr<Model> model_ptr_;
+    std::shared_ptr<Optimizer> optimizer_ptr_;
+    std::shared_ptr<Eigen::MatrixXd> coord_matrix_ptr_;
+    svgdb_ctx *ctx_ = nullptr;
+};
+#endif

@@ -702,7 +702,7 @@ int svgdb_set_particles(svgdb_ctx *ctx, const double *X)
 {
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
     CU(cudaMemcpyAsync(ctx->X[ctx->cur], X, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->have_pred = false;
+    // the median bracket prediction is only a hint (verified by exact counts), so it survives re-uploads
     return SVGDB_OK;
 }
 

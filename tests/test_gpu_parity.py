@@ -78,7 +78,7 @@ def _mvn_setup(sv, n, d, seed=0, opt="adam", iters=1, **kw):
 def test_phi_scale_and_grad_match_oracle(sv, oracle, n, d):
     """One ComputePhi (SVGD.hpp:407-454) on ragged / tiny / multi-chunk shapes."""
     svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=n * 1000 + d)
-    X = np.ascontiguousarray(x0.T)
+    X = np.array(x0.T, order="C", copy=True)
     G = svgd.EvaluateLogModelGrad().T
     G_ref = oracle.mvn_sum_logp_grad(X, mu, cov)
     assert _rel(G, G_ref) < 1e-12
@@ -97,7 +97,7 @@ def test_phi_scale_and_grad_match_oracle(sv, oracle, n, d):
 def test_trajectory_matches_oracle(sv, oracle, opt):
     n, d, iters = 256, 64, 25
     svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=7, opt=opt, iters=iters)
-    X0 = np.ascontiguousarray(x0.T)
+    X0 = np.array(x0.T, order="C", copy=True)
     svgd.Initialize()
     svgd.Run()
     kind = {"adam": oracle.OPT_ADAM, "adagrad": oracle.OPT_ADAGRAD, "rmsprop": oracle.OPT_RMSPROP}[opt]
@@ -114,14 +114,14 @@ def test_run_is_resumable_and_in_place(sv, oracle):
     x0 is updated in place like the reference's shared coordinate matrix, SVGD.hpp:393)."""
     n, d = 100, 6
     svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=11, iters=5)
-    X0 = np.ascontiguousarray(x0.T)
+    X0 = np.array(x0.T, order="C", copy=True)
     svgd.Initialize()
     svgd.Run()
     svgd.Run()
     ref = oracle.svgd_run(X0, 10, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
     assert _rel(x0.T, ref) < FINAL_RTOL
     svgd.Initialize()  # zeroes the optimizer state again (Adam.hpp:61-67)
-    X1 = np.ascontiguousarray(x0.T)
+    X1 = np.array(x0.T, order="C", copy=True)
     svgd.Run()
     ref2 = oracle.svgd_run(X1, 5, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
     assert _rel(x0.T, ref2) < FINAL_RTOL
@@ -133,7 +133,7 @@ def test_bounds_and_fixed_scale(sv, oracle):
     n, d, iters = 40, 2, 15
     svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=3, iters=iters, scale=sv.ScaleMethod.Fixed, fixed_scale=1.0,
                                    bound_lower=[-1.0, -0.5], bound_upper=[1.0, 0.75])
-    X0 = np.ascontiguousarray(x0.T)
+    X0 = np.array(x0.T, order="C", copy=True)
     svgd.Initialize()
     svgd.Run()
     ref = oracle.svgd_run(X0, iters, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1, scale_method=oracle.SCALE_FIXED, fixed_a=1.0,
@@ -156,7 +156,7 @@ def test_mixture_gradient_log_sum_exp(sv, oracle):
         model = m if model is None else model + m
     kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
     svgd = sv.SVGD(d, 10, x0, kernel, model, sv.AdaGrad(d, n, 0.1))
-    X0 = np.ascontiguousarray(x0.T)
+    X0 = np.array(x0.T, order="C", copy=True)
     G = svgd.EvaluateLogModelGrad().T
     G_ref = oracle.mvn_sum_logp_grad(X0, means, covs, lse=True)
     assert _rel(G, G_ref) < 1e-12
@@ -190,7 +190,7 @@ def test_median_select_narrowing_paths(sv, oracle, capacity, monkeypatch):
     rng = np.random.default_rng(5)
     for n, d in [(90, 3), (151, 64), (64, 2)]:
         svgd, x0, mu, cov = _mvn_setup(sv, n, d, seed=n)
-        X = np.ascontiguousarray(x0.T)
+        X = np.array(x0.T, order="C", copy=True)
         a = svgd.ComputeScale()
         a_ref = oracle.rbf_median_scale(X)
         assert abs(a - a_ref) <= 1e-12 * a_ref, (n, d)
@@ -247,19 +247,24 @@ def test_full_size_properties(sv):
     model = sv.MultivariateNormal(means[0], covs[0])
     kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
     svgd = sv.SVGD(d, 1, x0, kernel, model, sv.Adam(d, n, 0.1, 0.9, 0.999))
-    X = np.ascontiguousarray(x0.T)
+    X = np.array(x0.T, order="C", copy=True)
     phi, a = svgd.ComputePhi()
     G = -(X - means[0]) @ np.linalg.inv(covs[0])
     rows = np.random.default_rng(0).integers(0, n, 12)
-    frac = []
-    med = np.sqrt(np.log(n) / a)
     for i in rows:
         d2 = ((X - X[i]) ** 2).sum(1)
         k = np.exp(-a * d2)
         ref = (k @ G + (-2 * a * (X - X[i]) * k[:, None]).sum(0)) / n
         assert np.max(np.abs(phi[:, i] - ref)) <= 1e-10 * np.max(np.abs(ref))
-        frac.append(np.mean(np.sqrt(d2) < med))
-    assert abs(np.mean(frac) - 0.5) < 0.05
+    # the scale is log(n)/med^2 with med the median distance: half of 4M random ordered pairs lie below it
+    med = np.sqrt(np.log(n) / a)
+    rng = np.random.default_rng(1)
+    ii, jj = rng.integers(0, n, 4_000_000), rng.integers(0, n, 4_000_000)
+    below = 0
+    for s0 in range(0, ii.size, 500_000):
+        sl = slice(s0, s0 + 500_000)
+        below += int(np.sum(np.sqrt(((X[ii[sl]] - X[jj[sl]]) ** 2).sum(1)) < med))
+    assert abs(below / ii.size - 0.5) < 2e-3   # 8 sigma of the sampling error
     # one full step moves every particle by at most lr (Adam's first step is lr * sign(phi))
     before = x0.copy()
     svgd.Initialize()
