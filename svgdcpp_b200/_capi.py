@@ -73,7 +73,7 @@ def load():
             raise ImportError(
                 f"{LIB_PATH} is missing: build the CUDA extension first "
                 "(python -m svgdcpp_b200.build, or __graft_entry__.build()). There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export it
             fn.restype = res

@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     defines = ["-DSVGDB_WITH_TC32"] if os.path.exists(os.path.join(CSRC, "kernels_tc32.cuh")) else []
     cmd = [_nvcc(), *NVCC_FLAGS, *_host_cxx(), *defines, "-o", LIB_PATH,
-           os.path.join(CSRC, "svgd_b200_api.cu"), "-lnccl", "-lcuda"]
+           os.path.join(CSRC, "svgd_b200_api.cu"), "-ldl", "-lcuda"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

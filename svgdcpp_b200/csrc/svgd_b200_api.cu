@@ -7,7 +7,8 @@
 #include "../../include/svgd_b200.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is resolved lazily with dlopen (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,40 @@ namespace {
 
 enum { MODEL_UNSET = 0, MODEL_MVN_SUM = 1, MODEL_HOOK = 2 };
 constexpr uint64_t KEY_END = 0x7FF0000000000001ull; // one past the bit pattern of +inf
+
+// NCCL is bound at run time, on first multi-GPU use, instead of through DT_NEEDED: a process that
+// already carries an NCCL (PyTorch bundles its own libnccl.so.2) must keep exactly that one, and a
+// single-GPU process must not drag one in at all.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+    auto sym = [&](const char *name) { void *p = dlsym(h, name); if (!p) api.why = std::string("missing NCCL symbol ") + name; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+    return api;
+}
 
 struct HostScratch { // pinned
     unsigned long long below, max_below, cand_count;
@@ -113,7 +148,7 @@ int fail(svgdb_ctx *ctx, int code, const std::string &msg)
     do {                                                                                                 \
         ncclResult_t r_ = (call);                                                                        \
         if (r_ != ncclSuccess)                                                                           \
-            return fail(ctx, SVGDB_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));        \
+            return fail(ctx, SVGDB_ERR_NCCL, std::string(#call) + ": " + nccl().GetErrorString(r_));        \
     } while (0)
 
 #define TRY(call)                                                                                        \
@@ -212,7 +247,7 @@ int alloc_sharded(svgdb_ctx *ctx)
 int allreduce_u64(svgdb_ctx *ctx, unsigned long long *buf, size_t count, ncclRedOp_t op)
 {
     if (ctx->world == 1) return SVGDB_OK;
-    NC(ncclAllReduce(buf, buf, count, ncclUint64, op, ctx->comm, ctx->stream));
+    NC(nccl().AllReduce(buf, buf, count, ncclUint64, op, ctx->comm, ctx->stream));
     return SVGDB_OK;
 }
 
@@ -220,7 +255,7 @@ int allgather_rows(svgdb_ctx *ctx, double *buf, int64_t elems_per_row)
 {
     if (ctx->world == 1) return SVGDB_OK;
     size_t chunk = (size_t)ctx->rows_per_rank * elems_per_row;
-    NC(ncclAllGather(buf + (size_t)ctx->rank * chunk, buf, chunk, ncclDouble, ctx->comm, ctx->stream));
+    NC(nccl().AllGather(buf + (size_t)ctx->rank * chunk, buf, chunk, ncclDouble, ctx->comm, ctx->stream));
     return SVGDB_OK;
 }
 
@@ -649,7 +684,7 @@ void svgdb_destroy(svgdb_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    if (ctx->comm) nccl().CommDestroy(ctx->comm);
     free_sharded(ctx);
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
     cudaFree(ctx->below); cudaFree(ctx->max_below); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
@@ -672,7 +707,7 @@ int svgdb_nccl_unique_id(void *out_id, size_t bytes)
 {
     if (!out_id || bytes < sizeof(ncclUniqueId)) return SVGDB_ERR_INVALID;
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return SVGDB_ERR_NCCL;
+    if (!nccl().ok || nccl().GetUniqueId(&id) != ncclSuccess) return SVGDB_ERR_NCCL;
     std::memcpy(out_id, &id, sizeof(id));
     return SVGDB_OK;
 }
@@ -682,13 +717,14 @@ int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique
     if (!ctx) return SVGDB_ERR_INVALID;
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SVGDB_ERR_INVALID, "bad world/rank");
     if (world > ctx->N) return fail(ctx, SVGDB_ERR_DIMENSION, "more ranks than particles");
-    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->comm) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
     if (world > 1) {
+        if (!nccl().ok) return fail(ctx, SVGDB_ERR_NCCL, nccl().why);
         if (!nccl_unique_id || bytes < sizeof(ncclUniqueId)) return fail(ctx, SVGDB_ERR_INVALID, "missing ncclUniqueId");
         ncclUniqueId id;
         std::memcpy(&id, nccl_unique_id, sizeof(id));
         CU(cudaSetDevice(ctx->device));
-        NC(ncclCommInitRank(&ctx->comm, world, id, rank));
+        NC(nccl().CommInitRank(&ctx->comm, world, id, rank));
     }
     ctx->world = world;
     ctx->rank = rank;
