@@ -121,6 +121,15 @@ struct svgdb_ctx {
     double pred_d2_lo = 0.0, pred_d2_hi = 0.0, delta = 0.0;
     int skip_pred = 0, miss_streak = 0;
 
+    // tensor-core path (SVGDB_PRECISION_TC32)
+    int64_t n_pad128 = 0;
+    __nv_bfloat16 *XA = nullptr, *XB = nullptr;
+    __half *VT = nullptr;
+    float *beta = nullptr, *rf = nullptr, *phi_buf = nullptr;
+    double *rt = nullptr, *colsum = nullptr;
+    int *tc_err = nullptr;
+    CUtensorMap mapA{}, mapB{}, mapV{};
+
     // measurement
     svgdb_stats stats{};
     bool profiling = false;
@@ -214,8 +223,68 @@ int free_sharded(svgdb_ctx *ctx)
     cudaFree(ctx->X[0]); cudaFree(ctx->X[1]); cudaFree(ctx->V); cudaFree(ctx->G); cudaFree(ctx->r);
     cudaFree(ctx->s1); cudaFree(ctx->s2); cudaFree(ctx->phi_dbg);
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
+    cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
+    cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err);
+    ctx->XA = ctx->XB = nullptr;
+    ctx->VT = nullptr;
+    ctx->beta = ctx->rf = ctx->phi_buf = nullptr;
+    ctx->rt = ctx->colsum = nullptr;
+    ctx->tc_err = nullptr;
     return SVGDB_OK;
 }
+
+#ifdef SVGDB_WITH_TC32
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// rows x cols bf16, cols contiguous; box = 64 cols (128 B, SWIZZLE_128B) x box_rows; out-of-bounds reads give zeros
+int make_bf16_map(svgdb_ctx *ctx, CUtensorMap *m, void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+{
+    static TmapEncodeFn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        enc = (TmapEncodeFn)fn;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return SVGDB_OK;
+}
+
+int alloc_tc32(svgdb_ctx *ctx)
+{
+    using namespace svgdb::tc;
+    ctx->n_pad128 = (ctx->N + 127) / 128 * 128;
+    const size_t np = (size_t)ctx->n_pad128;
+    CU(cudaMalloc(&ctx->XA, np * TC_KTOT * 2));
+    CU(cudaMalloc(&ctx->XB, np * TC_KTOT * 2));
+    CU(cudaMalloc(&ctx->VT, (size_t)TC_NV * np * 2));
+    CU(cudaMalloc(&ctx->beta, np * 4));
+    CU(cudaMalloc(&ctx->rf, np * 4));
+    CU(cudaMalloc(&ctx->rt, np * 8));
+    CU(cudaMalloc(&ctx->colsum, 64 * 8));
+    CU(cudaMalloc(&ctx->tc_err, 4));
+    // rows of a tile may reach past the last rank-local row: keep a tile of slack
+    CU(cudaMalloc(&ctx->phi_buf, (np + 128) * TC_PHI_LD * 4));
+    CU(cudaMemsetAsync(ctx->XA, 0, np * TC_KTOT * 2, ctx->stream));
+    CU(cudaMemsetAsync(ctx->XB, 0, np * TC_KTOT * 2, ctx->stream));
+    CU(cudaMemsetAsync(ctx->VT, 0, (size_t)TC_NV * np * 2, ctx->stream));
+    CU(cudaMemsetAsync(ctx->beta, 0, np * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream));
+    TRY(make_bf16_map(ctx, &ctx->mapA, ctx->XA, np, TC_KTOT, 128));
+    TRY(make_bf16_map(ctx, &ctx->mapB, ctx->XB, np, TC_KTOT, 128));
+    TRY(make_bf16_map(ctx, &ctx->mapV, ctx->VT, TC_NV, np, TC_NV));
+    return SVGDB_OK;
+}
+#endif
 
 int alloc_sharded(svgdb_ctx *ctx)
 {
@@ -240,6 +309,9 @@ int alloc_sharded(svgdb_ctx *ctx)
     CU(cudaMemsetAsync(ctx->s1, 0, local, ctx->stream));
     CU(cudaMemsetAsync(ctx->s2, 0, local, ctx->stream));
     ctx->cur = 0;
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(alloc_tc32(ctx));
+#endif
     return SVGDB_OK;
 }
 
@@ -547,6 +619,91 @@ int launch_make_v(svgdb_ctx *ctx)
     return allgather_rows(ctx, ctx->V, ctx->d);
 }
 
+#ifdef SVGDB_WITH_TC32
+// centred bf16-split operands, r = |x~|^2
+int launch_tc_split(svgdb_ctx *ctx)
+{
+    using namespace svgdb::tc;
+    CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
+    colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
+    KERNEL_CHECK();
+    split_kernel<<<(unsigned)((ctx->n_pad128 + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->N, ctx->n_pad128, ctx->d,
+                                                                                 ctx->XA, ctx->XB, ctx->rt, ctx->rf);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+int pick_jsplit(int n_itiles, int n_jtiles, int sms)
+{
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= std::min(n_jtiles, 64); ++s) {
+        long units = (long)n_itiles * s;
+        long waves = (units + sms - 1) / sms;
+        double eff = (double)units / (double)(waves * sms);
+        if (n_jtiles / s < 4 && s > 1) break; // keep at least a few tiles per unit
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
+{
+    using namespace svgdb::tc;
+    if (ctx->n_rows <= 0) return SVGDB_OK;
+    make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
+                                                                            ctx->d, ctx->VT, ctx->beta);
+    KERNEL_CHECK();
+    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 128) * TC_PHI_LD * 4, ctx->stream));
+    PhiTcArgs a{};
+    a.beta = ctx->beta;
+    a.a_ptr = ctx->a_dev;
+    a.phi_buf = ctx->phi_buf;
+    a.n_total = ctx->N;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.n_jtiles = (int)(ctx->n_pad128 / 128);
+    const int n_itiles = (int)((ctx->n_rows + 127) / 128);
+    a.jsplit = pick_jsplit(n_itiles, a.n_jtiles, ctx->sm_count);
+    a.err = ctx->tc_err;
+    phi_tc32_kernel<<<(unsigned)(n_itiles * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
+    KERNEL_CHECK();
+    ++ctx->stats.phi_launches;
+    OptTcArgs o{};
+    o.X = ctx->X[ctx->cur];
+    o.colsum = ctx->colsum;
+    o.phi_buf = ctx->phi_buf;
+    o.a_ptr = ctx->a_dev;
+    o.n_total = ctx->N;
+    o.row0 = ctx->row0;
+    o.n_rows = ctx->n_rows;
+    o.d = ctx->d;
+    o.opt = ctx->opt;
+    o.s1 = ctx->s1;
+    o.s2 = ctx->s2;
+    o.lb = ctx->lb;
+    o.ub = ctx->ub;
+    o.X_out = ctx->X[ctx->cur ^ 1];
+    o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+    int64_t cnt = ctx->n_rows * ctx->d;
+    opt_update_tc32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+int check_tc_err(svgdb_ctx *ctx)
+{
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, ctx->tc_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (e != 0) {
+        cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream);
+        return fail(ctx, SVGDB_ERR_CUDA, "tensor-core pipeline timed out waiting on barrier tag " + std::to_string(e));
+    }
+    return SVGDB_OK;
+}
+#endif
+
 int check_ready(svgdb_ctx *ctx)
 {
     if (ctx->model_kind == MODEL_UNSET) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
@@ -563,6 +720,9 @@ void prof_mark(svgdb_ctx *ctx, int i)
 int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
 {
     prof_mark(ctx, 0);
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx));
+#endif
     TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     prof_mark(ctx, 1);
@@ -570,6 +730,13 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
     prof_mark(ctx, 2);
     TRY(launch_make_v(ctx));
     prof_mark(ctx, 3);
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) {
+        TRY(launch_phi_tc32(ctx, debug_phi));
+        prof_mark(ctx, 4);
+        return SVGDB_OK;
+    }
+#endif
     TRY(launch_phi(ctx, debug_phi));
     prof_mark(ctx, 4);
     return SVGDB_OK;
@@ -661,6 +828,13 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
             return fail(ctx, SVGDB_ERR_DIMENSION, "dimension too large for the built-in Gaussian gradient kernel (d <= 590)");
         CU(cudaFuncSetAttribute(mvn_sum_grad_f64_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
     }
+#ifdef SVGDB_WITH_TC32
+    if (precision_mode == SVGDB_PRECISION_TC32) {
+        if (d > svgdb::tc::TC_D)
+            return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
+        CU(cudaFuncSetAttribute(svgdb::tc::phi_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_PHI_SMEM));
+    }
+#endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
     CU(cudaMalloc(&ctx->below, 8));
     CU(cudaMalloc(&ctx->max_below, 8));
@@ -747,6 +921,9 @@ int svgdb_get_particles(svgdb_ctx *ctx, double *X)
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
     CU(cudaMemcpyAsync(X, ctx->X[ctx->cur], (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(check_tc_err(ctx));
+#endif
     return SVGDB_OK;
 }
 
@@ -950,6 +1127,9 @@ int svgdb_sync(svgdb_ctx *ctx)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
     CU(cudaStreamSynchronize(ctx->stream));
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(check_tc_err(ctx));
+#endif
     return SVGDB_OK;
 }
 

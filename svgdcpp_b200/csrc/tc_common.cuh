@@ -94,6 +94,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: f16 x f16 -> f32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- MMA (issued by ONE thread) ---------------------------------------------------------------------
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -151,6 +157,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) // lo -> bit
 {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) // lo -> bits [0,16), hi -> bits [16,32)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 

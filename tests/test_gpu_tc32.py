@@ -1,0 +1,75 @@
+"""GPU parity tests of the tensor-core path (SVGDB_PRECISION_TC32: tcgen05 MMA on split-bf16 operands,
+fp32 accumulation in TMEM, fp32 exp) against the FP64 CPU oracle.
+
+Stated tolerances (DESIGN.md "Precision modes"):
+  * one ComputePhi on identical particles: max|phi - phi_ref| <= 2e-4 * max|phi_ref|
+  * kernel scale a: <= 1e-5 relative (the median is an exact order statistic of fp32 distances)
+  * trajectories (AdaGrad / Adam, 50 iterations): RMS error <= 1e-3 * RMS|X|
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PHI_TOL = 2e-4
+TC32 = 1
+
+
+@pytest.fixture(scope="module")
+def sv():
+    import svgdcpp_b200
+
+    svgdcpp_b200._capi.load()
+    return svgdcpp_b200
+
+
+def _setup(sv, n, d, seed, opt="adam", iters=1, shift=0.0, **kw):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + 0.5 * np.eye(d)
+    mu = rng.standard_normal(d) + shift
+    x0 = np.asfortranarray(2.0 * rng.standard_normal((d, n)) + shift)
+    model = sv.MultivariateNormal(mu, cov)
+    kernel = sv.GaussianRBFKernel(x0, kw.pop("scale", sv.ScaleMethod.Median), model, fixed_scale=kw.pop("fixed_scale", 0.0))
+    optimizer = sv.Adam(d, n, 0.1, 0.9, 0.999) if opt == "adam" else sv.AdaGrad(d, n, 0.1)
+    return sv.SVGD(d, iters, x0, kernel, model, optimizer, precision=TC32, **kw), x0, mu[None], cov[None]
+
+
+@pytest.mark.parametrize("n,d,shift", [(128, 64, 0.0), (129, 64, 0.0), (300, 64, 0.0), (1000, 17, 0.0), (513, 2, 0.0),
+                                       (777, 33, 0.0), (2048, 64, 0.0), (640, 64, 25.0)])
+def test_tc32_phi_matches_oracle(sv, oracle, n, d, shift):
+    svgd, x0, mu, cov = _setup(sv, n, d, seed=n + d, shift=shift)
+    X = np.array(x0.T, order="C", copy=True)
+    phi, a = svgd.ComputePhi()
+    a_ref = oracle.rbf_median_scale(X)
+    G_ref = oracle.mvn_sum_logp_grad(X, mu, cov)
+    phi_ref = oracle.phi(X, G_ref, a_ref)
+    err = np.max(np.abs(phi.T - phi_ref)) / np.max(np.abs(phi_ref))
+    print("n=%d d=%d shift=%g: a rel err %.3g, phi max-rel err %.3g" % (n, d, shift, abs(a - a_ref) / a_ref, err))
+    assert abs(a - a_ref) <= 1e-5 * a_ref
+    assert err < PHI_TOL
+    svgd.close()
+
+
+@pytest.mark.parametrize("opt", ["adagrad", "adam"])
+def test_tc32_trajectory(sv, oracle, opt):
+    n, d, iters = 512, 64, 50
+    svgd, x0, mu, cov = _setup(sv, n, d, seed=3, opt=opt, iters=iters)
+    X0 = np.array(x0.T, order="C", copy=True)
+    svgd.Initialize()
+    svgd.Run()
+    kind = oracle.OPT_ADAM if opt == "adam" else oracle.OPT_ADAGRAD
+    ref = oracle.svgd_run(X0, iters, mu, cov, opt_kind=kind, lr=0.1)
+    diff = x0.T - ref
+    rms = np.sqrt(np.mean(diff ** 2)) / np.sqrt(np.mean(ref ** 2))
+    mx = np.max(np.abs(diff)) / np.max(np.abs(ref))
+    print("%s: trajectory rms rel err %.3g, max rel err %.3g" % (opt, rms, mx))
+    assert rms < 1e-3
+    svgd.close()
+
+
+def test_tc32_rejects_large_dimension(sv):
+    x0 = np.zeros((65, 8), order="F")
+    model = sv.MultivariateNormal(np.zeros(65), np.eye(65))
+    with pytest.raises(sv.DimensionMismatchException):
+        sv.SVGD(65, 1, x0, sv.GaussianRBFKernel(x0), model, sv.AdaGrad(65, 8, 0.1), precision=TC32)
