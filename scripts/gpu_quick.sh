@@ -7,7 +7,7 @@ PYT=${1:-"tests -m gpu"}; shift || true
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 python -c "import __graft_entry__ as g; g.build()" > "$OUT/build.log" 2>&1 || cat "$OUT/build.log"
-timeout 900 python -m pytest $PYT -q -s -p no:cacheprovider > "$OUT/pytest.log" 2>&1
+timeout ${PYTEST_TIMEOUT:-240} python -m pytest $PYT -q -s -p no:cacheprovider > "$OUT/pytest.log" 2>&1
 echo "pytest exit $?" >> "$OUT/pytest.log"
 grep -E "rel err|passed|failed|Error|error|exit" "$OUT/pytest.log" | tail -40
 if [ $# -gt 0 ]; then

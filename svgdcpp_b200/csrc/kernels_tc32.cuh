@@ -8,8 +8,9 @@
 //   * E = exp2(2c S - c r_i - c r_j), c = a log2(e), with r = |x~|^2 from FP64, one MUFU.EX2 per pair;
 //   * E is scaled by 2^15, rounded to fp16 (11-bit significand; every k >= 2^-29 stays a normal number)
 //     and written back to TMEM as the A operand of the second contraction against
-//     V^T = [v_hi | 1 | v_lo] (v = g - 2 a x~ split in two fp16 terms; the ones column yields the row
-//     sum with the SAME rounded E, so the k(x_i,x_i) = 1 self term cancels exactly in the repulsion);
+//     [v_hi | 1] and [v_lo | 0] (v = g - 2 a x~ split in two fp16 terms, both accumulated into the same
+//     TMEM columns; the ones column yields the row sum with the SAME rounded E, so the k(x_i,x_i) = 1
+//     self term cancels exactly in the repulsion);
 //   * the optimizer, clamp and the particle state stay FP64 (opt_update_tc32_kernel).
 // Error bound and measurements: DESIGN.md "Precision modes".
 //
@@ -27,8 +28,8 @@ constexpr int TC_D = 64;        // padded particle dimension (d <= 64 in this pa
 constexpr int TC_KCH = 3;       // 64-wide K chunks of the distance contraction: hi.hi, hi.lo, lo.hi
 constexpr int TC_KTOT = TC_KCH * 64;
 constexpr int TC_NVH = 80;      // V^T rows: [0,64) v_hi, 64 = ones, [65,80) zero
-constexpr int TC_NV = 144;      //           [80,144) v_lo
-constexpr int TC_ONES_ROW = 64;
+constexpr int TC_NV = 160;      //           [80,144) v_lo, [144,160) zero  (hi and lo blocks are contracted into
+constexpr int TC_ONES_ROW = 64; //           the SAME 80 accumulator columns: Phi += E v_hi^T ; Phi += E v_lo^T)
 constexpr int TC_PHI_LD = 80;   // phi_buf row: [0,64) sum_j E v, 64 = sum_j E
 constexpr int TC_TILE = 128;
 constexpr float TC_E_SCALE_LOG2 = 15.0f; // E is stored as fp16(2^15 E)
@@ -68,7 +69,7 @@ __global__ void split_kernel(const double *__restrict__ X, const double *__restr
         b[k] = hi; b[64 + k] = lo; b[128 + k] = hi;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) { rt[row] = s; rf[row] = (float)s; }
+    if (lane == 0) { rt[row] = s; rf[row] = row < n ? (float)s : INFINITY; }
 }
 
 // V^T (bf16, [TC_NV][ldn]) and beta = -a log2(e) r from the FP64 V = G - 2 a X (uncentred) of all particles:
@@ -96,6 +97,7 @@ make_vt_kernel(const double *__restrict__ V, const double *__restrict__ colsum, 
     for (int t = threadIdx.x; t < 16 * 64; t += blockDim.x) {
         int rr = TC_ONES_ROW + (t >> 6), jl = t & 63;
         tile[rr][jl] = __float2half_rn((rr == TC_ONES_ROW && j0 + jl < n) ? 1.f : 0.f);
+        tile[TC_NVH + rr][jl] = __float2half_rn(0.f); // the lo block carries no ones row
     }
     if (threadIdx.x < 64) {
         int64_t j = j0 + threadIdx.x;
@@ -144,19 +146,30 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
 }
 
 // ---- the fused pair-interaction kernel ---------------------------------------------------------------
+// One CTA owns TWO 128-row i-tiles (256 particles) and a range of 128-column j-tiles.  Warps 0-3 / 4-7 are the
+// exp warpgroups of i-tile 0 / 1 (thread = TMEM lane = row), warp 8 lane 0 is the TMA producer, warp 9 lane 0
+// issues every tcgen05.mma.  Both i-tiles contract against the same X_j / V_j tiles in shared memory, and the
+// MMA order  PV0(t) S0(t+1) PV1(t) S1(t+1)  gives each warpgroup a full  PV + S  window (~1400 tensor cycles) for
+// its 128x128 exponentials before the tensor pipe needs the result (FlashAttention-4 style ping-pong).
+//   TMEM   S_w [128 w, +128) fp32;  E_w = fp16 pairs over the first 64 columns of S_w;  Phi_w [256 + 80 w, +80)
+//   smem   A_w 2 x 48 KB resident;  X_j ring 4 x 16 KB chunks (3 per tile);  V_j ring 6 x 10 KB chunks (4 per tile:
+//          hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128));  beta ring 4 x 512 B
 struct PhiTcArgs {
     const float *beta;   // [n_pad] -c r_j (0 beyond n)
     const double *a_ptr;
-    float *phi_buf;      // [n_pad][TC_PHI_LD], zeroed; partial sums are added atomically
+    float *phi_buf;      // [n_pad + 256][TC_PHI_LD], zeroed; partial sums are added atomically
     int64_t n_total, row0, n_rows;
     int n_jtiles, jsplit;
     int *err;
 };
 
-constexpr uint32_t TC_A_BYTES = TC_KCH * 16384;            // resident X_i tile
-constexpr uint32_t TC_B_BYTES = TC_KCH * 16384;            // one X_j tile
-constexpr uint32_t TC_V_BYTES = 2 * TC_NV * 128;           // one V^T tile (two 64-wide K chunks)
-constexpr uint32_t TC_PHI_SMEM = TC_A_BYTES + 2 * TC_B_BYTES + 2 * TC_V_BYTES + 256 + 1024;
+constexpr uint32_t TC_CHUNK = 16384;                     // 128 rows x 128 B
+constexpr uint32_t TC_A_BYTES = TC_KCH * TC_CHUNK;       // one resident X_i tile
+constexpr int TC_NB = 4;                                 // X_j chunk ring
+constexpr uint32_t TC_VCHUNK = TC_NVH * 128;             // 80 rows x 128 B
+constexpr int TC_NVS = 6;                                // V chunk ring
+constexpr int TC_NBETA = 4;
+constexpr uint32_t TC_PHI_SMEM = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NVS * TC_VCHUNK + TC_NBETA * 512 + 512 + 1024;
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -164,39 +177,50 @@ __device__ __forceinline__ float ex2_approx(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void bulk_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
-// grid.x = n_itiles * jsplit; 320 threads: warps 0-3 / 4-7 = exp warpgroups for S buffers 0 / 1 (thread =
-// TMEM lane = row i), warp 8 = TMA producer, warp 9 = MMA issuer.  TMEM: S0 [0,128) S1 [128,256) Phi [256,400);
-// E_b (fp16 pairs) overwrites the first 64 columns of S_b in place.
 __global__ void __launch_bounds__(320, 1)
 phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapV, PhiTcArgs p)
 {
-    const int it = blockIdx.x / p.jsplit, js = blockIdx.x - it * p.jsplit;
+    const int ip = blockIdx.x / p.jsplit, js = blockIdx.x - ip * p.jsplit;
     const int tps = (p.n_jtiles + p.jsplit - 1) / p.jsplit;
     const int jbeg = js * tps;
     const int nt = min(p.n_jtiles, jbeg + tps) - jbeg;
     if (nt <= 0) return;
-    const int64_t i0 = p.row0 + (int64_t)it * TC_TILE;
+    const int64_t i0 = p.row0 + (int64_t)ip * (2 * TC_TILE);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;
-    uint8_t *sB = sA + TC_A_BYTES;
-    uint8_t *sV = sB + 2 * TC_B_BYTES;
-    uint64_t *bars = (uint64_t *)(sV + 2 * TC_V_BYTES);
-    uint64_t *a_full = bars + 0, *b_full = bars + 1, *b_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7;
-    uint64_t *s_full = bars + 9, *e_ready = bars + 11, *phi_full = bars + 13;
-    uint32_t *tmem_holder = (uint32_t *)(bars + 16);
+    uint8_t *sA = smem;                              // [2][TC_A_BYTES]
+    uint8_t *sB = sA + 2 * TC_A_BYTES;               // [TC_NB][TC_CHUNK]
+    uint8_t *sV = sB + TC_NB * TC_CHUNK;             // [TC_NVS][TC_VCHUNK]
+    float *sBeta = (float *)(sV + TC_NVS * TC_VCHUNK); // [TC_NBETA][128]
+    uint64_t *bars = (uint64_t *)(sBeta + TC_NBETA * 128);
+    uint64_t *a_full = bars;                // 1
+    uint64_t *b_full = bars + 1;            // TC_NB
+    uint64_t *b_empty = b_full + TC_NB;     // TC_NB
+    uint64_t *v_full = b_empty + TC_NB;     // TC_NVS
+    uint64_t *v_empty = v_full + TC_NVS;    // TC_NVS
+    uint64_t *s_full = v_empty + TC_NVS;    // 2
+    uint64_t *e_ready = s_full + 2;         // 2
+    uint64_t *phi_full = e_ready + 2;       // 1
+    uint64_t *r_full = phi_full + 1;        // TC_NBETA  (beta tile landed)
+    uint64_t *r_empty = r_full + TC_NBETA;  // TC_NBETA  (all 256 exp threads are done with it)
+    uint32_t *tmem_holder = (uint32_t *)(r_empty + TC_NBETA);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1);
-            mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1);
-            mbar_init(s_full + s, 1); mbar_init(e_ready + s, 128);
-        }
+        for (int s = 0; s < TC_NB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < TC_NVS; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 128); }
+        for (int s = 0; s < TC_NBETA; ++s) { mbar_init(r_full + s, 1); mbar_init(r_empty + s, 256); }
         mbar_init(phi_full, 1);
         fence_barrier_init();
     }
@@ -205,134 +229,383 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
-    const uint32_t tS[2] = {tmem, tmem + 128};
-    const uint32_t tPhi = tmem + 256;
 
     if (warp == 8) {
-        if (lane == 0) { // ---- TMA producer ------------------------------------------------------------
-            mbar_arrive_expect_tx(a_full, TC_A_BYTES);
-            for (int c = 0; c < TC_KCH; ++c) tma_load_2d(sA + c * 16384, &mapA, c * 64, (int)i0, a_full);
-            for (int t = 0; t < nt; ++t) {
-                const int slot = t & 1, ph = (t >> 1) & 1;
+        if (lane == 0) { // ---- TMA producer ------------------------------------------------------------------
+            mbar_arrive_expect_tx(a_full, 2 * TC_A_BYTES);
+            for (int w = 0; w < 2; ++w)
+                for (int c = 0; c < TC_KCH; ++c)
+                    tma_load_2d(sA + w * TC_A_BYTES + c * TC_CHUNK, &mapA, c * 64, (int)(i0 + w * TC_TILE), a_full);
+            bool ok = true;
+            for (int t = 0; ok && t < nt; ++t) {
                 const int j0 = (jbeg + t) * TC_TILE;
-                if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 10)) break;
-                mbar_arrive_expect_tx(b_full + slot, TC_B_BYTES);
-                for (int c = 0; c < TC_KCH; ++c) tma_load_2d(sB + slot * TC_B_BYTES + c * 16384, &mapB, c * 64, j0, b_full + slot);
-                if (!mbar_wait(v_empty + slot, ph ^ 1, p.err, 11)) break;
-                mbar_arrive_expect_tx(v_full + slot, TC_V_BYTES);
-                for (int c = 0; c < 2; ++c) tma_load_2d(sV + slot * TC_V_BYTES + c * TC_NV * 128, &mapV, j0 + c * 64, 0, v_full + slot);
+                {
+                    const int rs = t % TC_NBETA, rph = (t / TC_NBETA) & 1;
+                    if (!mbar_wait(r_empty + rs, rph ^ 1, p.err, 12)) { ok = false; break; }
+                    mbar_arrive_expect_tx(r_full + rs, 512);
+                    bulk_load_1d(sBeta + rs * 128, p.beta + j0, 512, r_full + rs);
+                }
+                for (int c = 0; ok && c < TC_KCH; ++c) {
+                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                    if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 10)) { ok = false; break; }
+                    mbar_arrive_expect_tx(b_full + slot, TC_CHUNK);
+                    tma_load_2d(sB + slot * TC_CHUNK, &mapB, c * 64, j0, b_full + slot);
+                }
+                for (int c = 0; ok && c < 4; ++c) {
+                    const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
+                    if (!mbar_wait(v_empty + slot, ph ^ 1, p.err, 11)) { ok = false; break; }
+                    mbar_arrive_expect_tx(v_full + slot, TC_VCHUNK);
+                    tma_load_2d(sV + slot * TC_VCHUNK, &mapV, j0 + (c & 1) * 64, (c >> 1) * TC_NVH, v_full + slot);
+                }
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) { // ---- MMA issuer ----------------------------------------------------------------
+        if (lane == 0) { // ---- MMA issuer ----------------------------------------------------------------------
             const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
-            const uint32_t idesc_v = make_idesc_f16(TC_TILE, TC_NV);
+            const uint32_t idesc_v = make_idesc_f16(TC_TILE, TC_NVH);
             bool ok = mbar_wait(a_full, 0, p.err, 20);
-            auto issue_s = [&](int t) -> bool {
-                const int slot = t & 1, ph = (t >> 1) & 1;
-                if (!mbar_wait(b_full + slot, ph, p.err, 21)) return false;
-                tc_fence_after();
+            auto issue_s = [&](int w, int t) -> bool { // S_w(t) = X_iw . X_j^T
 #pragma unroll
-                for (int c = 0; c < TC_KCH; ++c)
+                for (int c = 0; c < TC_KCH; ++c) {
+                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                    if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 21)) return false;
+                    if (w == 0 && c == 0) tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        uint64_t da = make_desc_k_sw128(smem_u32(sA + c * 16384) + k * 32);
-                        uint64_t db = make_desc_k_sw128(smem_u32(sB + slot * TC_B_BYTES + c * 16384) + k * 32);
-                        umma_bf16_ss(tS[slot], da, db, idesc_s, (c | k) ? 1u : 0u);
+                        uint64_t da = make_desc_k_sw128(smem_u32(sA + w * TC_A_BYTES + c * TC_CHUNK) + k * 32);
+                        uint64_t db = make_desc_k_sw128(smem_u32(sB + slot * TC_CHUNK) + k * 32);
+                        umma_bf16_ss(tmem + w * 128, da, db, idesc_s, (c | k) ? 1u : 0u);
                     }
-                umma_commit(b_empty + slot);
-                umma_commit(s_full + slot);
+                    if (w == 1) umma_commit(b_empty + slot); // both i-tiles have consumed this chunk
+                }
+                umma_commit(s_full + w);
                 return true;
             };
-            if (ok) ok = issue_s(0);
-            for (int t = 0; ok && t < nt; ++t) {
-                if (t + 1 < nt && !issue_s(t + 1)) { ok = false; break; }
-                const int slot = t & 1, ph = (t >> 1) & 1;
-                if (!mbar_wait(e_ready + slot, ph, p.err, 22)) { ok = false; break; }
-                if (!mbar_wait(v_full + slot, ph, p.err, 23)) { ok = false; break; }
-                tc_fence_after();
+            auto issue_pv = [&](int w, int t) -> bool { // Phi_w += E_w(t) . [v_hi ; v_lo]
+                if (!mbar_wait(e_ready + w, t & 1, p.err, 22 + w)) return false;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 4; ++c) {
+                    const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
+                    if (w == 0 && !mbar_wait(v_full + slot, ph, p.err, 24)) return false;
+                    if (c == 0) tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        uint64_t db = make_desc_k_sw128(smem_u32(sV + slot * TC_V_BYTES + c * TC_NV * 128) + k * 32);
-                        umma_bf16_ts(tPhi, tS[slot] + (c * 4 + k) * 8, db, idesc_v, (t | c | k) ? 1u : 0u);
+                        uint64_t db = make_desc_k_sw128(smem_u32(sV + slot * TC_VCHUNK) + k * 32);
+                        umma_bf16_ts(tmem + 256 + w * TC_NVH, tmem + w * 128 + ((c & 1) * 4 + k) * 8, db, idesc_v, (t | c | k) ? 1u : 0u);
                     }
-                umma_commit(v_empty + slot);
+                    if (w == 1) umma_commit(v_empty + slot);
+                }
+                return true;
+            };
+            if (ok) ok = issue_s(0, 0) && issue_s(1, 0);
+            for (int t = 0; ok && t < nt; ++t) {
+                ok = issue_pv(0, t);
+                if (ok && t + 1 < nt) ok = issue_s(0, t + 1);
+                if (ok) ok = issue_pv(1, t);
+                if (ok && t + 1 < nt) ok = issue_s(1, t + 1);
             }
             if (ok) umma_commit(phi_full);
         }
-    } else { // ---- exp warpgroups ----------------------------------------------------------------------------
-        const int b = warp >> 2;
+    } else { // ---- exp warpgroups ------------------------------------------------------------------------------
+        const int w = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const int64_t i = i0 + row;
+        const uint32_t tS = tmem + w * 128 + lane_base;
+        const int64_t iw0 = i0 + w * TC_TILE;
+        const int64_t i = iw0 + row;
         const float alpha = ((i < p.n_total) ? p.beta[i] : 0.f) + TC_E_SCALE_LOG2;
         const float two_c = (float)(2.0 * (*p.a_ptr) * 1.4426950408889634);
         bool ok = true;
-        for (int t = b; ok && t < nt; t += 2) {
-            const int ph = (t >> 1) & 1;
-            if (!mbar_wait(s_full + b, ph, p.err, 30 + b)) { ok = false; break; }
-            tc_fence_after();
+        for (int t = 0; ok && t < nt; ++t) {
             const int64_t j0 = (int64_t)(jbeg + t) * TC_TILE;
             const int64_t dcol = i - j0; // column of k(x_i, x_i) in this tile, if inside [0,128)
-            const bool tile_has_diag = (j0 < i0 + TC_TILE) && (j0 + TC_TILE > i0);
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_TILE; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tS[b] + lane_base + c0, r);
-                float4 bq[8];
-                const float4 *bp = reinterpret_cast<const float4 *>(p.beta + j0 + c0);
+            const bool tile_has_diag = (j0 < iw0 + TC_TILE) && (j0 + TC_TILE > iw0);
+            const float4 *bsm = reinterpret_cast<const float4 *>(sBeta + (t % TC_NBETA) * 128);
+            if (!mbar_wait(r_full + (t % TC_NBETA), (t / TC_NBETA) & 1, p.err, 32)) { ok = false; break; }
+            if (!mbar_wait(s_full + w, t & 1, p.err, 30 + w)) { ok = false; break; }
+            tc_fence_after();
+            uint32_t r[2][32];
+            tmem_ld32(tS, r[0]);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) bq[q] = __ldg(bp + q);
+            for (int c = 0; c < 4; ++c) {
                 tmem_ld_wait();
-                float e[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    e[4 * q + 0] = ex2_approx(fmaf(__uint_as_float(r[4 * q + 0]), two_c, alpha + bq[q].x));
-                    e[4 * q + 1] = ex2_approx(fmaf(__uint_as_float(r[4 * q + 1]), two_c, alpha + bq[q].y));
-                    e[4 * q + 2] = ex2_approx(fmaf(__uint_as_float(r[4 * q + 2]), two_c, alpha + bq[q].z));
-                    e[4 * q + 3] = ex2_approx(fmaf(__uint_as_float(r[4 * q + 3]), two_c, alpha + bq[q].w));
-                }
-                if (tile_has_diag) {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        if (dcol == c0 + q) e[q] = 32768.0f; // k(x_i, x_i) = exp(0) exactly, like the reference
-                }
+                if (c < 3) tmem_ld32(tS + (c + 1) * 32, r[(c + 1) & 1]); // overlaps the math on chunk c
                 uint32_t packed[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) packed[q] = pack_f16x2(e[2 * q], e[2 * q + 1]);
-                tmem_st16(tS[b] + lane_base + c0 / 2, packed);
+                for (int q = 0; q < 8; ++q) {
+                    const float4 bq = bsm[c * 8 + q];
+                    float e0 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 0]), two_c, alpha + bq.x));
+                    float e1 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 1]), two_c, alpha + bq.y));
+                    float e2 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 2]), two_c, alpha + bq.z));
+                    float e3 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 3]), two_c, alpha + bq.w));
+                    if (tile_has_diag) { // k(x_i, x_i) = exp(0) exactly, like the reference
+                        const int cb = c * 32 + 4 * q;
+                        if (dcol == cb) e0 = 32768.0f;
+                        if (dcol == cb + 1) e1 = 32768.0f;
+                        if (dcol == cb + 2) e2 = 32768.0f;
+                        if (dcol == cb + 3) e3 = 32768.0f;
+                    }
+                    packed[2 * q] = pack_f16x2(e0, e1);
+                    packed[2 * q + 1] = pack_f16x2(e2, e3);
+                }
+                // E chunk c overwrites S columns [16c, 16c+16), all of which this thread has already read
+                tmem_st16(tS + c * 16, packed);
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(e_ready + b);
+            mbar_arrive(e_ready + w);
+            mbar_arrive(r_empty + (t % TC_NBETA));
         }
-        if (b == 0 && ok) { // ---- flush Phi: TMEM -> global partial sums ------------------------------------
-            if (mbar_wait(phi_full, 0, p.err, 40)) {
-                tc_fence_after();
-                const bool valid = i < p.row0 + p.n_rows;
-                float *dst = p.phi_buf + i * TC_PHI_LD;
+        if (ok && mbar_wait(phi_full, 0, p.err, 40)) { // ---- flush Phi_w: TMEM -> global partial sums
+            tc_fence_after();
+            const bool valid = i < p.row0 + p.n_rows;
+            float *dst = p.phi_buf + i * TC_PHI_LD;
+            const uint32_t tP = tmem + 256 + w * TC_NVH + lane_base;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 16) {
-                    uint32_t hi[16], lo[16];
-                    tmem_ld16(tPhi + lane_base + c0, hi);
-                    tmem_ld16(tPhi + lane_base + TC_NVH + c0, lo);
-                    tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) atomicAdd(dst + c0 + q, (__uint_as_float(hi[q]) + __uint_as_float(lo[q])) * TC_E_UNSCALE);
-                    }
-                }
-                uint32_t rs[16];
-                tmem_ld16(tPhi + lane_base + TC_ONES_ROW, rs);
+            for (int c0 = 0; c0 < TC_NVH; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tP + c0, v);
                 tmem_ld_wait();
-                if (valid) atomicAdd(dst + TC_ONES_ROW, __uint_as_float(rs[0]) * TC_E_UNSCALE);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (c0 + q <= TC_ONES_ROW) atomicAdd(dst + c0 + q, __uint_as_float(v[q]) * TC_E_UNSCALE);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---- pairwise squared distances on the tensor cores, for the exact median --------------------------------
+// Same counting / collecting contract as dist_pass_f64_kernel (kernels_f64.cuh), on fp32 D2 = r_i + r_j - 2 S
+// with S from the bf16x3 contraction.  Keys are the IEEE bits of (double)D2, so the host-side bracket logic and
+// the radix select (select.cuh) are shared with the FP64 path; lo_f / hi_f are the float images of the key
+// bounds (d2 >= lo_f  <=>  (double)d2 >= lo).  rf[] holds +inf for padding rows, which therefore never count.
+// Layout as in phi_tc32_kernel: two i-tiles per CTA, one counting warpgroup each, TWO S buffers per warpgroup
+// (TMEM [256 w + 128 (t&1), +128)), X_j ring of 4 chunks, rf ring of 4 x 512 B.
+struct DistTcArgs {
+    const float *rf;       // [n_pad] |x~_j|^2, +inf beyond n
+    int64_t n_total, row0, n_rows;
+    int sym, n_jtiles, jsplit;
+    float lo_f, hi_f;
+    unsigned long long lo_key;
+    int shift;
+    unsigned long long *below, *max_below, *hist, *cand, *cand_count;
+    unsigned long long capacity;
+    int *err;
+};
+
+constexpr int TC_WBUF = 512; // candidate keys staged per warp
+constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NBETA * 512 + 8 * TC_WBUF * 8 + 8 * 4 + 512 + 1024;
+constexpr uint32_t TC_DIST_SMEM_HIST = TC_DIST_SMEM_BASE + HIST_BINS * 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(320, 1)
+dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, DistTcArgs p)
+{
+    const int ip = blockIdx.x / p.jsplit, js = blockIdx.x - ip * p.jsplit;
+    const int jfirst = p.sym ? 2 * ip : 0; // tile-level upper triangle when symmetric
+    const int len = p.n_jtiles - jfirst;
+    const int tps = (len + p.jsplit - 1) / p.jsplit;
+    const int jbeg = jfirst + js * tps;
+    const int nt = min(p.n_jtiles, jbeg + tps) - jbeg;
+    if (nt <= 0) return;
+    const int64_t i0 = p.row0 + (int64_t)ip * (2 * TC_TILE);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + 2 * TC_A_BYTES;
+    float *sR = (float *)(sB + TC_NB * TC_CHUNK);                     // [TC_NBETA][128]
+    unsigned long long *wbuf = (unsigned long long *)(sR + TC_NBETA * 128); // [8][TC_WBUF]
+    unsigned int *wcnt = (unsigned int *)(wbuf + 8 * TC_WBUF);        // [8]
+    uint64_t *bars = (uint64_t *)(wcnt + 8);
+    uint64_t *a_full = bars;
+    uint64_t *b_full = bars + 1;
+    uint64_t *b_empty = b_full + TC_NB;
+    uint64_t *s_full = b_empty + TC_NB;  // [2 wg][2 buf]
+    uint64_t *s_free = s_full + 4;       // [2 wg][2 buf]
+    uint64_t *r_full = s_free + 4;       // TC_NBETA
+    uint64_t *r_empty = r_full + TC_NBETA;
+    uint32_t *tmem_holder = (uint32_t *)(r_empty + TC_NBETA);
+    unsigned int *shist = (unsigned int *)(tmem_holder + 4); // [HIST_BINS] (MODE_HIST only)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < TC_NB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(s_free + s, 128); }
+        for (int s = 0; s < TC_NBETA; ++s) { mbar_init(r_full + s, 1); mbar_init(r_empty + s, 256); }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 8) wcnt[threadIdx.x] = 0u;
+    if (MODE == MODE_HIST)
+        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) shist[b] = 0u;
+    if (warp == 8) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp == 8) {
+        if (lane == 0) { // ---- TMA producer
+            mbar_arrive_expect_tx(a_full, 2 * TC_A_BYTES);
+            for (int w = 0; w < 2; ++w)
+                for (int c = 0; c < TC_KCH; ++c)
+                    tma_load_2d(sA + w * TC_A_BYTES + c * TC_CHUNK, &mapA, c * 64, (int)(i0 + w * TC_TILE), a_full);
+            bool ok = true;
+            for (int t = 0; ok && t < nt; ++t) {
+                const int j0 = (jbeg + t) * TC_TILE;
+                {
+                    const int rs = t % TC_NBETA, rph = (t / TC_NBETA) & 1;
+                    if (!mbar_wait(r_empty + rs, rph ^ 1, p.err, 52)) { ok = false; break; }
+                    mbar_arrive_expect_tx(r_full + rs, 512);
+                    bulk_load_1d(sR + rs * 128, p.rf + j0, 512, r_full + rs);
+                }
+                for (int c = 0; c < TC_KCH; ++c) {
+                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                    if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 50)) { ok = false; break; }
+                    mbar_arrive_expect_tx(b_full + slot, TC_CHUNK);
+                    tma_load_2d(sB + slot * TC_CHUNK, &mapB, c * 64, j0, b_full + slot);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) { // ---- MMA issuer: S_w(t) into buffer (w, t & 1)
+            const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
+            bool ok = mbar_wait(a_full, 0, p.err, 60);
+            for (int t = 0; ok && t < nt; ++t) {
+                const int buf = t & 1, bph = (t >> 1) & 1;
+                for (int w = 0; ok && w < 2; ++w) {
+                    if (!mbar_wait(s_free + 2 * w + buf, bph ^ 1, p.err, 62)) { ok = false; break; }
+#pragma unroll
+                    for (int c = 0; c < TC_KCH; ++c) {
+                        const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                        if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 61)) { ok = false; break; }
+                        if (c == 0) tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint64_t da = make_desc_k_sw128(smem_u32(sA + w * TC_A_BYTES + c * TC_CHUNK) + k * 32);
+                            uint64_t db = make_desc_k_sw128(smem_u32(sB + slot * TC_CHUNK) + k * 32);
+                            umma_bf16_ss(tmem + w * 256 + buf * 128, da, db, idesc_s, (c | k) ? 1u : 0u);
+                        }
+                        if (w == 1) umma_commit(b_empty + slot);
+                    }
+                    if (ok) umma_commit(s_full + 2 * w + buf);
+                }
+            }
+        }
+    } else { // ---- counting warpgroups: thread = row i
+        const int w = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int itile = 2 * ip + w;
+        const int64_t iw0 = i0 + w * TC_TILE;
+        const int64_t i = iw0 + row;
+        const float ri = (i < p.row0 + p.n_rows) ? p.rf[i] : INFINITY;
+        unsigned long long *mybuf = wbuf + warp * TC_WBUF;
+        unsigned int *mycnt = wcnt + warp;
+        unsigned long long below = 0ull;
+        float maxb = -1.0f;
+        const float lo = p.lo_f, hi = p.hi_f;
+        auto flush = [&]() { // warp-collective: move the staged keys to the global candidate list
+            __syncwarp();
+            const unsigned int n = min(*mycnt, (unsigned int)TC_WBUF);
+            unsigned long long base = 0ull;
+            if (lane == 0 && n) base = atomicAdd(p.cand_count, (unsigned long long)n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (unsigned int q = lane; q < n; q += 32)
+                if (base + q < p.capacity) p.cand[base + q] = mybuf[q];
+            __syncwarp();
+            if (lane == 0) *mycnt = 0u;
+            __syncwarp();
+        };
+        for (int t = 0; t < nt; ++t) {
+            const int buf = t & 1, bph = (t >> 1) & 1;
+            const int tj = jbeg + t;
+            const int64_t j0 = (int64_t)tj * TC_TILE;
+            // symmetric mode: tiles below the diagonal are covered by their transposes (weight 2)
+            const unsigned int wgt = !p.sym ? 1u : (tj < itile ? 0u : (tj == itile ? 1u : 2u));
+            const bool tile_has_diag = (j0 < iw0 + TC_TILE) && (j0 + TC_TILE > iw0);
+            const int64_t dcol = i - j0;
+            const float4 *rsm = reinterpret_cast<const float4 *>(sR + (t % TC_NBETA) * 128);
+            if (!mbar_wait(r_full + (t % TC_NBETA), (t / TC_NBETA) & 1, p.err, 72)) break;
+            if (!mbar_wait(s_full + 2 * w + buf, bph, p.err, 70 + w)) break;
+            tc_fence_after();
+            const uint32_t tS = tmem + w * 256 + buf * 128 + lane_base;
+            if (wgt == 0u) { // nothing to count: hand the buffers straight back
+                tc_fence_before();
+                mbar_arrive(s_free + 2 * w + buf);
+                mbar_arrive(r_empty + (t % TC_NBETA));
+                continue;
+            }
+            unsigned int cnt_below = 0;
+            uint32_t r[2][32];
+            tmem_ld32(tS, r[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c < 3) {
+                    tmem_ld32(tS + (c + 1) * 32, r[(c + 1) & 1]);
+                } else { // S is in registers: hand the buffer back to the MMA issuer
+                    tc_fence_before();
+                    mbar_arrive(s_free + 2 * w + buf);
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float4 r4 = rsm[c * 8 + (q >> 2)];
+                    const float rj = (q & 3) == 0 ? r4.x : (q & 3) == 1 ? r4.y : (q & 3) == 2 ? r4.z : r4.w;
+                    float d2 = fmaf(-2.0f, __uint_as_float(r[c & 1][q]), ri + rj);
+                    if (tile_has_diag && dcol == c * 32 + q) d2 = (ri < INFINITY) ? 0.0f : INFINITY; // |x_i - x_i|^2 = 0 exactly
+                    const bool is_below = d2 < lo;
+                    if (is_below) { ++cnt_below; maxb = fmaxf(maxb, d2); }
+                    if (!is_below && d2 < hi) { // rare: inside the bracket
+                        const unsigned long long key = (unsigned long long)__double_as_longlong((double)fmaxf(d2, 0.0f));
+                        if (MODE == MODE_HIST) {
+                            atomicAdd(&shist[(unsigned int)((key - p.lo_key) >> p.shift)], wgt);
+                        } else {
+                            const unsigned int pos = atomicAdd(mycnt, wgt);
+                            if (pos + wgt <= TC_WBUF) {
+                                mybuf[pos] = key;
+                                if (wgt == 2u) mybuf[pos + 1] = key;
+                            } else { // staging buffer full: reserve straight in the global list
+                                const unsigned long long g = atomicAdd(p.cand_count, (unsigned long long)wgt);
+                                if (g < p.capacity) p.cand[g] = key;
+                                if (wgt == 2u && g + 1 < p.capacity) p.cand[g + 1] = key;
+                            }
+                        }
+                    }
+                }
+                if (MODE == MODE_COLLECT) {
+                    __syncwarp();
+                    if (*mycnt > TC_WBUF / 2) flush();
+                }
+            }
+            below += (unsigned long long)cnt_below * wgt;
+            mbar_arrive(r_empty + (t % TC_NBETA));
+        }
+        if (MODE == MODE_COLLECT) flush();
+        unsigned long long maxb_key = maxb >= 0.0f ? (unsigned long long)__double_as_longlong((double)maxb) : 0ull;
+        for (int o = 16; o; o >>= 1) {
+            below += __shfl_xor_sync(0xffffffffu, below, o);
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, maxb_key, o);
+            maxb_key = other > maxb_key ? other : maxb_key;
+        }
+        if (lane == 0) {
+            if (below) atomicAdd(p.below, below);
+            if (maxb_key) atomicMax(p.max_below, maxb_key);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (MODE == MODE_HIST)
+        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) {
+            unsigned int c = shist[b];
+            if (c) atomicAdd(&p.hist[b], (unsigned long long)c);
+        }
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 

@@ -273,7 +273,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->colsum, 64 * 8));
     CU(cudaMalloc(&ctx->tc_err, 4));
     // rows of a tile may reach past the last rank-local row: keep a tile of slack
-    CU(cudaMalloc(&ctx->phi_buf, (np + 128) * TC_PHI_LD * 4));
+    CU(cudaMalloc(&ctx->phi_buf, (np + 256) * TC_PHI_LD * 4));
     CU(cudaMemsetAsync(ctx->XA, 0, np * TC_KTOT * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->XB, 0, np * TC_KTOT * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->VT, 0, (size_t)TC_NV * np * 2, ctx->stream));
@@ -281,7 +281,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream));
     TRY(make_bf16_map(ctx, &ctx->mapA, ctx->XA, np, TC_KTOT, 128));
     TRY(make_bf16_map(ctx, &ctx->mapB, ctx->XB, np, TC_KTOT, 128));
-    TRY(make_bf16_map(ctx, &ctx->mapV, ctx->VT, TC_NV, np, TC_NV));
+    TRY(make_bf16_map(ctx, &ctx->mapV, ctx->VT, TC_NV, np, TC_NVH));
     return SVGDB_OK;
 }
 #endif
@@ -348,8 +348,15 @@ size_t dist_smem_bytes(int d, bool hist)
     return (size_t)(2 * 64 * ldx + 128) * sizeof(double) + (hist ? HIST_BINS * sizeof(unsigned int) : 0);
 }
 
+#ifdef SVGDB_WITH_TC32
+int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift);
+#endif
+
 int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) return launch_dist_pass_tc32(ctx, mode, lo, hi, shift);
+#endif
     DistArgs a{};
     a.X = ctx->X[ctx->cur];
     a.r = ctx->r;
@@ -633,6 +640,60 @@ int launch_tc_split(svgdb_ctx *ctx)
     return SVGDB_OK;
 }
 
+// smallest float >= the double whose bits are `key` (+inf for keys past +inf)
+float key_to_float_ceil(uint64_t key)
+{
+    if (key >= 0x7FF0000000000000ull) return INFINITY;
+    double x;
+    std::memcpy(&x, &key, 8);
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
+{
+    using namespace svgdb::tc;
+    DistTcArgs a{};
+    a.rf = ctx->rf;
+    a.n_total = ctx->N;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.sym = ctx->world == 1 ? 1 : 0;
+    a.n_jtiles = (int)(ctx->n_pad128 / 128);
+    a.jsplit = std::max(1, std::min(8, a.n_jtiles / 8));
+    a.lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
+    a.hi_f = key_to_float_ceil(hi);
+    a.lo_key = lo;
+    a.shift = shift;
+    a.below = ctx->below;
+    a.max_below = ctx->max_below;
+    a.hist = ctx->hist;
+    a.cand = ctx->cand;
+    a.cand_count = ctx->cand_count;
+    a.capacity = ctx->capacity;
+    a.err = ctx->tc_err;
+    CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
+    const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
+    if (n_ipairs > 0) {
+        unsigned grid = (unsigned)(n_ipairs * a.jsplit);
+        if (mode == MODE_HIST) {
+            CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
+            dist_tc32_kernel<MODE_HIST><<<grid, 320, TC_DIST_SMEM_HIST, ctx->stream>>>(ctx->mapA, ctx->mapB, a);
+        } else {
+            CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
+            dist_tc32_kernel<MODE_COLLECT><<<grid, 320, TC_DIST_SMEM_BASE, ctx->stream>>>(ctx->mapA, ctx->mapB, a);
+        }
+        KERNEL_CHECK();
+    }
+    ++ctx->stats.median_passes;
+    TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
+    TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
+    if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
+    return SVGDB_OK;
+}
+
 int pick_jsplit(int n_itiles, int n_jtiles, int sms)
 {
     int best = 1;
@@ -654,7 +715,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
                                                                             ctx->d, ctx->VT, ctx->beta);
     KERNEL_CHECK();
-    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 128) * TC_PHI_LD * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, ctx->stream));
     PhiTcArgs a{};
     a.beta = ctx->beta;
     a.a_ptr = ctx->a_dev;
@@ -663,10 +724,10 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     a.row0 = ctx->row0;
     a.n_rows = ctx->n_rows;
     a.n_jtiles = (int)(ctx->n_pad128 / 128);
-    const int n_itiles = (int)((ctx->n_rows + 127) / 128);
-    a.jsplit = pick_jsplit(n_itiles, a.n_jtiles, ctx->sm_count);
+    const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
+    a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
     a.err = ctx->tc_err;
-    phi_tc32_kernel<<<(unsigned)(n_itiles * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
+    phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
     KERNEL_CHECK();
     ++ctx->stats.phi_launches;
     OptTcArgs o{};
@@ -723,7 +784,7 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx));
 #endif
-    TRY(launch_rownorm(ctx));
+    if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     prof_mark(ctx, 1);
     TRY(launch_grad(ctx));
@@ -833,6 +894,8 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         if (d > svgdb::tc::TC_D)
             return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
         CU(cudaFuncSetAttribute(svgdb::tc::phi_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_PHI_SMEM));
+        CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_HIST));
+        CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_BASE));
     }
 #endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
@@ -1068,7 +1131,10 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
     if (!ctx) return SVGDB_ERR_INVALID;
     if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
     CU(cudaSetDevice(ctx->device));
-    TRY(launch_rownorm(ctx));
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx));
+#endif
+    if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     double a = 0.0;
     CU(cudaMemcpyAsync(&a, ctx->a_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -16,7 +16,7 @@ namespace tc {
 // Development safety net: every spin on an mbarrier is bounded; on expiry the kernel records where it
 // was stuck and bails out instead of hanging the GPU.
 #ifndef SVGDB_SPIN_LIMIT
-#define SVGDB_SPIN_LIMIT (1u << 26)
+#define SVGDB_SPIN_LIMIT (1u << 22)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,8 +50,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // Returns false on timeout (and records `tag` in *err, first writer wins).
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err, int tag)
 {
-    for (uint32_t spin = 0; spin < SVGDB_SPIN_LIMIT; ++spin)
+    for (uint32_t spin = 0; spin < SVGDB_SPIN_LIMIT; ++spin) {
         if (mbar_try_wait(bar, parity)) return true;
+        // somebody else already gave up: do not serialise one timeout after another
+        if ((spin & 1023u) == 1023u && err && *reinterpret_cast<volatile int *>(err) != 0) return false;
+    }
     if (err) atomicCAS(err, 0, tag);
     return false;
 }

@@ -73,3 +73,25 @@ def test_tc32_rejects_large_dimension(sv):
     model = sv.MultivariateNormal(np.zeros(65), np.eye(65))
     with pytest.raises(sv.DimensionMismatchException):
         sv.SVGD(65, 1, x0, sv.GaussianRBFKernel(x0), model, sv.AdaGrad(65, 8, 0.1), precision=TC32)
+
+
+@pytest.mark.parametrize("capacity", [64, 4096])
+def test_tc32_median_narrowing_paths(sv, oracle, capacity, monkeypatch):
+    """Small candidate buffers force histogram narrowing, bracket prediction and tie handling on the
+    tensor-core distance pass; the scale must stay within 1e-5 of the FP64 oracle."""
+    monkeypatch.setenv("SVGDB_CAND_CAPACITY", str(capacity))
+    for n, d in [(200, 3), (700, 64), (1500, 16)]:
+        svgd, x0, mu, cov = _setup(sv, n, d, seed=n)
+        X = np.array(x0.T, order="C", copy=True)
+        a = svgd.ComputeScale()
+        a_ref = oracle.rbf_median_scale(X)
+        print("capacity=%d n=%d d=%d: a rel err %.3g" % (capacity, n, d, abs(a - a_ref) / a_ref))
+        assert abs(a - a_ref) <= 1e-5 * a_ref, (n, d)
+        svgd.Initialize()
+        svgd.Step(8)
+        ref = oracle.svgd_run(X, 8, mu, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
+        rms = np.sqrt(np.mean((x0.T - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+        st = svgd.Stats()
+        print("   8 steps: rms rel err %.3g, median passes %d, bracket hits %d" % (rms, st["median_passes"], st["median_bracket_hits"]))
+        assert rms < 1e-3
+        svgd.close()
