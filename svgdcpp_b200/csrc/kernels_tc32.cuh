@@ -264,18 +264,19 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
             const uint32_t idesc_v = make_idesc_f16(TC_TILE, TC_NVH);
             bool ok = mbar_wait(a_full, 0, p.err, 20);
+            const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB)), v_lo0 = desc_lo_k_sw128(smem_u32(sV));
             auto issue_s = [&](int w, int t) -> bool { // S_w(t) = X_iw . X_j^T
+                const uint32_t d = tmem + w * 128;
 #pragma unroll
                 for (int c = 0; c < TC_KCH; ++c) {
                     const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
                     if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 21)) return false;
                     if (w == 0 && c == 0) tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint64_t da = make_desc_k_sw128(smem_u32(sA + w * TC_A_BYTES + c * TC_CHUNK) + k * 32);
-                        uint64_t db = make_desc_k_sw128(smem_u32(sB + slot * TC_CHUNK) + k * 32);
-                        umma_bf16_ss(tmem + w * 128, da, db, idesc_s, (c | k) ? 1u : 0u);
-                    }
+                    const uint32_t al = a_lo0 + ((w * TC_A_BYTES + c * TC_CHUNK) >> 4), bl = b_lo0 + slot * (TC_CHUNK >> 4);
+                    if (c == 0) umma_f16_ss2<false>(d, al, bl, idesc_s); else umma_f16_ss2<true>(d, al, bl, idesc_s);
+                    umma_f16_ss2<true>(d, al + 2, bl + 2, idesc_s);
+                    umma_f16_ss2<true>(d, al + 4, bl + 4, idesc_s);
+                    umma_f16_ss2<true>(d, al + 6, bl + 6, idesc_s);
                     if (w == 1) umma_commit(b_empty + slot); // both i-tiles have consumed this chunk
                 }
                 umma_commit(s_full + w);
@@ -283,16 +284,17 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             };
             auto issue_pv = [&](int w, int t) -> bool { // Phi_w += E_w(t) . [v_hi ; v_lo]
                 if (!mbar_wait(e_ready + w, t & 1, p.err, 22 + w)) return false;
+                const uint32_t d = tmem + 256 + w * TC_NVH, e = tmem + w * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
                     if (w == 0 && !mbar_wait(v_full + slot, ph, p.err, 24)) return false;
                     if (c == 0) tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint64_t db = make_desc_k_sw128(smem_u32(sV + slot * TC_VCHUNK) + k * 32);
-                        umma_bf16_ts(tmem + 256 + w * TC_NVH, tmem + w * 128 + ((c & 1) * 4 + k) * 8, db, idesc_v, (t | c | k) ? 1u : 0u);
-                    }
+                    const uint32_t vl = v_lo0 + slot * (TC_VCHUNK >> 4), ea = e + (c & 1) * 32;
+                    if (c == 0) umma_f16_ts2r(d, ea, vl, idesc_v, t ? 1u : 0u); else umma_f16_ts2<true>(d, ea, vl, idesc_v);
+                    umma_f16_ts2<true>(d, ea + 8, vl + 2, idesc_v);
+                    umma_f16_ts2<true>(d, ea + 16, vl + 4, idesc_v);
+                    umma_f16_ts2<true>(d, ea + 24, vl + 6, idesc_v);
                     if (w == 1) umma_commit(v_empty + slot);
                 }
                 return true;
@@ -324,20 +326,16 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (!mbar_wait(r_full + (t % TC_NBETA), (t / TC_NBETA) & 1, p.err, 32)) { ok = false; break; }
             if (!mbar_wait(s_full + w, t & 1, p.err, 30 + w)) { ok = false; break; }
             tc_fence_after();
-            uint32_t r[2][32];
-            tmem_ld32(tS, r[0]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                if (c < 3) tmem_ld32(tS + (c + 1) * 32, r[(c + 1) & 1]); // overlaps the math on chunk c
+            // 32-column chunk c: exponentials of rr[] -> fp16 pairs over S columns [16c, 16c+16) (already read)
+            auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
                 uint32_t packed[16];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 bq = bsm[c * 8 + q];
-                    float e0 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 0]), two_c, alpha + bq.x));
-                    float e1 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 1]), two_c, alpha + bq.y));
-                    float e2 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 2]), two_c, alpha + bq.z));
-                    float e3 = ex2_approx(fmaf(__uint_as_float(r[c & 1][4 * q + 3]), two_c, alpha + bq.w));
+                    float e0 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 0]), two_c, alpha + bq.x));
+                    float e1 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 1]), two_c, alpha + bq.y));
+                    float e2 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 2]), two_c, alpha + bq.z));
+                    float e3 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 3]), two_c, alpha + bq.w));
                     if (tile_has_diag) { // k(x_i, x_i) = exp(0) exactly, like the reference
                         const int cb = c * 32 + 4 * q;
                         if (dcol == cb) e0 = 32768.0f;
@@ -348,8 +346,18 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     packed[2 * q] = pack_f16x2(e0, e1);
                     packed[2 * q + 1] = pack_f16x2(e2, e3);
                 }
-                // E chunk c overwrites S columns [16c, 16c+16), all of which this thread has already read
                 tmem_st16(tS + c * 16, packed);
+            };
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tS, r0);
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                tmem_ld_wait();
+                tmem_ld32(tS + (2 * cc + 1) * 32, r1); // overlaps the math on the even chunk
+                exp_chunk(r0, 2 * cc);
+                tmem_ld_wait();
+                if (cc == 0) tmem_ld32(tS + 64, r0);
+                exp_chunk(r1, 2 * cc + 1);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -402,9 +410,39 @@ constexpr int TC_WBUF = 512; // candidate keys staged per warp
 constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NBETA * 512 + 8 * TC_WBUF * 8 + 8 * 4 + 512 + 1024;
 constexpr uint32_t TC_DIST_SMEM_HIST = TC_DIST_SMEM_BASE + HIST_BINS * 4;
 
+// Rare path, kept out of line so the counting loop stays small: eight distances of which at least one lies
+// inside the bracket.  Candidates go to the warp's staging buffer (smem atomic reservation), or straight to
+// the global list when that is full; in histogram mode they bump the shared histogram.
+template <int MODE>
+__device__ __noinline__ void dist_in_bracket8(float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7,
+                                              float lo, float hi, unsigned int wgt, unsigned int *mycnt,
+                                              unsigned long long *mybuf, unsigned int *shist, const DistTcArgs *p)
+{
+    const float dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+        const float v = dd[e];
+        if (v < lo || !(v < hi)) continue;
+        const unsigned long long key = (unsigned long long)__double_as_longlong((double)fmaxf(v, 0.0f));
+        if (MODE == MODE_HIST) {
+            atomicAdd(&shist[(unsigned int)((key - p->lo_key) >> p->shift)], wgt);
+        } else {
+            const unsigned int pos = atomicAdd(mycnt, wgt);
+            if (pos + wgt <= TC_WBUF) {
+                mybuf[pos] = key;
+                if (wgt == 2u) mybuf[pos + 1] = key;
+            } else {
+                const unsigned long long g = atomicAdd(p->cand_count, (unsigned long long)wgt);
+                if (g < p->capacity) p->cand[g] = key;
+                if (wgt == 2u && g + 1 < p->capacity) p->cand[g + 1] = key;
+            }
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(320, 1)
-dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, DistTcArgs p)
+dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ DistTcArgs p)
 {
     const int ip = blockIdx.x / p.jsplit, js = blockIdx.x - ip * p.jsplit;
     const int jfirst = p.sym ? 2 * ip : 0; // tile-level upper triangle when symmetric
@@ -477,21 +515,22 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (lane == 0) { // ---- MMA issuer: S_w(t) into buffer (w, t & 1)
             const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
             bool ok = mbar_wait(a_full, 0, p.err, 60);
+            const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB));
             for (int t = 0; ok && t < nt; ++t) {
                 const int buf = t & 1, bph = (t >> 1) & 1;
                 for (int w = 0; ok && w < 2; ++w) {
                     if (!mbar_wait(s_free + 2 * w + buf, bph ^ 1, p.err, 62)) { ok = false; break; }
+                    const uint32_t d = tmem + w * 256 + buf * 128;
 #pragma unroll
                     for (int c = 0; c < TC_KCH; ++c) {
                         const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
                         if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 61)) { ok = false; break; }
                         if (c == 0) tc_fence_after();
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint64_t da = make_desc_k_sw128(smem_u32(sA + w * TC_A_BYTES + c * TC_CHUNK) + k * 32);
-                            uint64_t db = make_desc_k_sw128(smem_u32(sB + slot * TC_CHUNK) + k * 32);
-                            umma_bf16_ss(tmem + w * 256 + buf * 128, da, db, idesc_s, (c | k) ? 1u : 0u);
-                        }
+                        const uint32_t al = a_lo0 + ((w * TC_A_BYTES + c * TC_CHUNK) >> 4), bl = b_lo0 + slot * (TC_CHUNK >> 4);
+                        if (c == 0) umma_f16_ss2<false>(d, al, bl, idesc_s); else umma_f16_ss2<true>(d, al, bl, idesc_s);
+                        umma_f16_ss2<true>(d, al + 2, bl + 2, idesc_s);
+                        umma_f16_ss2<true>(d, al + 4, bl + 4, idesc_s);
+                        umma_f16_ss2<true>(d, al + 6, bl + 6, idesc_s);
                         if (w == 1) umma_commit(b_empty + slot);
                     }
                     if (ok) umma_commit(s_full + 2 * w + buf);
@@ -543,46 +582,45 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 continue;
             }
             unsigned int cnt_below = 0;
-            uint32_t r[2][32];
-            tmem_ld32(tS, r[0]);
+            auto count_chunk = [&](const uint32_t (&rr)[32], int c) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                if (c < 3) {
-                    tmem_ld32(tS + (c + 1) * 32, r[(c + 1) & 1]);
-                } else { // S is in registers: hand the buffer back to the MMA issuer
-                    tc_fence_before();
-                    mbar_arrive(s_free + 2 * w + buf);
-                }
+                for (int g = 0; g < 4; ++g) {
+                    float dd[8];
+                    bool any = false;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float4 r4 = rsm[c * 8 + (q >> 2)];
-                    const float rj = (q & 3) == 0 ? r4.x : (q & 3) == 1 ? r4.y : (q & 3) == 2 ? r4.z : r4.w;
-                    float d2 = fmaf(-2.0f, __uint_as_float(r[c & 1][q]), ri + rj);
-                    if (tile_has_diag && dcol == c * 32 + q) d2 = (ri < INFINITY) ? 0.0f : INFINITY; // |x_i - x_i|^2 = 0 exactly
-                    const bool is_below = d2 < lo;
-                    if (is_below) { ++cnt_below; maxb = fmaxf(maxb, d2); }
-                    if (!is_below && d2 < hi) { // rare: inside the bracket
-                        const unsigned long long key = (unsigned long long)__double_as_longlong((double)fmaxf(d2, 0.0f));
-                        if (MODE == MODE_HIST) {
-                            atomicAdd(&shist[(unsigned int)((key - p.lo_key) >> p.shift)], wgt);
-                        } else {
-                            const unsigned int pos = atomicAdd(mycnt, wgt);
-                            if (pos + wgt <= TC_WBUF) {
-                                mybuf[pos] = key;
-                                if (wgt == 2u) mybuf[pos + 1] = key;
-                            } else { // staging buffer full: reserve straight in the global list
-                                const unsigned long long g = atomicAdd(p.cand_count, (unsigned long long)wgt);
-                                if (g < p.capacity) p.cand[g] = key;
-                                if (wgt == 2u && g + 1 < p.capacity) p.cand[g + 1] = key;
-                            }
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const int q = g * 8 + e;
+                        const float4 r4 = rsm[c * 8 + (q >> 2)];
+                        const float rj = (q & 3) == 0 ? r4.x : (q & 3) == 1 ? r4.y : (q & 3) == 2 ? r4.z : r4.w;
+                        float d2 = fmaf(-2.0f, __uint_as_float(rr[q]), ri + rj);
+                        if (tile_has_diag && dcol == c * 32 + q) d2 = (ri < INFINITY) ? 0.0f : INFINITY; // |x_i - x_i|^2 = 0 exactly
+                        const bool is_below = d2 < lo;
+                        if (is_below) { ++cnt_below; maxb = fmaxf(maxb, d2); }
+                        any |= (!is_below && d2 < hi);
+                        dd[e] = d2;
                     }
+                    if (any) dist_in_bracket8<MODE>(dd[0], dd[1], dd[2], dd[3], dd[4], dd[5], dd[6], dd[7], lo, hi, wgt, mycnt, mybuf, shist, &p);
                 }
                 if (MODE == MODE_COLLECT) {
                     __syncwarp();
                     if (*mycnt > TC_WBUF / 2) flush();
                 }
+            };
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tS, r0);
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                tmem_ld_wait();
+                tmem_ld32(tS + (2 * cc + 1) * 32, r1);
+                count_chunk(r0, 2 * cc);
+                tmem_ld_wait();
+                if (cc == 0) {
+                    tmem_ld32(tS + 64, r0);
+                } else { // S is in registers: hand the buffer back to the MMA issuer
+                    tc_fence_before();
+                    mbar_arrive(s_free + 2 * w + buf);
+                }
+                count_chunk(r1, 2 * cc + 1);
             }
             below += (unsigned long long)cnt_below * wgt;
             mbar_arrive(r_empty + (t % TC_NBETA));

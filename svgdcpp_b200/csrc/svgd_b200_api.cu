@@ -113,13 +113,17 @@ struct svgdb_ctx {
 
     // median machinery
     unsigned long long *below = nullptr, *max_below = nullptr, *hist = nullptr, *cand = nullptr, *cand_count = nullptr;
-    uint64_t capacity = 1ull << 24;
+    uint64_t capacity = 1ull << 25;
     SelectState *sel = nullptr;
     MedianResult *medres = nullptr;
     HostScratch *hs = nullptr;
+    // bracket prediction for the next median: quadratic extrapolation of the last medians of D2
+    int n_hist = 0;              // valid entries of med_hist (most recent first)
+    double med_hist[3] = {0.0, 0.0, 0.0};
+    double delta = 0.0;          // relative half-width of the predicted bracket
+    double resid[2] = {0.0, 0.0}; // recent relative prediction errors
+    double last_pred = 0.0;
     bool have_pred = false;
-    double pred_d2_lo = 0.0, pred_d2_hi = 0.0, delta = 0.0;
-    int skip_pred = 0, miss_streak = 0;
 
     // tensor-core path (SVGDB_PRECISION_TC32)
     int64_t n_pad128 = 0;
@@ -472,10 +476,18 @@ int median_scale(svgdb_ctx *ctx)
     bool collected = false;
     uint64_t mid = 0;
 
-    // 1) predicted bracket around the previous iteration's median (one pass when it holds)
-    if (ctx->have_pred && ctx->skip_pred == 0 && total > ctx->capacity) {
-        double plo = ctx->pred_d2_lo * (1.0 - ctx->delta), phi = ctx->pred_d2_hi * (1.0 + ctx->delta);
-        uint64_t klo = key_of(std::max(plo, 0.0)), khi = key_of(phi) + 1;
+    // 1) predicted bracket (one pass when it holds): the median of D2 moves smoothly from step to step, so it is
+    //    extrapolated (up to quadratically) from the last medians; the bracket half-width follows the recent
+    //    extrapolation error and is capped by what the candidate buffer can hold.  The prediction is only a hint:
+    //    the exact counts returned by the pass decide whether it held.
+    const double delta_max = std::min(0.0625, (double)ctx->capacity / (10.0 * (double)total));
+    double predicted = 0.0;
+    if (ctx->n_hist > 0 && total > ctx->capacity) {
+        const double *m = ctx->med_hist;
+        predicted = ctx->n_hist >= 3 ? 3.0 * m[0] - 3.0 * m[1] + m[2] : ctx->n_hist == 2 ? 2.0 * m[0] - m[1] : m[0];
+        if (!(predicted > 0.0) || !std::isfinite(predicted)) predicted = m[0];
+        const double dl = std::min(delta_max, std::max(ctx->delta, 2e-5));
+        uint64_t klo = key_of(std::max(predicted * (1.0 - dl), 0.0)), khi = key_of(predicted * (1.0 + dl)) + 1;
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
         TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
         uint64_t b = ctx->hs->below;
@@ -483,19 +495,11 @@ int median_scale(svgdb_ctx *ctx)
         if (hit) {
             lo = klo; hi = khi; below_known = b; collected = true;
             ++ctx->stats.median_bracket_hits;
-            ctx->miss_streak = 0;
-            // proportional control: aim for capacity/4 candidates
-            double target = (double)ctx->capacity / 4.0;
-            ctx->delta = std::min(0.0625, std::max(1e-9, ctx->delta * target / (double)std::max<uint64_t>(mid, 1)));
         } else {
-            ++ctx->miss_streak;
-            ctx->skip_pred = std::min(64, 1 << std::min(ctx->miss_streak, 6)) - 1;
-            if (mid <= ctx->capacity) ctx->delta = std::min(0.0625, ctx->delta * 4.0);
-            else ctx->delta *= 0.25;
+            ctx->delta = std::min(delta_max, std::max(ctx->delta, 2e-5) * 4.0);
         }
-    } else if (ctx->skip_pred > 0) {
-        --ctx->skip_pred;
     }
+    ctx->last_pred = predicted;
 
     // 2) radix narrowing on the key bits until the bracket fits the candidate buffer
     if (!collected) {
@@ -536,11 +540,21 @@ int median_scale(svgdb_ctx *ctx)
     CU(cudaMemcpyAsync(&ctx->hs->med, ctx->medres, sizeof(MedianResult), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.last_scale = ctx->hs->med.scale;
-    ctx->pred_d2_lo = ctx->hs->med.d2_lo;
-    ctx->pred_d2_hi = ctx->hs->med.d2_hi;
-    if (!ctx->have_pred) {
-        ctx->have_pred = true;
-        ctx->delta = std::min(0.0625, std::max(1e-9, (double)ctx->capacity / (40.0 * (double)total)));
+    {
+        const double m_now = 0.5 * (ctx->hs->med.d2_lo + ctx->hs->med.d2_hi);
+        if (ctx->last_pred > 0.0 && m_now > 0.0) {
+            ctx->resid[1] = ctx->resid[0];
+            ctx->resid[0] = std::fabs(m_now - ctx->last_pred) / m_now;
+            // 4x the worse of the two most recent extrapolation errors, never below 2e-5
+            ctx->delta = std::min(delta_max, std::max(2e-5, 4.0 * std::max(ctx->resid[0], ctx->resid[1])));
+        } else {
+            ctx->delta = std::min(delta_max, 1e-3);
+        }
+        ctx->med_hist[2] = ctx->med_hist[1];
+        ctx->med_hist[1] = ctx->med_hist[0];
+        ctx->med_hist[0] = m_now;
+        ctx->n_hist = std::min(3, ctx->n_hist + 1);
+        if (!(m_now > 0.0) || !std::isfinite(m_now)) ctx->n_hist = 0;
     }
     return SVGDB_OK;
 }
@@ -694,16 +708,18 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     return SVGDB_OK;
 }
 
-int pick_jsplit(int n_itiles, int n_jtiles, int sms)
+// Split of the j range so that (i-pairs x splits) fills the SMs in whole waves: minimise
+// waves * (tiles per unit * t_tile + per-unit prologue/flush), both in tensor-pipe cycles.
+int pick_jsplit(int n_units_i, int n_jtiles, int sms)
 {
     int best = 1;
-    double best_eff = 0.0;
+    double best_cost = 1e300;
     for (int s = 1; s <= std::min(n_jtiles, 64); ++s) {
-        long units = (long)n_itiles * s;
+        long units = (long)n_units_i * s;
         long waves = (units + sms - 1) / sms;
-        double eff = (double)units / (double)(waves * sms);
-        if (n_jtiles / s < 4 && s > 1) break; // keep at least a few tiles per unit
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+        long tiles = (n_jtiles + s - 1) / s;
+        double cost = (double)waves * ((double)tiles * 1400.0 + 8000.0);
+        if (cost < best_cost * 0.98) { best_cost = cost; best = s; }
     }
     return best;
 }
@@ -965,7 +981,7 @@ int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique
     }
     ctx->world = world;
     ctx->rank = rank;
-    ctx->have_pred = false;
+    ctx->n_hist = 0;
     TRY(alloc_sharded(ctx));
     CU(cudaStreamSynchronize(ctx->stream));
     return SVGDB_OK;

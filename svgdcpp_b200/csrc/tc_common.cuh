@@ -118,6 +118,41 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
                  ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
+// Variants taking the 64-bit shared-memory descriptors as (lo, hi) register pairs: the issuing thread keeps
+// the constant hi word and advances only the 14-bit start-address field in lo (one integer add per MMA).
+__device__ __forceinline__ uint32_t desc_lo_k_sw128(uint32_t smem_addr) { return (smem_addr >> 4) & 0x3FFFu; }
+constexpr uint32_t DESC_HI_K_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29); // SBO = 1024 B, version 1, SWIZZLE_128B
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+                 "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI_K_SW128), "r"(idesc), "r"(ACC ? 1u : 0u)
+                 : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(DESC_HI_K_SW128), "r"(idesc), "r"(ACC ? 1u : 0u)
+                 : "memory");
+}
+// same with a run-time accumulate flag
+__device__ __forceinline__ void umma_f16_ts2r(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(DESC_HI_K_SW128), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+
 // Arrives on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
