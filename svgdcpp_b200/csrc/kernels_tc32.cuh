@@ -46,14 +46,35 @@ __global__ void colsum_kernel(const double *__restrict__ X, int64_t n, int d, do
     if (k < d) atomicAdd(&sum[k], acc);
 }
 
-// one warp per particle: centred bf16 split into the A and B operand layouts, r = |x~|^2
-__global__ void split_kernel(const double *__restrict__ X, const double *__restrict__ colsum, int64_t n, int64_t n_pad, int d,
-                             __nv_bfloat16 *__restrict__ XA, __nv_bfloat16 *__restrict__ XB, double *__restrict__ rt,
-                             float *__restrict__ rf)
+// Three-term bf16 split of a scalar (24 significant bits): v ~= t0 + t1 + t2.
+__device__ __forceinline__ void split3_bf16(double v, __nv_bfloat16 &t0, __nv_bfloat16 &t1, __nv_bfloat16 &t2)
+{
+    t0 = __float2bfloat16_rn((float)v);
+    double rem = isfinite(__bfloat162float(t0)) ? v - (double)__bfloat162float(t0) : 0.0;
+    t1 = __float2bfloat16_rn((float)rem);
+    rem -= (double)__bfloat162float(t1);
+    t2 = __float2bfloat16_rn((float)rem);
+}
+
+// Operand rows for the tensor-core contractions, one warp per particle.  Both layouts are K = 3 x 64 bf16:
+//     A_i = [ sa*hi_i | sa*lo_i | u1 u2 u3 1 1 1 0.. ]        B_j = [ sb*hi_j | sb*lo_j | 1 1 1 w1 w2 w3 0.. ]
+// with y = scale * x~ = hi + lo (two bf16 terms) and the MMAs  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi + A_ex.B_ex
+// so that the accumulator IS the quantity the epilogue needs (no per-pair arithmetic left):
+//   MODE_DIST (scale = 1, sa = -2, sb = 1, u = w = |x~|^2):   S = |x~_i|^2 + |x~_j|^2 - 2 x~_i.x~_j = D2_ij
+//   MODE_PHI  (scale = sqrt(2c), sa = sb = 1, u = 15 - c r_i, w = -c r_j):   S = log2( 2^15 k(x_j, x_i) )
+// Padding rows (row >= n) get u = w = +inf in MODE_DIST (their distances never count) and zeros in MODE_PHI.
+enum { SPLIT_DIST = 0, SPLIT_PHI = 1 };
+__global__ void split_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
+                             int64_t n, int64_t n_rows_alloc, int d, int mode, __nv_bfloat16 *__restrict__ XA,
+                             __nv_bfloat16 *__restrict__ XB, double *__restrict__ rt)
 {
     int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     int lane = threadIdx.x & 31;
-    if (row >= n_pad) return;
+    if (row >= n_rows_alloc) return;
+    const double c = mode == SPLIT_PHI ? (*a_ptr) * 1.4426950408889634 : 0.0; // a log2(e)
+    const double scale = mode == SPLIT_PHI ? sqrt(2.0 * c) : 1.0;
+    const float sa = mode == SPLIT_PHI ? 1.0f : -2.0f;
+    __nv_bfloat16 *a = XA + row * TC_KTOT, *b = XB + row * TC_KTOT;
     double s = 0.0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -61,23 +82,44 @@ __global__ void split_kernel(const double *__restrict__ X, const double *__restr
         double xc = 0.0;
         if (row < n && k < d) xc = X[row * d + k] - colsum[k] / (double)n;
         s += xc * xc;
-        float xf = (float)xc;
-        __nv_bfloat16 hi = __float2bfloat16_rn(xf);
-        __nv_bfloat16 lo = __float2bfloat16_rn((float)(xc - (double)__bfloat162float(hi)));
-        __nv_bfloat16 *a = XA + row * TC_KTOT, *b = XB + row * TC_KTOT;
-        a[k] = hi; a[64 + k] = hi; a[128 + k] = lo;
-        b[k] = hi; b[64 + k] = lo; b[128 + k] = hi;
+        const double y = scale * xc;
+        __nv_bfloat16 hi = __float2bfloat16_rn((float)y);
+        __nv_bfloat16 lo = __float2bfloat16_rn((float)(y - (double)__bfloat162float(hi)));
+        a[k] = __float2bfloat16_rn(sa * __bfloat162float(hi)); // exact: a power-of-two multiple
+        a[64 + k] = __float2bfloat16_rn(sa * __bfloat162float(lo));
+        b[k] = hi;
+        b[64 + k] = lo;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) { rt[row] = s; rf[row] = row < n ? (float)s : INFINITY; }
+    if (lane == 0 && mode == SPLIT_DIST) rt[row] = s;
+    // the 16 extra K columns (the remaining 48 of the chunk are never contracted, but keep them defined)
+    double u, w;
+    if (mode == SPLIT_DIST) { u = w = (row < n) ? s : (double)INFINITY; }
+    else { u = (row < n) ? 15.0 - c * s : 0.0; w = (row < n) ? -c * s : 0.0; }
+    __nv_bfloat16 u0, u1, u2, w0, w1, w2;
+    split3_bf16(u, u0, u1, u2);
+    split3_bf16(w, w0, w1, w2);
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int k = lane + 32 * h;
+        __nv_bfloat16 av = zero, bv = zero;
+        if (k == 0) { av = u0; bv = one; }
+        if (k == 1) { av = u1; bv = one; }
+        if (k == 2) { av = u2; bv = one; }
+        if (k == 3) { av = one; bv = w0; }
+        if (k == 4) { av = one; bv = w1; }
+        if (k == 5) { av = one; bv = w2; }
+        a[128 + k] = av;
+        b[128 + k] = bv;
+    }
 }
 
-// V^T (bf16, [TC_NV][ldn]) and beta = -a log2(e) r from the FP64 V = G - 2 a X (uncentred) of all particles:
+// V^T (fp16, [TC_NV][ldn]) from the FP64 V = G - 2 a X (uncentred) of all particles:
 // v~ = V + 2 a mean.  One block = 64 particles, transposed through shared memory.
 __global__ void __launch_bounds__(256)
 make_vt_kernel(const double *__restrict__ V, const double *__restrict__ colsum, const double *__restrict__ rt,
-               const double *__restrict__ a_ptr, int64_t n, int64_t ldn, int d, __half *__restrict__ VT,
-               float *__restrict__ beta)
+               const double *__restrict__ a_ptr, int64_t n, int64_t ldn, int d, __half *__restrict__ VT)
 {
     __shared__ __half tile[TC_NV][64 + 2];
     const double a = *a_ptr;
@@ -99,10 +141,7 @@ make_vt_kernel(const double *__restrict__ V, const double *__restrict__ colsum, 
         tile[rr][jl] = __float2half_rn((rr == TC_ONES_ROW && j0 + jl < n) ? 1.f : 0.f);
         tile[TC_NVH + rr][jl] = __float2half_rn(0.f); // the lo block carries no ones row
     }
-    if (threadIdx.x < 64) {
-        int64_t j = j0 + threadIdx.x;
-        if (j < ldn) beta[j] = (j < n) ? (float)(-a * 1.4426950408889634 * rt[j]) : 0.f;
-    }
+    (void)rt;
     __syncthreads();
     for (int t = threadIdx.x; t < TC_NV * 64; t += blockDim.x) {
         int rr = t >> 6, jl = t & 63;
@@ -147,29 +186,35 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
 
 // ---- the fused pair-interaction kernel ---------------------------------------------------------------
 // One CTA owns TWO 128-row i-tiles (256 particles) and a range of 128-column j-tiles.  Warps 0-3 / 4-7 are the
-// exp warpgroups of i-tile 0 / 1 (thread = TMEM lane = row), warp 8 lane 0 is the TMA producer, warp 9 lane 0
-// issues every tcgen05.mma.  Both i-tiles contract against the same X_j / V_j tiles in shared memory, and the
-// MMA order  PV0(t) S0(t+1) PV1(t) S1(t+1)  gives each warpgroup a full  PV + S  window (~1400 tensor cycles) for
-// its 128x128 exponentials before the tensor pipe needs the result (FlashAttention-4 style ping-pong).
+// exp warpgroups of i-tile 0 / 1 (thread = TMEM lane = row), warp 8 is the TMA producer, warp 9 issues every
+// tcgen05.mma (both warp-uniform, one elected lane executes the instruction).  Both i-tiles contract against the
+// same X_j / V_j tiles in shared memory, and the MMA order  PV0(t) S0(t+1) PV1(t) S1(t+1)  gives each warpgroup
+// a full  PV + S  window for its 128x128 exponentials (FlashAttention-4 style ping-pong).
+// The accumulator of the first contraction already is log2(2^15 k(x_j,x_i)) (see split_kernel), so the exp stage
+// is one MUFU.EX2 per pair plus the fp16 pack.
 //   TMEM   S_w [128 w, +128) fp32;  E_w = fp16 pairs over the first 64 columns of S_w;  Phi_w [256 + 80 w, +80)
-//   smem   A_w 2 x 48 KB resident;  X_j ring 4 x 16 KB chunks (3 per tile);  V_j ring 6 x 10 KB chunks (4 per tile:
-//          hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128));  beta ring 4 x 512 B
+//   smem   A_w 2 x 48 KB resident (hi | lo | extra);  X_j ring 4 x 16 KB chunks (hi, lo, extra per tile);
+//          V_j ring 6 x 10 KB chunks (4 per tile: hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128))
 struct PhiTcArgs {
-    const float *beta;   // [n_pad] -c r_j (0 beyond n)
-    const double *a_ptr;
     float *phi_buf;      // [n_pad + 256][TC_PHI_LD], zeroed; partial sums are added atomically
     int64_t n_total, row0, n_rows;
     int n_jtiles, jsplit;
     int *err;
+    long long *trace; // optional timeline of CTA 0 (development aid): [role][tile][event] clock64 values
 };
+
+// trace slots: role 0 = MMA issuer, 1 = exp WG0 thread 0, 2 = exp WG1 thread 0; 8 events per tile, 64 tiles
+#define TC_TRACE(role, t, ev)                                                                      \
+    do {                                                                                           \
+        if (p.trace != nullptr && blockIdx.x == 0 && (t) < 64) p.trace[((role) * 64 + (t)) * 8 + (ev)] = clock64(); \
+    } while (0)
 
 constexpr uint32_t TC_CHUNK = 16384;                     // 128 rows x 128 B
 constexpr uint32_t TC_A_BYTES = TC_KCH * TC_CHUNK;       // one resident X_i tile
 constexpr int TC_NB = 4;                                 // X_j chunk ring
 constexpr uint32_t TC_VCHUNK = TC_NVH * 128;             // 80 rows x 128 B
 constexpr int TC_NVS = 6;                                // V chunk ring
-constexpr int TC_NBETA = 4;
-constexpr uint32_t TC_PHI_SMEM = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NVS * TC_VCHUNK + TC_NBETA * 512 + 512 + 1024;
+constexpr uint32_t TC_PHI_SMEM = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NVS * TC_VCHUNK + 512 + 1024;
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -177,11 +222,43 @@ __device__ __forceinline__ float ex2_approx(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void bulk_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+
+// S_w = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo + A_ex.B_ex for one i-tile: 13 MMAs (K = 16 each) issued by the elected
+// lane as the X_j chunks (ring slots q = 3t + {0: hi, 1: lo, 2: extra}) become available.
+template <class WaitFull, class Release>
+__device__ __forceinline__ bool issue_dist_mmas(uint32_t d, uint32_t a_lo, uint32_t b_lo0, uint32_t idesc, int t, bool wait_b, bool release_b,
+                                                WaitFull wait_full, Release release)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+    const uint32_t a_hi_d = a_lo, a_lo_d = a_lo + (TC_CHUNK >> 4), a_ex_d = a_lo + 2 * (TC_CHUNK >> 4);
+#pragma unroll
+    for (int c = 0; c < TC_KCH; ++c) {
+        const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+        if (wait_b && !wait_full(slot, ph)) return false;
+        if (c == 0) tc_fence_after();
+        const uint32_t bl = b_lo0 + slot * (TC_CHUNK >> 4);
+        if (elect_one()) {
+            if (c == 0) { // B_hi: against A_hi (starts the accumulation) and A_lo
+                umma_f16_ss2<false>(d, a_hi_d, bl, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 2, bl + 2, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 4, bl + 4, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 6, bl + 6, idesc);
+                umma_f16_ss2<true>(d, a_lo_d, bl, idesc);
+                umma_f16_ss2<true>(d, a_lo_d + 2, bl + 2, idesc);
+                umma_f16_ss2<true>(d, a_lo_d + 4, bl + 4, idesc);
+                umma_f16_ss2<true>(d, a_lo_d + 6, bl + 6, idesc);
+            } else if (c == 1) { // B_lo: against A_hi
+                umma_f16_ss2<true>(d, a_hi_d, bl, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 2, bl + 2, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 4, bl + 4, idesc);
+                umma_f16_ss2<true>(d, a_hi_d + 6, bl + 6, idesc);
+            } else { // 16 extra K columns: norms / exponent offsets
+                umma_f16_ss2<true>(d, a_ex_d, bl, idesc);
+            }
+            if (release_b) release(slot);
+        }
+        __syncwarp();
+    }
+    return true;
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -200,8 +277,7 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t *sA = smem;                              // [2][TC_A_BYTES]
     uint8_t *sB = sA + 2 * TC_A_BYTES;               // [TC_NB][TC_CHUNK]
     uint8_t *sV = sB + TC_NB * TC_CHUNK;             // [TC_NVS][TC_VCHUNK]
-    float *sBeta = (float *)(sV + TC_NVS * TC_VCHUNK); // [TC_NBETA][128]
-    uint64_t *bars = (uint64_t *)(sBeta + TC_NBETA * 128);
+    uint64_t *bars = (uint64_t *)(sV + TC_NVS * TC_VCHUNK);
     uint64_t *a_full = bars;                // 1
     uint64_t *b_full = bars + 1;            // TC_NB
     uint64_t *b_empty = b_full + TC_NB;     // TC_NB
@@ -210,9 +286,7 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t *s_full = v_empty + TC_NVS;    // 2
     uint64_t *e_ready = s_full + 2;         // 2
     uint64_t *phi_full = e_ready + 2;       // 1
-    uint64_t *r_full = phi_full + 1;        // TC_NBETA  (beta tile landed)
-    uint64_t *r_empty = r_full + TC_NBETA;  // TC_NBETA  (all 256 exp threads are done with it)
-    uint32_t *tmem_holder = (uint32_t *)(r_empty + TC_NBETA);
+    uint32_t *tmem_holder = (uint32_t *)(phi_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -220,7 +294,6 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int s = 0; s < TC_NB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < TC_NVS; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 128); }
-        for (int s = 0; s < TC_NBETA; ++s) { mbar_init(r_full + s, 1); mbar_init(r_empty + s, 256); }
         mbar_init(phi_full, 1);
         fence_barrier_init();
     }
@@ -230,84 +303,83 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 8) {
-        if (lane == 0) { // ---- TMA producer ------------------------------------------------------------------
+    if (warp == 8) { // ---- TMA producer: the whole warp runs the loop (uniform registers), one elected lane issues
+        if (elect_one()) {
             mbar_arrive_expect_tx(a_full, 2 * TC_A_BYTES);
             for (int w = 0; w < 2; ++w)
                 for (int c = 0; c < TC_KCH; ++c)
                     tma_load_2d(sA + w * TC_A_BYTES + c * TC_CHUNK, &mapA, c * 64, (int)(i0 + w * TC_TILE), a_full);
-            bool ok = true;
-            for (int t = 0; ok && t < nt; ++t) {
-                const int j0 = (jbeg + t) * TC_TILE;
-                {
-                    const int rs = t % TC_NBETA, rph = (t / TC_NBETA) & 1;
-                    if (!mbar_wait(r_empty + rs, rph ^ 1, p.err, 12)) { ok = false; break; }
-                    mbar_arrive_expect_tx(r_full + rs, 512);
-                    bulk_load_1d(sBeta + rs * 128, p.beta + j0, 512, r_full + rs);
-                }
-                for (int c = 0; ok && c < TC_KCH; ++c) {
-                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
-                    if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 10)) { ok = false; break; }
+        }
+        __syncwarp();
+        bool ok = true;
+        for (int t = 0; ok && t < nt; ++t) {
+            const int j0 = (jbeg + t) * TC_TILE;
+            for (int c = 0; ok && c < TC_KCH; ++c) {
+                const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 10)) { ok = false; break; }
+                if (elect_one()) {
                     mbar_arrive_expect_tx(b_full + slot, TC_CHUNK);
                     tma_load_2d(sB + slot * TC_CHUNK, &mapB, c * 64, j0, b_full + slot);
                 }
-                for (int c = 0; ok && c < 4; ++c) {
-                    const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
-                    if (!mbar_wait(v_empty + slot, ph ^ 1, p.err, 11)) { ok = false; break; }
+                __syncwarp();
+            }
+            for (int c = 0; ok && c < 4; ++c) {
+                const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
+                if (!mbar_wait(v_empty + slot, ph ^ 1, p.err, 11)) { ok = false; break; }
+                if (elect_one()) {
                     mbar_arrive_expect_tx(v_full + slot, TC_VCHUNK);
                     tma_load_2d(sV + slot * TC_VCHUNK, &mapV, j0 + (c & 1) * 64, (c >> 1) * TC_NVH, v_full + slot);
                 }
+                __syncwarp();
             }
         }
-    } else if (warp == 9) {
-        if (lane == 0) { // ---- MMA issuer ----------------------------------------------------------------------
-            const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
-            const uint32_t idesc_v = make_idesc_f16(TC_TILE, TC_NVH);
-            bool ok = mbar_wait(a_full, 0, p.err, 20);
-            const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB)), v_lo0 = desc_lo_k_sw128(smem_u32(sV));
-            auto issue_s = [&](int w, int t) -> bool { // S_w(t) = X_iw . X_j^T
-                const uint32_t d = tmem + w * 128;
+    } else if (warp == 9) { // ---- MMA issuer: warp-uniform control flow, tcgen05 instructions from one elected lane
+        const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
+        const uint32_t idesc_v = make_idesc_f16(TC_TILE, TC_NVH);
+        bool ok = mbar_wait(a_full, 0, p.err, 20);
+        const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB)), v_lo0 = desc_lo_k_sw128(smem_u32(sV));
+        auto issue_s = [&](int w, int t) -> bool { // S_w(t)
+            bool r = issue_dist_mmas(tmem + w * 128, a_lo0 + w * (TC_A_BYTES >> 4), b_lo0, idesc_s, t, w == 0, w == 1,
+                                     [&](int slot, int ph) { return mbar_wait(b_full + slot, ph, p.err, 21); },
+                                     [&](int slot) { umma_commit(b_empty + slot); });
+            if (r && elect_one()) umma_commit(s_full + w);
+            __syncwarp();
+            return r;
+        };
+        auto issue_pv = [&](int w, int t) -> bool { // Phi_w += E_w(t) . [v_hi ; v_lo]
+            if (!mbar_wait(e_ready + w, t & 1, p.err, 22 + w)) return false;
+            const uint32_t d = tmem + 256 + w * TC_NVH, e = tmem + w * 128;
 #pragma unroll
-                for (int c = 0; c < TC_KCH; ++c) {
-                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
-                    if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 21)) return false;
-                    if (w == 0 && c == 0) tc_fence_after();
-                    const uint32_t al = a_lo0 + ((w * TC_A_BYTES + c * TC_CHUNK) >> 4), bl = b_lo0 + slot * (TC_CHUNK >> 4);
-                    if (c == 0) umma_f16_ss2<false>(d, al, bl, idesc_s); else umma_f16_ss2<true>(d, al, bl, idesc_s);
-                    umma_f16_ss2<true>(d, al + 2, bl + 2, idesc_s);
-                    umma_f16_ss2<true>(d, al + 4, bl + 4, idesc_s);
-                    umma_f16_ss2<true>(d, al + 6, bl + 6, idesc_s);
-                    if (w == 1) umma_commit(b_empty + slot); // both i-tiles have consumed this chunk
-                }
-                umma_commit(s_full + w);
-                return true;
-            };
-            auto issue_pv = [&](int w, int t) -> bool { // Phi_w += E_w(t) . [v_hi ; v_lo]
-                if (!mbar_wait(e_ready + w, t & 1, p.err, 22 + w)) return false;
-                const uint32_t d = tmem + 256 + w * TC_NVH, e = tmem + w * 128;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
-                    if (w == 0 && !mbar_wait(v_full + slot, ph, p.err, 24)) return false;
-                    if (c == 0) tc_fence_after();
-                    const uint32_t vl = v_lo0 + slot * (TC_VCHUNK >> 4), ea = e + (c & 1) * 32;
+            for (int c = 0; c < 4; ++c) {
+                const int q = 4 * t + c, slot = q % TC_NVS, ph = (q / TC_NVS) & 1;
+                if (w == 0 && !mbar_wait(v_full + slot, ph, p.err, 24)) return false;
+                if (c == 0) tc_fence_after();
+                const uint32_t vl = v_lo0 + slot * (TC_VCHUNK >> 4), ea = e + (c & 1) * 32;
+                if (elect_one()) {
                     if (c == 0) umma_f16_ts2r(d, ea, vl, idesc_v, t ? 1u : 0u); else umma_f16_ts2<true>(d, ea, vl, idesc_v);
                     umma_f16_ts2<true>(d, ea + 8, vl + 2, idesc_v);
                     umma_f16_ts2<true>(d, ea + 16, vl + 4, idesc_v);
                     umma_f16_ts2<true>(d, ea + 24, vl + 6, idesc_v);
                     if (w == 1) umma_commit(v_empty + slot);
                 }
-                return true;
-            };
-            if (ok) ok = issue_s(0, 0) && issue_s(1, 0);
-            for (int t = 0; ok && t < nt; ++t) {
-                ok = issue_pv(0, t);
-                if (ok && t + 1 < nt) ok = issue_s(0, t + 1);
-                if (ok) ok = issue_pv(1, t);
-                if (ok && t + 1 < nt) ok = issue_s(1, t + 1);
+                __syncwarp();
             }
-            if (ok) umma_commit(phi_full);
+            return true;
+        };
+        if (ok) ok = issue_s(0, 0) && issue_s(1, 0);
+        for (int t = 0; ok && t < nt; ++t) {
+            if (lane == 0) TC_TRACE(0, t, 0);
+            ok = issue_pv(0, t);
+            if (lane == 0) TC_TRACE(0, t, 1);
+            if (ok && t + 1 < nt) ok = issue_s(0, t + 1);
+            if (lane == 0) TC_TRACE(0, t, 2);
+            if (ok) ok = issue_pv(1, t);
+            if (lane == 0) TC_TRACE(0, t, 3);
+            if (ok && t + 1 < nt) ok = issue_s(1, t + 1);
+            if (lane == 0) TC_TRACE(0, t, 4);
         }
+        if (ok && elect_one()) umma_commit(phi_full);
+        __syncwarp();
     } else { // ---- exp warpgroups ------------------------------------------------------------------------------
         const int w = warp >> 2;
         const int row = (warp & 3) * 32 + lane;
@@ -315,36 +387,31 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t tS = tmem + w * 128 + lane_base;
         const int64_t iw0 = i0 + w * TC_TILE;
         const int64_t i = iw0 + row;
-        const float alpha = ((i < p.n_total) ? p.beta[i] : 0.f) + TC_E_SCALE_LOG2;
-        const float two_c = (float)(2.0 * (*p.a_ptr) * 1.4426950408889634);
         bool ok = true;
         for (int t = 0; ok && t < nt; ++t) {
             const int64_t j0 = (int64_t)(jbeg + t) * TC_TILE;
-            const int64_t dcol = i - j0; // column of k(x_i, x_i) in this tile, if inside [0,128)
+            const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this tile, if inside [0,128)
             const bool tile_has_diag = (j0 < iw0 + TC_TILE) && (j0 + TC_TILE > iw0);
-            const float4 *bsm = reinterpret_cast<const float4 *>(sBeta + (t % TC_NBETA) * 128);
-            if (!mbar_wait(r_full + (t % TC_NBETA), (t / TC_NBETA) & 1, p.err, 32)) { ok = false; break; }
+            if (row == 0) TC_TRACE(1 + w, t, 1);
             if (!mbar_wait(s_full + w, t & 1, p.err, 30 + w)) { ok = false; break; }
+            if (row == 0) TC_TRACE(1 + w, t, 2);
             tc_fence_after();
             // 32-column chunk c: exponentials of rr[] -> fp16 pairs over S columns [16c, 16c+16) (already read)
             auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
                 uint32_t packed[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bq = bsm[c * 8 + q];
-                    float e0 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 0]), two_c, alpha + bq.x));
-                    float e1 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 1]), two_c, alpha + bq.y));
-                    float e2 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 2]), two_c, alpha + bq.z));
-                    float e3 = ex2_approx(fmaf(__uint_as_float(rr[4 * q + 3]), two_c, alpha + bq.w));
-                    if (tile_has_diag) { // k(x_i, x_i) = exp(0) exactly, like the reference
-                        const int cb = c * 32 + 4 * q;
-                        if (dcol == cb) e0 = 32768.0f;
-                        if (dcol == cb + 1) e1 = 32768.0f;
-                        if (dcol == cb + 2) e2 = 32768.0f;
-                        if (dcol == cb + 3) e3 = 32768.0f;
+                for (int q = 0; q < 16; ++q) {
+                    float e0 = ex2_approx(__uint_as_float(rr[2 * q]));
+                    float e1 = ex2_approx(__uint_as_float(rr[2 * q + 1]));
+                    packed[q] = pack_f16x2(e0, e1);
+                }
+                if (tile_has_diag) { // k(x_i, x_i) = exp(0) exactly, like the reference: fp16(2^15) = 0x7800
+                    const int q = dcol - c * 32;
+                    if (q >= 0 && q < 32) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)
+                            if ((q >> 1) == u) packed[u] = (q & 1) ? ((packed[u] & 0x0000FFFFu) | 0x78000000u) : ((packed[u] & 0xFFFF0000u) | 0x00007800u);
                     }
-                    packed[2 * q] = pack_f16x2(e0, e1);
-                    packed[2 * q + 1] = pack_f16x2(e2, e3);
                 }
                 tmem_st16(tS + c * 16, packed);
             };
@@ -359,10 +426,11 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (cc == 0) tmem_ld32(tS + 64, r0);
                 exp_chunk(r1, 2 * cc + 1);
             }
+            if (row == 0) TC_TRACE(1 + w, t, 3);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(e_ready + w);
-            mbar_arrive(r_empty + (t % TC_NBETA));
+            if (row == 0) TC_TRACE(1 + w, t, 4);
         }
         if (ok && mbar_wait(phi_full, 0, p.err, 40)) { // ---- flush Phi_w: TMEM -> global partial sums
             tc_fence_after();
@@ -388,14 +456,14 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // ---- pairwise squared distances on the tensor cores, for the exact median --------------------------------
-// Same counting / collecting contract as dist_pass_f64_kernel (kernels_f64.cuh), on fp32 D2 = r_i + r_j - 2 S
-// with S from the bf16x3 contraction.  Keys are the IEEE bits of (double)D2, so the host-side bracket logic and
-// the radix select (select.cuh) are shared with the FP64 path; lo_f / hi_f are the float images of the key
-// bounds (d2 >= lo_f  <=>  (double)d2 >= lo).  rf[] holds +inf for padding rows, which therefore never count.
+// Same counting / collecting contract as dist_pass_f64_kernel (kernels_f64.cuh) on fp32 D2, which the MMA
+// delivers directly (split_kernel, SPLIT_DIST: the row norms ride in the extra K columns; padding rows give
+// +inf and never count).  Keys are the IEEE bits of (double)D2, so the host-side bracket logic and the radix
+// select (select.cuh) are shared with the FP64 path; lo_f / hi_f are the float images of the key bounds
+// (d2 >= lo_f  <=>  (double)d2 >= lo).
 // Layout as in phi_tc32_kernel: two i-tiles per CTA, one counting warpgroup each, TWO S buffers per warpgroup
-// (TMEM [256 w + 128 (t&1), +128)), X_j ring of 4 chunks, rf ring of 4 x 512 B.
+// (TMEM [256 w + 128 (t&1), +128)), X_j ring of 4 chunks.
 struct DistTcArgs {
-    const float *rf;       // [n_pad] |x~_j|^2, +inf beyond n
     int64_t n_total, row0, n_rows;
     int sym, n_jtiles, jsplit;
     float lo_f, hi_f;
@@ -407,7 +475,7 @@ struct DistTcArgs {
 };
 
 constexpr int TC_WBUF = 512; // candidate keys staged per warp
-constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + TC_NBETA * 512 + 8 * TC_WBUF * 8 + 8 * 4 + 512 + 1024;
+constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + 8 * TC_WBUF * 8 + 8 * 4 + 512 + 1024;
 constexpr uint32_t TC_DIST_SMEM_HIST = TC_DIST_SMEM_BASE + HIST_BINS * 4;
 
 // Rare path, kept out of line so the counting loop stays small: eight distances of which at least one lies
@@ -457,8 +525,7 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + 2 * TC_A_BYTES;
-    float *sR = (float *)(sB + TC_NB * TC_CHUNK);                     // [TC_NBETA][128]
-    unsigned long long *wbuf = (unsigned long long *)(sR + TC_NBETA * 128); // [8][TC_WBUF]
+    unsigned long long *wbuf = (unsigned long long *)(sB + TC_NB * TC_CHUNK); // [8][TC_WBUF]
     unsigned int *wcnt = (unsigned int *)(wbuf + 8 * TC_WBUF);        // [8]
     uint64_t *bars = (uint64_t *)(wcnt + 8);
     uint64_t *a_full = bars;
@@ -466,9 +533,7 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint64_t *b_empty = b_full + TC_NB;
     uint64_t *s_full = b_empty + TC_NB;  // [2 wg][2 buf]
     uint64_t *s_free = s_full + 4;       // [2 wg][2 buf]
-    uint64_t *r_full = s_free + 4;       // TC_NBETA
-    uint64_t *r_empty = r_full + TC_NBETA;
-    uint32_t *tmem_holder = (uint32_t *)(r_empty + TC_NBETA);
+    uint32_t *tmem_holder = (uint32_t *)(s_free + 4);
     unsigned int *shist = (unsigned int *)(tmem_holder + 4); // [HIST_BINS] (MODE_HIST only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -476,7 +541,6 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_init(a_full, 1);
         for (int s = 0; s < TC_NB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(s_free + s, 128); }
-        for (int s = 0; s < TC_NBETA; ++s) { mbar_init(r_full + s, 1); mbar_init(r_empty + s, 256); }
         fence_barrier_init();
     }
     if (threadIdx.x < 8) wcnt[threadIdx.x] = 0u;
@@ -488,53 +552,40 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 8) {
-        if (lane == 0) { // ---- TMA producer
+    if (warp == 8) { // ---- TMA producer (whole warp, one elected lane issues)
+        if (elect_one()) {
             mbar_arrive_expect_tx(a_full, 2 * TC_A_BYTES);
             for (int w = 0; w < 2; ++w)
                 for (int c = 0; c < TC_KCH; ++c)
                     tma_load_2d(sA + w * TC_A_BYTES + c * TC_CHUNK, &mapA, c * 64, (int)(i0 + w * TC_TILE), a_full);
-            bool ok = true;
-            for (int t = 0; ok && t < nt; ++t) {
-                const int j0 = (jbeg + t) * TC_TILE;
-                {
-                    const int rs = t % TC_NBETA, rph = (t / TC_NBETA) & 1;
-                    if (!mbar_wait(r_empty + rs, rph ^ 1, p.err, 52)) { ok = false; break; }
-                    mbar_arrive_expect_tx(r_full + rs, 512);
-                    bulk_load_1d(sR + rs * 128, p.rf + j0, 512, r_full + rs);
-                }
-                for (int c = 0; c < TC_KCH; ++c) {
-                    const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
-                    if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 50)) { ok = false; break; }
+        }
+        __syncwarp();
+        bool ok = true;
+        for (int t = 0; ok && t < nt; ++t) {
+            const int j0 = (jbeg + t) * TC_TILE;
+            for (int c = 0; ok && c < TC_KCH; ++c) {
+                const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
+                if (!mbar_wait(b_empty + slot, ph ^ 1, p.err, 50)) { ok = false; break; }
+                if (elect_one()) {
                     mbar_arrive_expect_tx(b_full + slot, TC_CHUNK);
                     tma_load_2d(sB + slot * TC_CHUNK, &mapB, c * 64, j0, b_full + slot);
                 }
+                __syncwarp();
             }
         }
-    } else if (warp == 9) {
-        if (lane == 0) { // ---- MMA issuer: S_w(t) into buffer (w, t & 1)
-            const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
-            bool ok = mbar_wait(a_full, 0, p.err, 60);
-            const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB));
-            for (int t = 0; ok && t < nt; ++t) {
-                const int buf = t & 1, bph = (t >> 1) & 1;
-                for (int w = 0; ok && w < 2; ++w) {
-                    if (!mbar_wait(s_free + 2 * w + buf, bph ^ 1, p.err, 62)) { ok = false; break; }
-                    const uint32_t d = tmem + w * 256 + buf * 128;
-#pragma unroll
-                    for (int c = 0; c < TC_KCH; ++c) {
-                        const int q = TC_KCH * t + c, slot = q % TC_NB, ph = (q / TC_NB) & 1;
-                        if (w == 0 && !mbar_wait(b_full + slot, ph, p.err, 61)) { ok = false; break; }
-                        if (c == 0) tc_fence_after();
-                        const uint32_t al = a_lo0 + ((w * TC_A_BYTES + c * TC_CHUNK) >> 4), bl = b_lo0 + slot * (TC_CHUNK >> 4);
-                        if (c == 0) umma_f16_ss2<false>(d, al, bl, idesc_s); else umma_f16_ss2<true>(d, al, bl, idesc_s);
-                        umma_f16_ss2<true>(d, al + 2, bl + 2, idesc_s);
-                        umma_f16_ss2<true>(d, al + 4, bl + 4, idesc_s);
-                        umma_f16_ss2<true>(d, al + 6, bl + 6, idesc_s);
-                        if (w == 1) umma_commit(b_empty + slot);
-                    }
-                    if (ok) umma_commit(s_full + 2 * w + buf);
-                }
+    } else if (warp == 9) { // ---- MMA issuer: S_w(t) into buffer (w, t & 1); warp-uniform, one elected lane issues
+        const uint32_t idesc_s = make_idesc_bf16(TC_TILE, TC_TILE);
+        bool ok = mbar_wait(a_full, 0, p.err, 60);
+        const uint32_t a_lo0 = desc_lo_k_sw128(smem_u32(sA)), b_lo0 = desc_lo_k_sw128(smem_u32(sB));
+        for (int t = 0; ok && t < nt; ++t) {
+            const int buf = t & 1, bph = (t >> 1) & 1;
+            for (int w = 0; ok && w < 2; ++w) {
+                if (!mbar_wait(s_free + 2 * w + buf, bph ^ 1, p.err, 62)) { ok = false; break; }
+                ok = issue_dist_mmas(tmem + w * 256 + buf * 128, a_lo0 + w * (TC_A_BYTES >> 4), b_lo0, idesc_s, t, w == 0, w == 1,
+                                     [&](int slot, int ph) { return mbar_wait(b_full + slot, ph, p.err, 61); },
+                                     [&](int slot) { umma_commit(b_empty + slot); });
+                if (ok && elect_one()) umma_commit(s_full + 2 * w + buf);
+                __syncwarp();
             }
         }
     } else { // ---- counting warpgroups: thread = row i
@@ -544,12 +595,13 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int itile = 2 * ip + w;
         const int64_t iw0 = i0 + w * TC_TILE;
         const int64_t i = iw0 + row;
-        const float ri = (i < p.row0 + p.n_rows) ? p.rf[i] : INFINITY;
+        const bool row_valid = i < p.row0 + p.n_rows;
         unsigned long long *mybuf = wbuf + warp * TC_WBUF;
         unsigned int *mycnt = wcnt + warp;
         unsigned long long below = 0ull;
         float maxb = -1.0f;
-        const float lo = p.lo_f, hi = p.hi_f;
+        // rows outside this rank's range never count: give them an empty bracket with nothing below it
+        const float lo = row_valid ? p.lo_f : -INFINITY, hi = row_valid ? p.hi_f : -INFINITY;
         auto flush = [&]() { // warp-collective: move the staged keys to the global candidate list
             __syncwarp();
             const unsigned int n = min(*mycnt, (unsigned int)TC_WBUF);
@@ -569,16 +621,13 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             // symmetric mode: tiles below the diagonal are covered by their transposes (weight 2)
             const unsigned int wgt = !p.sym ? 1u : (tj < itile ? 0u : (tj == itile ? 1u : 2u));
             const bool tile_has_diag = (j0 < iw0 + TC_TILE) && (j0 + TC_TILE > iw0);
-            const int64_t dcol = i - j0;
-            const float4 *rsm = reinterpret_cast<const float4 *>(sR + (t % TC_NBETA) * 128);
-            if (!mbar_wait(r_full + (t % TC_NBETA), (t / TC_NBETA) & 1, p.err, 72)) break;
+            const int dcol = (int)(i - j0);
             if (!mbar_wait(s_full + 2 * w + buf, bph, p.err, 70 + w)) break;
             tc_fence_after();
             const uint32_t tS = tmem + w * 256 + buf * 128 + lane_base;
-            if (wgt == 0u) { // nothing to count: hand the buffers straight back
+            if (wgt == 0u) { // nothing to count: hand the buffer straight back
                 tc_fence_before();
                 mbar_arrive(s_free + 2 * w + buf);
-                mbar_arrive(r_empty + (t % TC_NBETA));
                 continue;
             }
             unsigned int cnt_below = 0;
@@ -590,10 +639,8 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int q = g * 8 + e;
-                        const float4 r4 = rsm[c * 8 + (q >> 2)];
-                        const float rj = (q & 3) == 0 ? r4.x : (q & 3) == 1 ? r4.y : (q & 3) == 2 ? r4.z : r4.w;
-                        float d2 = fmaf(-2.0f, __uint_as_float(rr[q]), ri + rj);
-                        if (tile_has_diag && dcol == c * 32 + q) d2 = (ri < INFINITY) ? 0.0f : INFINITY; // |x_i - x_i|^2 = 0 exactly
+                        float d2 = __uint_as_float(rr[q]);
+                        if (tile_has_diag && dcol == c * 32 + q) d2 = 0.0f; // |x_i - x_i|^2 = 0 exactly, like the reference
                         const bool is_below = d2 < lo;
                         if (is_below) { ++cnt_below; maxb = fmaxf(maxb, d2); }
                         any |= (!is_below && d2 < hi);
@@ -623,7 +670,6 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 count_chunk(r1, 2 * cc + 1);
             }
             below += (unsigned long long)cnt_below * wgt;
-            mbar_arrive(r_empty + (t % TC_NBETA));
         }
         if (MODE == MODE_COLLECT) flush();
         unsigned long long maxb_key = maxb >= 0.0f ? (unsigned long long)__double_as_longlong((double)maxb) : 0ull;

@@ -132,6 +132,7 @@ struct svgdb_ctx {
     float *beta = nullptr, *rf = nullptr, *phi_buf = nullptr;
     double *rt = nullptr, *colsum = nullptr;
     int *tc_err = nullptr;
+    long long *tc_trace = nullptr; // SVGDB_TC_TRACE=<file>: timeline of CTA 0 of the pair-interaction kernel
     CUtensorMap mapA{}, mapB{}, mapV{};
 
     // measurement
@@ -228,7 +229,8 @@ int free_sharded(svgdb_ctx *ctx)
     cudaFree(ctx->s1); cudaFree(ctx->s2); cudaFree(ctx->phi_dbg);
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
     cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
-    cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err);
+    cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
+    ctx->tc_trace = nullptr;
     ctx->XA = ctx->XB = nullptr;
     ctx->VT = nullptr;
     ctx->beta = ctx->rf = ctx->phi_buf = nullptr;
@@ -271,17 +273,18 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->XA, np * TC_KTOT * 2));
     CU(cudaMalloc(&ctx->XB, np * TC_KTOT * 2));
     CU(cudaMalloc(&ctx->VT, (size_t)TC_NV * np * 2));
-    CU(cudaMalloc(&ctx->beta, np * 4));
-    CU(cudaMalloc(&ctx->rf, np * 4));
     CU(cudaMalloc(&ctx->rt, np * 8));
     CU(cudaMalloc(&ctx->colsum, 64 * 8));
     CU(cudaMalloc(&ctx->tc_err, 4));
+    if (std::getenv("SVGDB_TC_TRACE")) {
+        CU(cudaMalloc(&ctx->tc_trace, 3 * 64 * 8 * 8));
+        CU(cudaMemsetAsync(ctx->tc_trace, 0, 3 * 64 * 8 * 8, ctx->stream));
+    }
     // rows of a tile may reach past the last rank-local row: keep a tile of slack
     CU(cudaMalloc(&ctx->phi_buf, (np + 256) * TC_PHI_LD * 4));
     CU(cudaMemsetAsync(ctx->XA, 0, np * TC_KTOT * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->XB, 0, np * TC_KTOT * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->VT, 0, (size_t)TC_NV * np * 2, ctx->stream));
-    CU(cudaMemsetAsync(ctx->beta, 0, np * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream));
     TRY(make_bf16_map(ctx, &ctx->mapA, ctx->XA, np, TC_KTOT, 128));
     TRY(make_bf16_map(ctx, &ctx->mapB, ctx->XB, np, TC_KTOT, 128));
@@ -641,15 +644,17 @@ int launch_make_v(svgdb_ctx *ctx)
 }
 
 #ifdef SVGDB_WITH_TC32
-// centred bf16-split operands, r = |x~|^2
-int launch_tc_split(svgdb_ctx *ctx)
+// centred bf16-split operand rows for the distance pass (mode 0) or the pair-interaction pass (mode 1, needs a)
+int launch_tc_split(svgdb_ctx *ctx, int mode)
 {
     using namespace svgdb::tc;
-    CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
-    colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
-    KERNEL_CHECK();
-    split_kernel<<<(unsigned)((ctx->n_pad128 + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->N, ctx->n_pad128, ctx->d,
-                                                                                 ctx->XA, ctx->XB, ctx->rt, ctx->rf);
+    if (mode == SPLIT_DIST) {
+        CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
+        colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
+        KERNEL_CHECK();
+    }
+    split_kernel<<<(unsigned)((ctx->n_pad128 + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128,
+                                                                                 ctx->d, mode, ctx->XA, ctx->XB, ctx->rt);
     KERNEL_CHECK();
     return SVGDB_OK;
 }
@@ -669,7 +674,6 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
 {
     using namespace svgdb::tc;
     DistTcArgs a{};
-    a.rf = ctx->rf;
     a.n_total = ctx->N;
     a.row0 = ctx->row0;
     a.n_rows = ctx->n_rows;
@@ -728,13 +732,12 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
+    TRY(launch_tc_split(ctx, SPLIT_PHI)); // the operands now carry the bandwidth: the accumulator is the exponent
     make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
-                                                                            ctx->d, ctx->VT, ctx->beta);
+                                                                            ctx->d, ctx->VT);
     KERNEL_CHECK();
     CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, ctx->stream));
     PhiTcArgs a{};
-    a.beta = ctx->beta;
-    a.a_ptr = ctx->a_dev;
     a.phi_buf = ctx->phi_buf;
     a.n_total = ctx->N;
     a.row0 = ctx->row0;
@@ -743,9 +746,19 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
     a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
     a.err = ctx->tc_err;
+    a.trace = ctx->tc_trace;
     phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
     KERNEL_CHECK();
     ++ctx->stats.phi_launches;
+    if (ctx->tc_trace) {
+        std::vector<long long> h(3 * 64 * 8);
+        CU(cudaMemcpyAsync(h.data(), ctx->tc_trace, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (FILE *f = std::fopen(std::getenv("SVGDB_TC_TRACE"), "w")) {
+            for (size_t k = 0; k < h.size(); ++k) std::fprintf(f, "%lld%c", h[k], (k % 8 == 7) ? '\n' : ' ');
+            std::fclose(f);
+        }
+    }
     OptTcArgs o{};
     o.X = ctx->X[ctx->cur];
     o.colsum = ctx->colsum;
@@ -798,7 +811,7 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
 {
     prof_mark(ctx, 0);
 #ifdef SVGDB_WITH_TC32
-    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx));
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx, svgdb::tc::SPLIT_DIST));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
@@ -1148,7 +1161,7 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
     if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
     CU(cudaSetDevice(ctx->device));
 #ifdef SVGDB_WITH_TC32
-    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx));
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx, svgdb::tc::SPLIT_DIST));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));

@@ -21,6 +21,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  Code that feeds tcgen05.mma / TMA must stay warp-uniform up to this
+// point so that descriptors and addresses live in uniform registers (a lane-0 branch forces slow R2UR moves
+// in front of every instruction: ~100 cycles per MMA measured).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
