@@ -399,18 +399,18 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             // 32-column chunk c: exponentials of rr[] -> fp16 pairs over S columns [16c, 16c+16) (already read)
             auto exp_chunk = [&](const uint32_t (&rr)[32], int c) {
                 uint32_t packed[16];
+                if (!tile_has_diag) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    float e0 = ex2_approx(__uint_as_float(rr[2 * q]));
-                    float e1 = ex2_approx(__uint_as_float(rr[2 * q + 1]));
-                    packed[q] = pack_f16x2(e0, e1);
-                }
-                if (tile_has_diag) { // k(x_i, x_i) = exp(0) exactly, like the reference: fp16(2^15) = 0x7800
-                    const int q = dcol - c * 32;
-                    if (q >= 0 && q < 32) {
+                    for (int q = 0; q < 16; ++q)
+                        packed[q] = pack_f16x2(ex2_approx(__uint_as_float(rr[2 * q])), ex2_approx(__uint_as_float(rr[2 * q + 1])));
+                } else { // k(x_i, x_i) = exp(0) exactly, like the reference (2^15 after the fp16 scaling)
+                    const int dq = dcol - c * 32;
 #pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if ((q >> 1) == u) packed[u] = (q & 1) ? ((packed[u] & 0x0000FFFFu) | 0x78000000u) : ((packed[u] & 0xFFFF0000u) | 0x00007800u);
+                    for (int q = 0; q < 16; ++q) {
+                        float e0 = ex2_approx(__uint_as_float(rr[2 * q])), e1 = ex2_approx(__uint_as_float(rr[2 * q + 1]));
+                        if (dq == 2 * q) e0 = 32768.0f;
+                        if (dq == 2 * q + 1) e1 = 32768.0f;
+                        packed[q] = pack_f16x2(e0, e1);
                     }
                 }
                 tmem_st16(tS + c * 16, packed);
@@ -469,43 +469,42 @@ struct DistTcArgs {
     float lo_f, hi_f;
     unsigned long long lo_key;
     int shift;
-    unsigned long long *below, *max_below, *hist, *cand, *cand_count;
+    unsigned long long *below, *hist, *cand, *cand_count; // (no max-below tracking: the host re-brackets instead)
     unsigned long long capacity;
     int *err;
+    long long *trace;
 };
 
-constexpr int TC_WBUF = 512; // candidate keys staged per warp
-constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + 8 * TC_WBUF * 8 + 8 * 4 + 512 + 1024;
-constexpr uint32_t TC_DIST_SMEM_HIST = TC_DIST_SMEM_BASE + HIST_BINS * 4;
+constexpr int TC_WBUF = 512;  // candidate distances (fp32) staged per warp before one global reservation
+constexpr int TC_PRIV = 40;   // per-thread staging slots: compacted once a thread holds more than TC_PRIV - 32
+constexpr uint32_t TC_DIST_SMEM_BASE = 2 * TC_A_BYTES + TC_NB * TC_CHUNK + 8 * TC_WBUF * 4 + 256 * TC_PRIV * 4 + 512 + 1024;
+constexpr uint32_t TC_DIST_SMEM_HIST = TC_DIST_SMEM_BASE; // the histogram aliases the (unused) warp staging buffers
+static_assert(HIST_BINS * 4 <= 8 * TC_WBUF * 4, "histogram must fit the warp staging area");
 
-// Rare path, kept out of line so the counting loop stays small: eight distances of which at least one lies
-// inside the bracket.  Candidates go to the warp's staging buffer (smem atomic reservation), or straight to
-// the global list when that is full; in histogram mode they bump the shared histogram.
-template <int MODE>
-__device__ __noinline__ void dist_in_bracket8(float d0, float d1, float d2, float d3, float d4, float d5, float d6, float d7,
-                                              float lo, float hi, unsigned int wgt, unsigned int *mycnt,
-                                              unsigned long long *mybuf, unsigned int *shist, const DistTcArgs *p)
+__device__ __forceinline__ unsigned long long dist_key(float d2)
 {
-    const float dd[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
-#pragma unroll 1
-    for (int e = 0; e < 8; ++e) {
-        const float v = dd[e];
-        if (v < lo || !(v < hi)) continue;
-        const unsigned long long key = (unsigned long long)__double_as_longlong((double)fmaxf(v, 0.0f));
-        if (MODE == MODE_HIST) {
-            atomicAdd(&shist[(unsigned int)((key - p->lo_key) >> p->shift)], wgt);
-        } else {
-            const unsigned int pos = atomicAdd(mycnt, wgt);
-            if (pos + wgt <= TC_WBUF) {
-                mybuf[pos] = key;
-                if (wgt == 2u) mybuf[pos + 1] = key;
-            } else {
-                const unsigned long long g = atomicAdd(p->cand_count, (unsigned long long)wgt);
-                if (g < p->capacity) p->cand[g] = key;
-                if (wgt == 2u && g + 1 < p->capacity) p->cand[g + 1] = key;
-            }
-        }
-    }
+    return (unsigned long long)__double_as_longlong((double)fmaxf(d2, 0.0f));
+}
+// staging bypass for a chunk that overflows the warp buffer (very wide bracket): reserve straight in the global list
+__device__ __noinline__ void dist_append_global(float d2, unsigned int wgt, const DistTcArgs *p)
+{
+    const unsigned long long key = dist_key(d2);
+    const unsigned long long g = atomicAdd(p->cand_count, (unsigned long long)wgt);
+    if (g < p->capacity) p->cand[g] = key;
+    if (wgt == 2u && g + 1 < p->capacity) p->cand[g + 1] = key;
+}
+
+// warp-collective and out of line: move `count` staged distances to the global candidate list as keys
+__device__ __noinline__ void dist_flush(const float *mybuf, unsigned int count, const DistTcArgs *p)
+{
+    __syncwarp();
+    const unsigned int lane = threadIdx.x & 31;
+    unsigned long long base = 0ull;
+    if (lane == 0 && count) base = atomicAdd(p->cand_count, (unsigned long long)count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned int q = lane; q < count; q += 32)
+        if (base + q < p->capacity) p->cand[base + q] = dist_key(mybuf[q]);
+    __syncwarp();
 }
 
 template <int MODE>
@@ -525,16 +524,16 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + 2 * TC_A_BYTES;
-    unsigned long long *wbuf = (unsigned long long *)(sB + TC_NB * TC_CHUNK); // [8][TC_WBUF]
-    unsigned int *wcnt = (unsigned int *)(wbuf + 8 * TC_WBUF);        // [8]
-    uint64_t *bars = (uint64_t *)(wcnt + 8);
+    float *wbuf = (float *)(sB + TC_NB * TC_CHUNK); // [8][TC_WBUF]   per-warp staging
+    float *priv = wbuf + 8 * TC_WBUF;               // [8][TC_PRIV][32] per-thread staging, lane-interleaved
+    uint64_t *bars = (uint64_t *)(priv + 256 * TC_PRIV);
     uint64_t *a_full = bars;
     uint64_t *b_full = bars + 1;
     uint64_t *b_empty = b_full + TC_NB;
     uint64_t *s_full = b_empty + TC_NB;  // [2 wg][2 buf]
     uint64_t *s_free = s_full + 4;       // [2 wg][2 buf]
     uint32_t *tmem_holder = (uint32_t *)(s_free + 4);
-    unsigned int *shist = (unsigned int *)(tmem_holder + 4); // [HIST_BINS] (MODE_HIST only)
+    unsigned int *shist = (unsigned int *)wbuf; // [HIST_BINS] (MODE_HIST only: aliases the warp staging buffers)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -543,7 +542,6 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(s_free + s, 128); }
         fence_barrier_init();
     }
-    if (threadIdx.x < 8) wcnt[threadIdx.x] = 0u;
     if (MODE == MODE_HIST)
         for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) shist[b] = 0u;
     if (warp == 8) tmem_alloc(tmem_holder, 512);
@@ -580,12 +578,15 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int t = 0; ok && t < nt; ++t) {
             const int buf = t & 1, bph = (t >> 1) & 1;
             for (int w = 0; ok && w < 2; ++w) {
+                if (lane == 0) TC_TRACE(0, t, 3 * w);
                 if (!mbar_wait(s_free + 2 * w + buf, bph ^ 1, p.err, 62)) { ok = false; break; }
+                if (lane == 0) TC_TRACE(0, t, 3 * w + 1);
                 ok = issue_dist_mmas(tmem + w * 256 + buf * 128, a_lo0 + w * (TC_A_BYTES >> 4), b_lo0, idesc_s, t, w == 0, w == 1,
                                      [&](int slot, int ph) { return mbar_wait(b_full + slot, ph, p.err, 61); },
                                      [&](int slot) { umma_commit(b_empty + slot); });
                 if (ok && elect_one()) umma_commit(s_full + 2 * w + buf);
                 __syncwarp();
+                if (lane == 0) TC_TRACE(0, t, 3 * w + 2);
             }
         }
     } else { // ---- counting warpgroups: thread = row i
@@ -596,23 +597,46 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int64_t iw0 = i0 + w * TC_TILE;
         const int64_t i = iw0 + row;
         const bool row_valid = i < p.row0 + p.n_rows;
-        unsigned long long *mybuf = wbuf + warp * TC_WBUF;
-        unsigned int *mycnt = wcnt + warp;
+        float *mybuf = wbuf + warp * TC_WBUF;
+        const uint32_t priv_base = smem_u32(priv + warp * (TC_PRIV * 32) + lane); // this thread's lane-interleaved slots
+        const uint32_t wbuf_base = smem_u32(mybuf);
+        unsigned int count = 0; // warp-uniform fill level of mybuf
         unsigned long long below = 0ull;
-        float maxb = -1.0f;
         // rows outside this rank's range never count: give them an empty bracket with nothing below it
         const float lo = row_valid ? p.lo_f : -INFINITY, hi = row_valid ? p.hi_f : -INFINITY;
-        auto flush = [&]() { // warp-collective: move the staged keys to the global candidate list
-            __syncwarp();
-            const unsigned int n = min(*mycnt, (unsigned int)TC_WBUF);
-            unsigned long long base = 0ull;
-            if (lane == 0 && n) base = atomicAdd(p.cand_count, (unsigned long long)n);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (unsigned int q = lane; q < n; q += 32)
-                if (base + q < p.capacity) p.cand[base + q] = mybuf[q];
-            __syncwarp();
-            if (lane == 0) *mycnt = 0u;
-            __syncwarp();
+        uint32_t paddr = priv_base; // next free private slot (slot e of this thread lives at priv_base + 128 e)
+        unsigned int cur_wgt = 1u;  // weight of the entries currently staged in the private slots
+        // warp-collective: move the private entries (all of weight cur_wgt) into the warp buffer / histogram
+        auto compact = [&]() {
+            const uint32_t mine = (paddr - priv_base) >> 7;
+            const unsigned int tot = __reduce_add_sync(0xffffffffu, mine);
+            if (tot) { // warp-uniform
+                if (MODE == MODE_HIST) {
+                    for (uint32_t e = 0; e < mine; ++e)
+                        atomicAdd(&shist[(unsigned int)((dist_key(lds_f32(priv_base + 128u * e)) - p.lo_key) >> p.shift)], cur_wgt);
+                } else {
+                    if (count + tot * cur_wgt > (unsigned int)TC_WBUF) { dist_flush(mybuf, count, &p); count = 0; }
+                    if (tot * cur_wgt > (unsigned int)TC_WBUF) { // more than an empty buffer holds: straight to global
+                        for (uint32_t e = 0; e < mine; ++e) dist_append_global(lds_f32(priv_base + 128u * e), cur_wgt, &p);
+                    } else {
+                        uint32_t incl = mine; // inclusive scan over lanes
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        uint32_t dst = wbuf_base + 4u * (count + (incl - mine) * cur_wgt);
+                        for (uint32_t e = 0; e < mine; ++e) {
+                            const float v = lds_f32(priv_base + 128u * e);
+                            sts_f32(dst, v); dst += 4u;
+                            if (cur_wgt == 2u) { sts_f32(dst, v); dst += 4u; }
+                        }
+                        count += tot * cur_wgt;
+                    }
+                }
+                paddr = priv_base;
+                __syncwarp();
+            }
         };
         for (int t = 0; t < nt; ++t) {
             const int buf = t & 1, bph = (t >> 1) & 1;
@@ -622,7 +646,9 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const unsigned int wgt = !p.sym ? 1u : (tj < itile ? 0u : (tj == itile ? 1u : 2u));
             const bool tile_has_diag = (j0 < iw0 + TC_TILE) && (j0 + TC_TILE > iw0);
             const int dcol = (int)(i - j0);
+            if (row == 0) TC_TRACE(1 + w, t, 0);
             if (!mbar_wait(s_full + 2 * w + buf, bph, p.err, 70 + w)) break;
+            if (row == 0) TC_TRACE(1 + w, t, 1);
             tc_fence_after();
             const uint32_t tS = tmem + w * 256 + buf * 128 + lane_base;
             if (wgt == 0u) { // nothing to count: hand the buffer straight back
@@ -630,28 +656,31 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_arrive(s_free + 2 * w + buf);
                 continue;
             }
-            unsigned int cnt_below = 0;
+            if (wgt != cur_wgt) { compact(); cur_wgt = wgt; }
+            unsigned int cnt4[4] = {0u, 0u, 0u, 0u}; // four independent counters: no 128-long dependent add chain
+            // Per distance: two compares, a predicated count and a predicated store into the thread's private staging
+            // column (no branch, no vote: a vote + branch per element serialises the warp at ~80 cycles each).
+            auto visit = [&](float d2, unsigned int &cnt) {
+                asm volatile("{\n\t.reg .pred pb, pi;\n\t"
+                             "setp.lt.f32 pb, %2, %3;\n\t"
+                             "@pb add.u32 %0, %0, 1;\n\t"
+                             "setp.lt.and.f32 pi, %2, %4, !pb;\n\t"
+                             "@pi st.shared.f32 [%1], %2;\n\t"
+                             "@pi add.u32 %1, %1, 128;\n\t}"
+                             : "+r"(cnt), "+r"(paddr)
+                             : "f"(d2), "f"(lo), "f"(hi)
+                             : "memory");
+            };
             auto count_chunk = [&](const uint32_t (&rr)[32], int c) {
+                if (!tile_has_diag) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float dd[8];
-                    bool any = false;
+                    for (int q = 0; q < 32; ++q) visit(__uint_as_float(rr[q]), cnt4[q & 3]);
+                } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int q = g * 8 + e;
-                        float d2 = __uint_as_float(rr[q]);
-                        if (tile_has_diag && dcol == c * 32 + q) d2 = 0.0f; // |x_i - x_i|^2 = 0 exactly, like the reference
-                        const bool is_below = d2 < lo;
-                        if (is_below) { ++cnt_below; maxb = fmaxf(maxb, d2); }
-                        any |= (!is_below && d2 < hi);
-                        dd[e] = d2;
-                    }
-                    if (any) dist_in_bracket8<MODE>(dd[0], dd[1], dd[2], dd[3], dd[4], dd[5], dd[6], dd[7], lo, hi, wgt, mycnt, mybuf, shist, &p);
+                    for (int q = 0; q < 32; ++q) visit(dcol == c * 32 + q ? 0.0f : __uint_as_float(rr[q]), cnt4[q & 3]); // |x_i - x_i|^2 = 0 exactly
                 }
-                if (MODE == MODE_COLLECT) {
-                    __syncwarp();
-                    if (*mycnt > TC_WBUF / 2) flush();
-                }
+                // the next chunk may add up to 32 entries per thread: compact when any thread could overflow
+                if (__any_sync(0xffffffffu, paddr - priv_base > (uint32_t)(TC_PRIV - 32) * 128u)) compact();
             };
             uint32_t r0[32], r1[32];
             tmem_ld32(tS, r0);
@@ -669,19 +698,13 @@ dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 count_chunk(r1, 2 * cc + 1);
             }
-            below += (unsigned long long)cnt_below * wgt;
+            below += (unsigned long long)(cnt4[0] + cnt4[1] + cnt4[2] + cnt4[3]) * wgt;
+            if (row == 0) TC_TRACE(1 + w, t, 2);
         }
-        if (MODE == MODE_COLLECT) flush();
-        unsigned long long maxb_key = maxb >= 0.0f ? (unsigned long long)__double_as_longlong((double)maxb) : 0ull;
-        for (int o = 16; o; o >>= 1) {
-            below += __shfl_xor_sync(0xffffffffu, below, o);
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, maxb_key, o);
-            maxb_key = other > maxb_key ? other : maxb_key;
-        }
-        if (lane == 0) {
-            if (below) atomicAdd(p.below, below);
-            if (maxb_key) atomicMax(p.max_below, maxb_key);
-        }
+        compact();
+        if (MODE == MODE_COLLECT && count) dist_flush(mybuf, count, &p);
+        for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0 && below) atomicAdd(p.below, below);
     }
     tc_fence_before();
     __syncthreads();

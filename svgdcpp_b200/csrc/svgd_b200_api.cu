@@ -494,7 +494,10 @@ int median_scale(svgdb_ctx *ctx)
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
         TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
         uint64_t b = ctx->hs->below;
-        bool hit = (b <= k_hi) && (k_hi < b + mid) && (mid <= ctx->capacity) && (!even || k_hi >= 1);
+        // the tensor-core pass does not track the largest value below the bracket, so for an even count the lower
+        // middle element must be a candidate as well (b < k_hi)
+        const bool need_both = even && ctx->precision == SVGDB_PRECISION_TC32;
+        bool hit = (need_both ? b < k_hi : b <= k_hi) && (k_hi < b + mid) && (mid <= ctx->capacity) && (!even || k_hi >= 1);
         if (hit) {
             lo = klo; hi = khi; below_known = b; collected = true;
             ++ctx->stats.median_bracket_hits;
@@ -524,11 +527,18 @@ int median_scale(svgdb_ctx *ctx)
             uint64_t nhi = std::min<uint64_t>(hi, nlo + (1ull << shift));
             lo = nlo; hi = nhi; below_known = cum; in_range = ctx->hs->hist[b];
         }
-        TRY(launch_dist_pass(ctx, MODE_COLLECT, lo, hi, 0));
-        TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
-        below_known = ctx->hs->below;
-        if (!(below_known <= k_hi && k_hi < below_known + mid))
-            return fail(ctx, SVGDB_ERR_NUMERIC, "median select: bracket lost the rank (non-finite particles?)");
+        for (int attempt = 0;; ++attempt) {
+            TRY(launch_dist_pass(ctx, MODE_COLLECT, lo, hi, 0));
+            TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
+            below_known = ctx->hs->below;
+            if (!(below_known <= k_hi && k_hi < below_known + mid))
+                return fail(ctx, SVGDB_ERR_NUMERIC, "median select: bracket lost the rank (non-finite particles?)");
+            // tensor-core pass, even count, lower middle element just below the bracket: widen downwards and recollect
+            const bool pred_outside = even && ctx->precision == SVGDB_PRECISION_TC32 && below_known == k_hi && lo > 0 && mid <= ctx->capacity;
+            if (!pred_outside || attempt >= 40) break;
+            const uint64_t step = std::max<uint64_t>(hi - lo, 1ull) << std::min(attempt, 20);
+            lo = lo > step ? lo - step : 0;
+        }
     }
 
     const uint64_t kk = k_hi - below_known;
@@ -685,12 +695,12 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     a.lo_key = lo;
     a.shift = shift;
     a.below = ctx->below;
-    a.max_below = ctx->max_below;
     a.hist = ctx->hist;
     a.cand = ctx->cand;
     a.cand_count = ctx->cand_count;
     a.capacity = ctx->capacity;
     a.err = ctx->tc_err;
+    a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? ctx->tc_trace : nullptr;
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
     const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
@@ -746,7 +756,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
     a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
     a.err = ctx->tc_err;
-    a.trace = ctx->tc_trace;
+    a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
     phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
     KERNEL_CHECK();
     ++ctx->stats.phi_launches;

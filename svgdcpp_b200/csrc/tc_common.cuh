@@ -208,6 +208,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) // lo -> bit
     return r;
 }
 
+// Explicit shared-space accesses through 32-bit addresses (pointers derived from the re-aligned dynamic smem
+// base are generic to the compiler, which then emits 64-bit generic ST/LD with several address instructions).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) // lo -> bits [0,16), hi -> bits [16,32)
 {
     uint32_t r;
