@@ -370,6 +370,7 @@ struct DistArgs {
     int64_t row0, n_rows;
     int sym;
     int64_t n_tiles_i, n_tiles_j, n_work; // tile counts and number of tile pairs
+    int work_offset, work_stride;         // this rank takes tile pairs offset, offset + stride, ... (cyclic over ranks)
     uint64_t lo, hi;
     int shift;
     unsigned long long *below;      // [1]
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(128, 2) dist_pass_f64_kernel(DistArgs p)
     }
     unsigned long long below = 0ull, maxb = 0ull;
 
-    for (int64_t w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+    for (int64_t w = (int64_t)blockIdx.x * p.work_stride + p.work_offset; w < p.n_work; w += (int64_t)gridDim.x * p.work_stride) {
         int64_t ti, tj;
         decode_tile(p, w, ti, tj);
         const int64_t i0 = p.row0 + ti * 64, j0 = tj * 64;

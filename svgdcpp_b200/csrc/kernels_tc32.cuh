@@ -466,6 +466,7 @@ phi_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 struct DistTcArgs {
     int64_t n_total, row0, n_rows;
     int sym, n_jtiles, jsplit;
+    int pair_offset, pair_stride; // this rank owns i-pairs offset, offset + stride, ... (cyclic: balances the triangle)
     float lo_f, hi_f;
     unsigned long long lo_key;
     int shift;
@@ -511,7 +512,8 @@ template <int MODE>
 __global__ void __launch_bounds__(320, 1)
 dist_tc32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ DistTcArgs p)
 {
-    const int ip = blockIdx.x / p.jsplit, js = blockIdx.x - ip * p.jsplit;
+    const int ipl = blockIdx.x / p.jsplit, js = blockIdx.x - ipl * p.jsplit;
+    const int ip = p.pair_offset + p.pair_stride * ipl;
     const int jfirst = p.sym ? 2 * ip : 0; // tile-level upper triangle when symmetric
     const int len = p.n_jtiles - jfirst;
     const int tps = (len + p.jsplit - 1) / p.jsplit;

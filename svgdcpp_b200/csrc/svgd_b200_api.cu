@@ -369,12 +369,16 @@ int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shi
     a.r = ctx->r;
     a.n_total = ctx->N;
     a.d = ctx->d;
-    a.row0 = ctx->row0;
-    a.n_rows = ctx->n_rows;
-    a.sym = ctx->world == 1 ? 1 : 0;
+    // the distance pass only needs X, which every rank holds: keep the symmetric (upper-triangle) enumeration at
+    // any world size and deal the tile pairs cyclically to the ranks
+    a.row0 = 0;
+    a.n_rows = ctx->N;
+    a.sym = 1;
     a.n_tiles_j = (ctx->N + 63) / 64;
-    a.n_tiles_i = (ctx->n_rows + 63) / 64;
-    a.n_work = a.sym ? a.n_tiles_j * (a.n_tiles_j + 1) / 2 : a.n_tiles_i * a.n_tiles_j;
+    a.n_tiles_i = a.n_tiles_j;
+    a.n_work = a.n_tiles_j * (a.n_tiles_j + 1) / 2;
+    a.work_offset = ctx->rank;
+    a.work_stride = ctx->world;
     a.lo = lo;
     a.hi = hi;
     a.shift = shift;
@@ -387,7 +391,7 @@ int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shi
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
     if (a.n_work > 0) {
-        unsigned grid = (unsigned)std::min<int64_t>(a.n_work, (int64_t)ctx->sm_count * 4);
+        unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((a.n_work + ctx->world - 1) / ctx->world, (int64_t)ctx->sm_count * 4));
         if (mode == MODE_HIST) {
             CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
             dist_pass_f64_kernel<MODE_HIST><<<grid, 128, dist_smem_bytes(ctx->d, true), ctx->stream>>>(a);
@@ -447,7 +451,10 @@ int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even,
     select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, prefix, mask, kk);
     KERNEL_CHECK();
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m_local + 2047) / 2048, (uint64_t)ctx->sm_count * 8));
-    for (int shift = first_shift; shift >= 0; shift -= 8) {
+    // keys of the tensor-core path are fp32 distances widened to double: their low 29 bits are zero, so the three
+    // lowest digit passes cannot change anything (prefix bits stay 0 there)
+    const int last_shift = ctx->precision == SVGDB_PRECISION_TC32 ? 24 : 0;
+    for (int shift = first_shift; shift >= last_shift; shift -= 8) {
         select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, ctx->sel);
         KERNEL_CHECK();
         TRY(allreduce_u64(ctx, ctx->sel->hist, 256, ncclSum));
@@ -685,9 +692,11 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     using namespace svgdb::tc;
     DistTcArgs a{};
     a.n_total = ctx->N;
-    a.row0 = ctx->row0;
-    a.n_rows = ctx->n_rows;
-    a.sym = ctx->world == 1 ? 1 : 0;
+    a.row0 = 0; // symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks
+    a.n_rows = ctx->N;
+    a.sym = 1;
+    a.pair_offset = ctx->rank;
+    a.pair_stride = ctx->world;
     a.n_jtiles = (int)(ctx->n_pad128 / 128);
     a.jsplit = std::max(1, std::min(8, a.n_jtiles / 8));
     a.lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
@@ -703,7 +712,8 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? ctx->tc_trace : nullptr;
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
-    const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
+    const int n_ipairs_all = (int)((ctx->N + 255) / 256);
+    const int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
     if (n_ipairs > 0) {
         unsigned grid = (unsigned)(n_ipairs * a.jsplit);
         if (mode == MODE_HIST) {
