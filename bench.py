@@ -284,8 +284,13 @@ def main():
         phi_flops = (4 * d + 2) * float(rows_local) * float(n)          # algorithmic flops of ONE launch (this rank's rows)
         achieved_tf = phi_flops / (phi_ms * 1e-3) * 1e-12 if phi_ms > 0 else 0.0
         step_tf = (6 * d + 2) * pairs * args.steps / (ms * 1e-3) * 1e-12  # incl. one distance evaluation for the median
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tpath) and world == 1 and n == N_PARTICLES and d == DIM:
+            with open(tpath) as f:
+                traffic = json.load(f).get("tc32_phi" if precision == _capi.PRECISION_TC32 else "f64_phi")
         roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
                 "kernel": "phi (pair interaction + optimizer epilogue)", "kernel_ms": phi_ms,
                 "algorithmic_flops_per_launch": phi_flops, "peak_source": peaks["source"] + ", dense bf16 sustained",
                 "whole_step_algorithmic_tflops": step_tf / max(world, 1), "phase_ms_per_step": phase_ms}
@@ -299,12 +304,15 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if precision == _capi.PRECISION_F64 else "f32 (bf16x3 split operands, fp32 accumulate)",
+            "dtype": "f64" if precision == _capi.PRECISION_F64 else "f32",
             "data": "synthetic",
             "config": {"workload": "64-D MVN dense covariance, N=%d, median bandwidth, Adam (BASELINE configs[2])" % n,
                        "n_particles": n, "dim": d, "parallelism": "rows sharded over %d GPU(s), NCCL all-gather of X and V" % world,
                        "l2": "working set (X, V, X_next, optimizer state) = %d MB > 126 MB L2; compute-bound, no flush" % (5 * nbytes // 2 ** 20),
-                       "median_passes_per_step": median_passes / max(1, args.steps), "finite": finite},
+                       "median_passes_per_step": median_passes / max(1, args.steps), "finite": finite,
+                       "precision_mode": "F64: DMMA fp64 end to end" if precision == _capi.PRECISION_F64 else
+                       "TC32: tcgen05 kind::f16 MMAs on split-bf16 particles / scaled-fp16 kernel values, fp32 accumulation in TMEM, "
+                       "fp32 ex2, FP64 optimizer state (error bound in DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms / args.steps,
                     "call": "svgdb_set_particles(host) + svgdb_step(1) + svgdb_get_particles(host) == SVGD::Run() with NumIterations=1"},
