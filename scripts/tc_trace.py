@@ -2,7 +2,7 @@
 import os, sys
 import numpy as np
 sys.path.insert(0, ".")
-os.environ["SVGDB_TC_TRACE"] = "gpurun_out/tc_trace.txt"
+os.environ.setdefault("SVGDB_TC_TRACE", "gpurun_out/tc_trace.txt")
 import svgdcpp_b200 as sv
 from svgdcpp_b200 import synth, _capi
 n, d = 65536, 64
@@ -11,7 +11,7 @@ model = sv.MultivariateNormal(means[0], covs[0])
 s = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999), precision=1)
 s.Initialize(); s._upload()
 _capi.load().svgdb_step(s._ctx, 2)
-tr = np.loadtxt("gpurun_out/tc_trace.txt").reshape(3, 64, 8)
+tr = np.loadtxt(os.environ["SVGDB_TC_TRACE"]).reshape(3, 64, 8)
 t0 = tr[0, 0, 0]
 names = ["mma", "wg0", "wg1"]
 for t in range(4, 12):

@@ -1,0 +1,447 @@
+// kernels_phi_tc.cuh — the persistent tensor-core pair-interaction kernel of SVGDB_PRECISION_TC32 (sm_100a).
+//
+//   phi_i = (1/n) [ sum_j k(x_j,x_i) v_j + 2 a x~_i sum_j k(x_j,x_i) ],  v_j = g_j - 2 a x~_j        (SVGD.hpp:407-454)
+//
+// Arithmetic (error budget: DESIGN.md "Precision modes"):
+//   * y = sqrt(2c) (x - mean), c = a log2(e).  Row side  y_i = hi_i + lo_i  (two fp16 terms, 22 bits),
+//     column side  y^_j = fp16(y_j).  The first contraction is  S = y_i . y^_j  (fp16 products are exact in
+//     fp32, fp32 accumulation in TMEM) and the exponent  S + u_i + w_j  with  u_i = 15 - |y_i|^2/2,
+//     w_j = -|y^_j|^2/2  equals  15 - |y_i - y^_j|^2 / 2 <= 15: the kernel matrix is the EXACT Gaussian
+//     kernel between the particles and their fp16-rounded images (2^-12 relative per coordinate).
+//   * E = 2^15 k rounded to fp16 (normal down to k = 2^-29), one MUFU.EX2 per pair (optionally a share of
+//     them as a Cody-Waite + degree-4 polynomial on the FMA pipe); the row sum adds the SAME rounded values
+//     (FHADD), so k(x_i,x_i) = 1 cancels exactly in the repulsive term.
+//   * second contraction  Phi += E . [v_hi ; v_lo]  (v split in two fp16 terms).
+//
+// Mapping onto the SM (one persistent CTA per SM, 10 warps):
+//   * TMEM (512 columns):  S_b [64 b, +64) fp32 for the four (i-tile w, j-half k) units b = 2w + k (E_b aliases its
+//     first 32 columns as fp16 pairs), Phi_w [256 + 64 w, +64) fp32,  A_w [384 + 64 w, +64) = the row operand [hi | lo] of i-tile w, written
+//     ONCE per segment by the exp warps (tcgen05.st) -> every MMA runs in TS mode: only the column operand
+//     is read from shared memory (64 B/clk instead of the 128 B/clk an SS MMA at M = N = 128 needs, which is
+//     the whole shared-memory bandwidth of the SM and was the limiter of the first version of this kernel).
+//   * shared memory: 4 stages of { X^_j tile 16 KB | V_j tile 4 x 8 KB | w_j 512 B }, one TMA producer warp.
+//   * warp 9 issues every tcgen05.mma (M=128, N=64, K=16): per unit 8 MMAs for S and 8 for Phi, four units in
+//     flight (see the kernel's comment); warps 0-3 / 4-7 are the exp warpgroups of i-tile 0 / 1.
+//   * work: the (i-pair, j-tile) rectangle is linearised and cut into one contiguous range per CTA; a CTA
+//     walks its range segment by segment (segment = one i-pair), so operand load, pipeline fill and the
+//     flush of Phi happen ~3 times per SM instead of once per (i-pair, j-split) CTA.
+#pragma once
+#include "kernels_tc32.cuh"
+#include <type_traits>
+
+namespace svgdb {
+namespace tc {
+
+constexpr int P2_STAGES = 4;
+constexpr uint32_t P2_XB_BYTES = 16384;               // 128 particles x 64 fp16 (128 B rows, SWIZZLE_128B)
+constexpr uint32_t P2_VBOX = 8192;                    // 64 coordinates x 64 particles fp16
+constexpr uint32_t P2_V_BYTES = 4 * P2_VBOX;          // hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128)
+constexpr uint32_t P2_W_BYTES = 512;                  // 128 floats
+constexpr uint32_t P2_STAGE = 50176;                  // 49 KB per stage (1024-aligned)
+constexpr uint32_t P2_TX = P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES;
+constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 256 + 1024;
+constexpr int P2_A_LD = 128;                          // XA2 row: [hi(64) | lo(64)] fp16
+constexpr uint32_t P2_COL_PHI = 256, P2_COL_A = 384;
+
+// ---- operand preparation ---------------------------------------------------------------------------
+// One warp per particle.  XA2[row] = [hi | lo] (row operand, read by the owning thread into TMEM),
+// XB2[row] = hi (column operand, TMA), u[row] = 15 - |hi+lo|^2/2, w[row] = -|hi|^2/2 (-inf for padding rows:
+// their kernel values are exactly 0).
+__global__ void split_phi2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
+                                  int64_t n, int64_t n_rows_a, int64_t n_rows_b, int d, __half *__restrict__ XA2,
+                                  __half *__restrict__ XB2, float *__restrict__ u, float *__restrict__ w)
+{
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_a) return;
+    const double c = (*a_ptr) * 1.4426950408889634; // a log2(e)
+    const double scale = sqrt(2.0 * c);
+    double s_full = 0.0, s_hi = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        double y = 0.0;
+        if (row < n && k < d) y = scale * (X[row * d + k] - colsum[k] / (double)n);
+        const __half hi = __double2half(y);
+        const double hid = (double)__half2float(hi);
+        const __half lo = __double2half(y - hid);
+        const double full = hid + (double)__half2float(lo);
+        s_full += full * full;
+        s_hi += hid * hid;
+        XA2[row * P2_A_LD + k] = hi;
+        XA2[row * P2_A_LD + 64 + k] = lo;
+        if (row < n_rows_b) XB2[row * 64 + k] = hi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        s_full += __shfl_xor_sync(0xffffffffu, s_full, o);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
+    }
+    if (lane == 0) {
+        u[row] = (row < n) ? (float)(15.0 - 0.5 * s_full) : 0.0f;
+        if (row < n_rows_b) w[row] = (row < n) ? (float)(-0.5 * s_hi) : -INFINITY;
+    }
+}
+
+// V^T (fp16, [128][ldn]): rows [0,64) v_hi, [64,128) v_lo of v~ = V + 2 a mean (V = G - 2 a X, uncentred).
+// One block = 64 particles, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+make_vt2_kernel(const double *__restrict__ V, const double *__restrict__ colsum, const double *__restrict__ a_ptr, int64_t n,
+                int64_t ldn, int d, __half *__restrict__ VT)
+{
+    __shared__ __half tile[128][64 + 2];
+    const double a = *a_ptr;
+    const int64_t j0 = (int64_t)blockIdx.x * 64;
+    for (int t = threadIdx.x; t < 64 * 64; t += blockDim.x) {
+        const int jl = t >> 6, c = t & 63;
+        const int64_t j = j0 + jl;
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (j < n && c < d) {
+            const double v = V[j * d + c] + 2.0 * a * (colsum[c] / (double)n);
+            hi = __double2half(v);
+            lo = __double2half(v - (double)__half2float(hi));
+        }
+        tile[c][jl] = hi;
+        tile[64 + c][jl] = lo;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 128 * 64; t += blockDim.x) {
+        const int rr = t >> 6, jl = t & 63;
+        if (j0 + jl < ldn) VT[(int64_t)rr * ldn + j0 + jl] = tile[rr][jl];
+    }
+}
+
+// ---- device helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float &a, float &b, float &c, float &d)
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+// (a0 + b0, a1 + b1): one FADD2
+__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1)
+{
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+// acc += lo half, acc2 += hi half of a packed f16x2 (FHADD: fp32 accumulation of the ROUNDED values)
+__device__ __forceinline__ void acc_f16x2(float &acc_lo, float &acc_hi, uint32_t p)
+{
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.rn.f32.f16 %0, l, %0;\n\tadd.rn.f32.f16 %1, h, %1;\n\t}"
+        : "+f"(acc_lo), "+f"(acc_hi)
+        : "r"(p));
+}
+// 2^x for x <= 15 on the FMA / ALU pipes: round-to-nearest split x = n + f (magic-number add), degree-4
+// polynomial for 2^f on [-1/2, 1/2], exponent add.  x is clamped at
+// -126 (results that small round to +0 in fp16 anyway; -inf from padding columns lands there too).
+__device__ __forceinline__ float ex2_poly(float x)
+{
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f; // 1.5 * 2^23: the integer part of x now sits in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = 9.666368515e-3f; // Chebyshev-node fit of 2^f on [-1/2, 1/2]: max rel error 3.6e-6 (fp16 rounding: 2.4e-4)
+    p = fmaf(p, f, 5.592197584e-2f);
+    p = fmaf(p, f, 2.402234904e-1f);
+    p = fmaf(p, f, 6.931210452e-1f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+struct Phi2Args {
+    float *phi_buf;        // [n_pad128 + 256][TC_PHI_LD], zeroed; [0,64) sum_j E v, [64] sum_j E; added atomically
+    const __half *XA2;     // [n_pad128 + 256][128]
+    const float *u;        // [n_pad128 + 256]
+    const float *w;        // [n_pad128]
+    int64_t row0, n_rows;  // this rank's rows
+    int n_jtiles, n_ipairs;
+    int poly;              // pairs (of 16) per 32-column chunk whose exponentials use ex2_poly
+    int dbg;               // development: 1 = exp warps only hand the barriers on, 2 = TMEM load/store without the math
+    int *err;
+    long long *trace;
+};
+
+// segment s of CTA b: i-pair `ip`, j-tiles [jb, je)
+struct P2Seg { int ip, jb, je; };
+__device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, long long end, P2Seg &s)
+{
+    if (pos >= end) return false;
+    s.ip = (int)(pos / p.n_jtiles);
+    s.jb = (int)(pos - (long long)s.ip * p.n_jtiles);
+    const long long seg_end = min(end, (long long)(s.ip + 1) * p.n_jtiles);
+    s.je = s.jb + (int)(seg_end - pos);
+    pos = seg_end;
+    return true;
+}
+
+// POLY of the 16 pairs of a 32-column chunk go through ex2_poly (0 = all MUFU).
+//
+// Pipeline units.  A (i-tile w, j-half k) pair of 128 x 64 pairs is one unit with its own S buffer b = 2w + k
+// (TMEM columns [64 b, +64); E_b aliases its first 32 columns).  Per j-tile the MMA warp issues
+//     [PV(b0) S'(b0)] [PV(b1) S'(b1)] [PV(b2) S'(b2)] [PV(b3) S'(b3)]          (S' = the next j-tile's S)
+// so between the completion of S(b) and the issue of PV(b) lie three other units (1536 tensor-pipe cycles):
+// the commit -> mbarrier -> exp warps -> mbarrier -> MMA warp round trip (~1.5k cycles measured with idle exp
+// warps) no longer starves the tensor pipe, which it did with two 128-column buffers (one unit of slack).
+template <int POLY>
+__global__ void __launch_bounds__(320, 1)
+phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p)
+{
+    // this CTA's contiguous range of (i-pair, j-tile) work units
+    const long long units = (long long)p.n_ipairs * p.n_jtiles;
+    const long long u_beg = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
+    if (u_beg >= u_end) return;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + P2_STAGES * P2_STAGE);
+    uint64_t *full = bars;                  // P2_STAGES: TMA bytes landed
+    uint64_t *empty = full + P2_STAGES;     // P2_STAGES: every MMA reading the stage has completed
+    uint64_t *s_full = empty + P2_STAGES;   // 4: S_b complete
+    uint64_t *e_ready = s_full + 4;         // 4: E_b written (one arrival per exp warp of the tile)
+    uint64_t *phi_full = e_ready + 4;       // 1: every MMA of the segment complete
+    uint64_t *a_ready = phi_full + 1;       // 1: row operands in TMEM, Phi flushed (one arrival per exp warp)
+    uint32_t *tmem_holder = (uint32_t *)(a_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 4); }
+        mbar_init(phi_full, 1);
+        mbar_init(a_ready, 8);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp == 8) { // ---- TMA producer (whole warp runs the loop, one elected lane issues)
+        long long pos = u_beg;
+        P2Seg sg;
+        uint32_t g = 0;
+        bool ok = true;
+        while (ok && p2_segment(p, pos, u_end, sg)) {
+            for (int jt = sg.jb; ok && jt < sg.je; ++jt, ++g) {
+                const uint32_t slot = g % P2_STAGES, use = g / P2_STAGES;
+                if (!mbar_wait(empty + slot, (use & 1) ^ 1, p.err, 10)) { ok = false; break; }
+                if (elect_one()) {
+                    uint8_t *st = smem + slot * P2_STAGE;
+                    const int j0 = jt * TC_TILE;
+                    mbar_arrive_expect_tx(full + slot, P2_TX);
+                    tma_load_2d(st, &mapB, 0, j0, full + slot);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
+                    bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, p.w + j0, P2_W_BYTES, full + slot);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 9) { // ---- MMA issuer: warp-uniform control flow, one elected lane issues
+        const uint32_t idesc = make_idesc_f16(TC_TILE, 64);
+        const uint32_t st_lo0 = desc_lo_k_sw128(smem_u32(smem));
+        uint32_t g = 0;
+        // S_b(gt) = [hi_i | lo_i] . hi_j over the 64 particles of j-half k: 8 TS MMAs (N = 64)
+        auto issue_s = [&](int b, uint32_t gt) -> bool {
+            const int w = b >> 1, k = b & 1;
+            const uint32_t slot = gt % P2_STAGES, use = gt / P2_STAGES;
+            if (b == 0 && !mbar_wait(full + slot, use & 1, p.err, 21)) return false;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t dS = tmem + b * 64, aT = tmem + P2_COL_A + w * 64;
+                const uint32_t bl = st_lo0 + slot * (P2_STAGE >> 4) + k * (8192 >> 4);
+                umma_f16_ts2<false>(dS, aT, bl, idesc);
+                umma_f16_ts2<true>(dS, aT + 8, bl + 2, idesc);
+                umma_f16_ts2<true>(dS, aT + 16, bl + 4, idesc);
+                umma_f16_ts2<true>(dS, aT + 24, bl + 6, idesc);
+                umma_f16_ts2<true>(dS, aT + 32, bl, idesc);
+                umma_f16_ts2<true>(dS, aT + 40, bl + 2, idesc);
+                umma_f16_ts2<true>(dS, aT + 48, bl + 4, idesc);
+                umma_f16_ts2<true>(dS, aT + 56, bl + 6, idesc);
+                umma_commit(s_full + b);
+            }
+            __syncwarp();
+            return true;
+        };
+        // Phi_w += E_b(gt) . [v_hi ; v_lo] (64 particles of j-half k): 8 TS MMAs (N = 64)
+        auto issue_pv = [&](int b, uint32_t gt, bool first, bool last) -> bool {
+            const int w = b >> 1, k = b & 1;
+            if (!mbar_wait(e_ready + b, gt & 1, p.err, 22 + b)) return false;
+            tc_fence_after();
+            const uint32_t slot = gt % P2_STAGES;
+            if (elect_one()) {
+                const uint32_t dP = tmem + P2_COL_PHI + w * 64, e = tmem + b * 64;
+                const uint32_t vh = st_lo0 + slot * (P2_STAGE >> 4) + (P2_XB_BYTES >> 4) + k * (P2_VBOX >> 4), vl = vh + 2 * (P2_VBOX >> 4);
+                umma_f16_ts2r(dP, e, vh, idesc, (first && k == 0) ? 0u : 1u);
+                umma_f16_ts2<true>(dP, e + 8, vh + 2, idesc);
+                umma_f16_ts2<true>(dP, e + 16, vh + 4, idesc);
+                umma_f16_ts2<true>(dP, e + 24, vh + 6, idesc);
+                umma_f16_ts2<true>(dP, e, vl, idesc);
+                umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
+                umma_f16_ts2<true>(dP, e + 16, vl + 4, idesc);
+                umma_f16_ts2<true>(dP, e + 24, vl + 6, idesc);
+                if (b == 3) umma_commit(empty + slot);
+                if (b == 3 && last) umma_commit(phi_full);
+            }
+            __syncwarp();
+            return true;
+        };
+        long long pos = u_beg;
+        P2Seg sg;
+        bool ok = true;
+        for (uint32_t seg = 0; ok && p2_segment(p, pos, u_end, sg); ++seg) {
+            const int nt = sg.je - sg.jb;
+            if (!mbar_wait(a_ready, seg & 1, p.err, 20)) { ok = false; break; }
+            // unit order b = 0, 2, 1, 3: (tile 0, half 0), (tile 1, half 0), (tile 0, half 1), (tile 1, half 1)
+            ok = issue_s(0, g) && issue_s(2, g) && issue_s(1, g) && issue_s(3, g);
+            for (int t = 0; ok && t < nt; ++t) {
+                const bool more = t + 1 < nt, last = !more;
+                if (lane == 0) TC_TRACE(0, g + t, 0);
+                ok = issue_pv(0, g + t, t == 0, last) && (!more || issue_s(0, g + t + 1));
+                if (lane == 0) TC_TRACE(0, g + t, 1);
+                ok = ok && issue_pv(2, g + t, t == 0, last) && (!more || issue_s(2, g + t + 1));
+                if (lane == 0) TC_TRACE(0, g + t, 2);
+                ok = ok && issue_pv(1, g + t, t == 0, last) && (!more || issue_s(1, g + t + 1));
+                if (lane == 0) TC_TRACE(0, g + t, 3);
+                ok = ok && issue_pv(3, g + t, t == 0, last) && (!more || issue_s(3, g + t + 1));
+                if (lane == 0) TC_TRACE(0, g + t, 4);
+            }
+            g += nt;
+        }
+    } else { // ---- exp warpgroups, one i-tile each: thread = TMEM lane = particle row ---------------------------
+        const int w = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tP = tmem + P2_COL_PHI + w * 64 + lane_base;
+        const uint32_t tA = tmem + P2_COL_A + w * 64 + lane_base;
+        long long pos = u_beg;
+        P2Seg sg;
+        uint32_t g = 0;
+        bool ok = true;
+        for (uint32_t seg = 0; ok && p2_segment(p, pos, u_end, sg); ++seg) {
+            const int nt = sg.je - sg.jb;
+            const int64_t iw0 = p.row0 + (int64_t)sg.ip * (2 * TC_TILE) + w * TC_TILE;
+            const int64_t i = iw0 + row;
+            { // row operand [hi | lo] of particle i -> TMEM (the previous segment's MMAs are complete: phi_full)
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.XA2 + i * P2_A_LD);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 x = __ldg(src + 4 * k + q);
+                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                    }
+                    tmem_st16(tA + 16 * k, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+            const float ui = __ldg(p.u + i);
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f; // row sum of the rounded E (4 independent chains)
+            for (int t = 0; ok && t < nt; ++t) {
+                const uint32_t gt = g + t, slot = gt % P2_STAGES, use = gt / P2_STAGES;
+                if (!mbar_wait(full + slot, use & 1, p.err, 32 + w)) { ok = false; break; } // w_j visible to this thread
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int b = 2 * w + k;
+                    const uint32_t tS = tmem + b * 64 + lane_base;
+                    const int64_t j0 = (int64_t)(sg.jb + t) * TC_TILE + 64 * k;
+                    const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this half tile, if inside [0,64)
+                    const bool has_diag = (j0 < iw0 + TC_TILE) && (j0 + 64 > iw0);
+                    const uint32_t w_addr = smem_u32(smem + slot * P2_STAGE + P2_XB_BYTES + P2_V_BYTES) + 256u * k;
+                    if (row == 0) TC_TRACE(1 + w, gt, 1 + 3 * k);
+                    if (!mbar_wait(s_full + b, gt & 1, p.err, 40 + b)) { ok = false; break; }
+                    if (row == 0) TC_TRACE(1 + w, gt, 2 + 3 * k);
+                    tc_fence_after();
+                    if (p.dbg != 1) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tS, r0);
+                        tmem_ld32(tS + 32, r1);
+                        // 32-column chunk c: exponentials of rr[] -> fp16 pairs over S columns [16c, 16c+16) (already read)
+                        auto exp_chunk = [&](const uint32_t (&rr)[32], int c, auto diag_tag) {
+                            constexpr bool DIAG = decltype(diag_tag)::value;
+                            uint32_t packed[16];
+                            const int dq = dcol - c * 32;
+#pragma unroll
+                            for (int q4 = 0; q4 < 8; ++q4) {
+                                float w0, w1, w2, w3;
+                                lds128(w_addr + c * 128 + q4 * 16, w0, w1, w2, w3);
+                                float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
+                                float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
+                                add2(w0, w1, ui, ui);
+                                add2(w2, w3, ui, ui);
+                                add2(x0, x1, w0, w1);
+                                add2(x2, x3, w2, w3);
+                                float e0, e1, e2, e3;
+                                if (2 * q4 < POLY) { e0 = ex2_poly(x0); e1 = ex2_poly(x1); } else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+                                if (2 * q4 + 1 < POLY) { e2 = ex2_poly(x2); e3 = ex2_poly(x3); } else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
+                                if (DIAG) { // k(x_i, x_i) = exp(0) exactly, like the reference (2^15 after the fp16 scaling)
+                                    if (dq == 4 * q4) e0 = 32768.0f;
+                                    if (dq == 4 * q4 + 1) e1 = 32768.0f;
+                                    if (dq == 4 * q4 + 2) e2 = 32768.0f;
+                                    if (dq == 4 * q4 + 3) e3 = 32768.0f;
+                                }
+                                packed[2 * q4] = pack_f16x2(e0, e1);
+                                packed[2 * q4 + 1] = pack_f16x2(e2, e3);
+                                acc_f16x2(rs0, rs1, packed[2 * q4]);
+                                acc_f16x2(rs2, rs3, packed[2 * q4 + 1]);
+                            }
+                            tmem_st16(tS + c * 16, packed);
+                        };
+                        tmem_ld_wait();
+                        if (p.dbg == 2) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) pk[q] = r0[q] ^ r1[2 * q];
+                            tmem_st16(tS, pk);
+                            tmem_st16(tS + 16, pk);
+                        } else if (has_diag) {
+                            exp_chunk(r0, 0, std::true_type{});
+                            exp_chunk(r1, 1, std::true_type{});
+                        } else {
+                            exp_chunk(r0, 0, std::false_type{});
+                            exp_chunk(r1, 1, std::false_type{});
+                        }
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(e_ready + b);
+                    if (row == 0) TC_TRACE(1 + w, gt, 3 + 3 * k);
+                }
+            }
+            g += nt;
+            if (!ok || !mbar_wait(phi_full, seg & 1, p.err, 50)) { ok = false; break; }
+            tc_fence_after();
+            { // ---- flush Phi_w and the row sum: TMEM -> global partial sums
+                const bool valid = i < p.row0 + p.n_rows;
+                float *dst = p.phi_buf + i * TC_PHI_LD;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tP + c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) atomicAdd(dst + c0 + q, __uint_as_float(v[q]) * TC_E_UNSCALE);
+                    }
+                }
+                if (valid) atomicAdd(dst + TC_ONES_ROW, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
+                tc_fence_before(); // the a_ready arrival of the next segment orders these loads before its first MMA
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+} // namespace tc
+} // namespace svgdb

@@ -22,6 +22,7 @@
 #include "select.cuh"
 #ifdef SVGDB_WITH_TC32
 #include "kernels_tc32.cuh"
+#include "kernels_phi_tc.cuh"
 #endif
 
 using namespace svgdb;
@@ -134,6 +135,14 @@ struct svgdb_ctx {
     int *tc_err = nullptr;
     long long *tc_trace = nullptr; // SVGDB_TC_TRACE=<file>: timeline of CTA 0 of the pair-interaction kernel
     CUtensorMap mapA{}, mapB{}, mapV{};
+    // persistent pair-interaction kernel (kernels_phi_tc.cuh): fp16 row / column operands, exponent offsets, V^T
+    __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
+    float *u2 = nullptr, *w2 = nullptr;
+    CUtensorMap mapB2{}, mapV2{};
+    int phi_version = 2; // SVGDB_PHI_KERNEL=1 selects the first (SS-mode, one CTA per j-split) kernel
+    int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
+    int phi_split = 1;   // SVGDB_PHI_SPLIT=0: one exp warpgroup per i-tile instead of both on the same tile
+    int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
 
     // measurement
     svgdb_stats stats{};
@@ -174,7 +183,9 @@ int fail(svgdb_ctx *ctx, int code, const std::string &msg)
 #define KERNEL_CHECK()                                                                                   \
     do {                                                                                                 \
         ++ctx->stats.kernel_launches;                                                                    \
-        CU(cudaGetLastError());                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, SVGDB_ERR_CUDA, std::string("kernel launch at svgd_b200_api.cu:") + std::to_string(__LINE__) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
 // Gauss-Jordan inverse with partial pivoting (double).  A is d x d; returns false if singular.
@@ -230,6 +241,9 @@ int free_sharded(svgdb_ctx *ctx)
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
     cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
+    cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->u2); cudaFree(ctx->w2);
+    ctx->XA2 = ctx->XB2 = ctx->VT2 = nullptr;
+    ctx->u2 = ctx->w2 = nullptr;
     ctx->tc_trace = nullptr;
     ctx->XA = ctx->XB = nullptr;
     ctx->VT = nullptr;
@@ -289,6 +303,20 @@ int alloc_tc32(svgdb_ctx *ctx)
     TRY(make_bf16_map(ctx, &ctx->mapA, ctx->XA, np, TC_KTOT, 128));
     TRY(make_bf16_map(ctx, &ctx->mapB, ctx->XB, np, TC_KTOT, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV, ctx->VT, TC_NV, np, TC_NVH));
+    // persistent kernel operands (16-bit elements: the bf16 tensor-map type moves fp16 bit patterns unchanged)
+    CU(cudaMalloc(&ctx->XA2, (np + 256) * P2_A_LD * 2));
+    CU(cudaMalloc(&ctx->XB2, np * 64 * 2));
+    CU(cudaMalloc(&ctx->VT2, (size_t)128 * np * 2));
+    CU(cudaMalloc(&ctx->u2, (np + 256) * 4));
+    CU(cudaMalloc(&ctx->w2, np * 4));
+    CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * P2_A_LD * 2, ctx->stream));
+    CU(cudaMemsetAsync(ctx->u2, 0, (np + 256) * 4, ctx->stream));
+    TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
+    TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
+    if (const char *e = std::getenv("SVGDB_PHI_KERNEL")) ctx->phi_version = std::atoi(e) == 1 ? 1 : 2;
+    if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_SPLIT")) ctx->phi_split = std::atoi(e) != 0;
+    if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     return SVGDB_OK;
 }
 #endif
@@ -752,23 +780,60 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
-    TRY(launch_tc_split(ctx, SPLIT_PHI)); // the operands now carry the bandwidth: the accumulator is the exponent
-    make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
-                                                                            ctx->d, ctx->VT);
-    KERNEL_CHECK();
     CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, ctx->stream));
-    PhiTcArgs a{};
-    a.phi_buf = ctx->phi_buf;
-    a.n_total = ctx->N;
-    a.row0 = ctx->row0;
-    a.n_rows = ctx->n_rows;
-    a.n_jtiles = (int)(ctx->n_pad128 / 128);
-    const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
-    a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
-    a.err = ctx->tc_err;
-    a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
-    phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
-    KERNEL_CHECK();
+    if (ctx->phi_version == 2) {
+        const int64_t rows_a = ctx->n_pad128 + 256;
+        split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a,
+                                                                                  ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->u2, ctx->w2);
+        KERNEL_CHECK();
+        make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d,
+                                                                                 ctx->VT2);
+        KERNEL_CHECK();
+        Phi2Args a{};
+        a.phi_buf = ctx->phi_buf;
+        a.XA2 = ctx->XA2;
+        a.u = ctx->u2;
+        a.w = ctx->w2;
+        a.row0 = ctx->row0;
+        a.n_rows = ctx->n_rows;
+        a.n_jtiles = (int)(ctx->n_pad128 / 128);
+        a.n_ipairs = (int)((ctx->n_rows + 255) / 256);
+        a.poly = ctx->phi_poly;
+        a.err = ctx->tc_err;
+        a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
+        const long long units = (long long)a.n_ipairs * a.n_jtiles;
+        const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units);
+        a.dbg = ctx->phi_dbg_mode;
+#define SVGDB_PHI2_CASE(P)                                                                                \
+    case P: phi2_tc32_kernel<P><<<grid, 320, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
+        switch (ctx->phi_poly) {
+            SVGDB_PHI2_CASE(0)
+            SVGDB_PHI2_CASE(2)
+            SVGDB_PHI2_CASE(4)
+            SVGDB_PHI2_CASE(6)
+            SVGDB_PHI2_CASE(8)
+        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
+        }
+#undef SVGDB_PHI2_CASE
+        KERNEL_CHECK();
+    } else {
+        TRY(launch_tc_split(ctx, SPLIT_PHI)); // the operands now carry the bandwidth: the accumulator is the exponent
+        make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
+                                                                                ctx->d, ctx->VT);
+        KERNEL_CHECK();
+        PhiTcArgs a{};
+        a.phi_buf = ctx->phi_buf;
+        a.n_total = ctx->N;
+        a.row0 = ctx->row0;
+        a.n_rows = ctx->n_rows;
+        a.n_jtiles = (int)(ctx->n_pad128 / 128);
+        const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
+        a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
+        a.err = ctx->tc_err;
+        a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
+        phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
+        KERNEL_CHECK();
+    }
     ++ctx->stats.phi_launches;
     if (ctx->tc_trace) {
         std::vector<long long> h(3 * 64 * 8);
@@ -796,6 +861,11 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     o.X_out = ctx->X[ctx->cur ^ 1];
     o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
     int64_t cnt = ctx->n_rows * ctx->d;
+    if (ctx->phi_dbg_mode != 0 && !debug_phi) { // development: the kernel produced garbage on purpose, keep the particles
+        CU(cudaMemcpyAsync(ctx->X[ctx->cur ^ 1] + ctx->row0 * ctx->d, ctx->X[ctx->cur] + ctx->row0 * ctx->d, (size_t)cnt * sizeof(double),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+        return SVGDB_OK;
+    }
     opt_update_tc32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
     KERNEL_CHECK();
     return SVGDB_OK;
@@ -943,6 +1013,14 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         if (d > svgdb::tc::TC_D)
             return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
         CU(cudaFuncSetAttribute(svgdb::tc::phi_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_PHI_SMEM));
+#define SVGDB_PHI2_ATTR(P) \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2_SMEM));
+        SVGDB_PHI2_ATTR(0)
+        SVGDB_PHI2_ATTR(2)
+        SVGDB_PHI2_ATTR(4)
+        SVGDB_PHI2_ATTR(6)
+        SVGDB_PHI2_ATTR(8)
+#undef SVGDB_PHI2_ATTR
         CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_HIST));
         CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_BASE));
     }
