@@ -36,20 +36,40 @@ constexpr int P2_STAGES = 4;
 constexpr uint32_t P2_XB_BYTES = 16384;               // 128 particles x 64 fp16 (128 B rows, SWIZZLE_128B)
 constexpr uint32_t P2_VBOX = 8192;                    // 64 coordinates x 64 particles fp16
 constexpr uint32_t P2_V_BYTES = 4 * P2_VBOX;          // hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128)
-constexpr uint32_t P2_W_BYTES = 512;                  // 128 floats
-constexpr uint32_t P2_STAGE = 50176;                  // 49 KB per stage (1024-aligned)
+constexpr uint32_t P2_W_BYTES = 4096;                 // 128 particles x 16 fp16 exponent-offset columns (no-swizzle core-matrix order)
+constexpr uint32_t P2_STAGE = 53248;                  // 52 KB per stage (1024-aligned)
 constexpr uint32_t P2_TX = P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES;
-constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 256 + 1024;
+constexpr uint32_t P2_AEX_BYTES = 4096;               // per i-tile: 128 rows x 16 fp16 exponent-offset columns
+constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 2 * P2_AEX_BYTES + 256 + 1024;
+// K-major operand of 16 fp16 columns WITHOUT swizzle: 8 x 16 B core matrices; row r, column k lives at
+// (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2   (LBO = 128 B between the two K halves, SBO = 256 B per 8 rows)
+__host__ __device__ constexpr uint32_t p2_ex_offset(uint32_t r, uint32_t k) { return (r >> 3) * 256u + (k >> 3) * 128u + (r & 7u) * 16u + (k & 7u) * 2u; }
+constexpr uint32_t DESC_HI_K_NOSW = (256u >> 4) | (1u << 14);  // SBO = 256 B, version 1, SWIZZLE_NONE
+constexpr uint32_t DESC_LO_K_NOSW_LBO = (128u >> 4) << 16;     // LBO = 128 B
 constexpr int P2_A_LD = 128;                          // XA2 row: [hi(64) | lo(64)] fp16
 constexpr uint32_t P2_COL_PHI = 256, P2_COL_A = 384;
 
 // ---- operand preparation ---------------------------------------------------------------------------
+// Three-term fp16 split of a scalar (33 significant bits): v ~= t0 + t1 + t2.
+__device__ __forceinline__ void split3_f16(double v, __half &t0, __half &t1, __half &t2)
+{
+    v = fmax(v, -60000.0); // below every exponent that matters, above the fp16 range limit
+    t0 = __double2half(v);
+    double rem = v - (double)__half2float(t0);
+    t1 = __double2half(rem);
+    rem -= (double)__half2float(t1);
+    t2 = __double2half(rem);
+}
+
 // One warp per particle.  XA2[row] = [hi | lo] (row operand, read by the owning thread into TMEM),
-// XB2[row] = hi (column operand, TMA), u[row] = 15 - |hi+lo|^2/2, w[row] = -|hi|^2/2 (-inf for padding rows:
-// their kernel values are exactly 0).
+// XB2[row] = hi (column operand, TMA).  The exponent offsets u = 15 - |hi+lo|^2/2 (row) and w = -|hi|^2/2
+// (column; -60000 for padding rows, whose kernel values are then exactly 0) ride in a 16-column K chunk
+//     UA[row] = [u0 u1 u2 1 1 1 0..]      WB[row] = [1 1 1 w0 w1 w2 0..]      (three-term fp16 splits)
+// so that the accumulator of the first contraction IS the exponent.  WB is stored per 128-particle tile in the
+// core-matrix order the MMA reads (p2_ex_offset), UA as plain rows.
 __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
                                   int64_t n, int64_t n_rows_a, int64_t n_rows_b, int d, __half *__restrict__ XA2,
-                                  __half *__restrict__ XB2, float *__restrict__ u, float *__restrict__ w)
+                                  __half *__restrict__ XB2, __half *__restrict__ UA, __half *__restrict__ WB)
 {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
@@ -76,9 +96,16 @@ __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__
         s_full += __shfl_xor_sync(0xffffffffu, s_full, o);
         s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
     }
-    if (lane == 0) {
-        u[row] = (row < n) ? (float)(15.0 - 0.5 * s_full) : 0.0f;
-        if (row < n_rows_b) w[row] = (row < n) ? (float)(-0.5 * s_hi) : -INFINITY;
+    if (lane < 16) {
+        __half u0, u1, u2, w0, w1, w2;
+        split3_f16((row < n) ? 15.0 - 0.5 * s_full : 0.0, u0, u1, u2);
+        split3_f16((row < n) ? -0.5 * s_hi : -60000.0, w0, w1, w2);
+        const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+        const __half ua = lane == 0 ? u0 : lane == 1 ? u1 : lane == 2 ? u2 : lane < 6 ? one : zero;
+        const __half wb = lane < 3 ? one : lane == 3 ? w0 : lane == 4 ? w1 : lane == 5 ? w2 : zero;
+        UA[row * 16 + lane] = ua;
+        if (row < n_rows_b)
+            *reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(WB) + (row >> 7) * P2_W_BYTES + p2_ex_offset((uint32_t)(row & 127), (uint32_t)lane)) = wb;
     }
 }
 
@@ -117,16 +144,15 @@ __device__ __forceinline__ void bulk_load_1d(void *dst_smem, const void *src, ui
                  ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void lds128(uint32_t addr, float &a, float &b, float &c, float &d)
+// SS MMA with explicit descriptor words for both operands (any layout), accumulating
+__device__ __forceinline__ void umma_f16_ss_desc(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc)
 {
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
-}
-// (a0 + b0, a1 + b1): one FADD2
-__device__ __forceinline__ void add2(float &a0, float &a1, float b0, float b1)
-{
-    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
-        : "+f"(a0), "+f"(a1)
-        : "f"(b0), "f"(b1));
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "setp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+                 : "memory");
 }
 // acc += lo half, acc2 += hi half of a packed f16x2 (FHADD: fp32 accumulation of the ROUNDED values)
 __device__ __forceinline__ void acc_f16x2(float &acc_lo, float &acc_hi, uint32_t p)
@@ -154,8 +180,8 @@ __device__ __forceinline__ float ex2_poly(float x)
 struct Phi2Args {
     float *phi_buf;        // [n_pad128 + 256][TC_PHI_LD], zeroed; [0,64) sum_j E v, [64] sum_j E; added atomically
     const __half *XA2;     // [n_pad128 + 256][128]
-    const float *u;        // [n_pad128 + 256]
-    const float *w;        // [n_pad128]
+    const __half *UA;      // [n_pad128 + 256][16] row exponent-offset chunk
+    const __half *WB;      // [n_pad128 / 128][4 KB] column exponent-offset chunks, core-matrix order
     int64_t row0, n_rows;  // this rank's rows
     int n_jtiles, n_ipairs;
     int poly;              // pairs (of 16) per 32-column chunk whose exponentials use ex2_poly
@@ -185,8 +211,10 @@ __device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, lo
 // so between the completion of S(b) and the issue of PV(b) lie three other units (1536 tensor-pipe cycles):
 // the commit -> mbarrier -> exp warps -> mbarrier -> MMA warp round trip (~1.5k cycles measured with idle exp
 // warps) no longer starves the tensor pipe, which it did with two 128-column buffers (one unit of slack).
+constexpr int P2_THREADS = 352; // warps 0-3 / 4-7: exp warpgroups of i-tile 0 / 1; 8: TMA producer; 9, 10: MMA issuers of i-tile 0 / 1
+
 template <int POLY>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(P2_THREADS, 1)
 phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p)
 {
     // this CTA's contiguous range of (i-pair, j-tile) work units
@@ -196,21 +224,21 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t *)(smem + P2_STAGES * P2_STAGE);
+    uint8_t *sAex = smem + P2_STAGES * P2_STAGE; // [2][P2_AEX_BYTES]
+    uint64_t *bars = (uint64_t *)(sAex + 2 * P2_AEX_BYTES);
     uint64_t *full = bars;                  // P2_STAGES: TMA bytes landed
     uint64_t *empty = full + P2_STAGES;     // P2_STAGES: every MMA reading the stage has completed
     uint64_t *s_full = empty + P2_STAGES;   // 4: S_b complete
     uint64_t *e_ready = s_full + 4;         // 4: E_b written (one arrival per exp warp of the tile)
-    uint64_t *phi_full = e_ready + 4;       // 1: every MMA of the segment complete
-    uint64_t *a_ready = phi_full + 1;       // 1: row operands in TMEM, Phi flushed (one arrival per exp warp)
-    uint32_t *tmem_holder = (uint32_t *)(a_ready + 1);
+    uint64_t *phi_full = e_ready + 4;       // [2] every MMA of the segment on tile w complete
+    uint64_t *a_ready = phi_full + 2;       // [2] row operand of tile w in TMEM, Phi_w flushed (one arrival per exp warp)
+    uint32_t *tmem_holder = (uint32_t *)(a_ready + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2); }
         for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 4); }
-        mbar_init(phi_full, 1);
-        mbar_init(a_ready, 8);
+        for (int s = 0; s < 2; ++s) { mbar_init(phi_full + s, 1); mbar_init(a_ready + s, 4); }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(tmem_holder, 512);
@@ -236,20 +264,23 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
-                    bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, p.w + j0, P2_W_BYTES, full + slot);
+                    bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, reinterpret_cast<const uint8_t *>(p.WB) + (size_t)jt * P2_W_BYTES, P2_W_BYTES, full + slot);
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == 9) { // ---- MMA issuer: warp-uniform control flow, one elected lane issues
+    } else if (warp >= 9) { // ---- MMA issuer of i-tile wm: warp-uniform control flow, one elected lane issues
+        const int wm = warp - 9;
         const uint32_t idesc = make_idesc_f16(TC_TILE, 64);
         const uint32_t st_lo0 = desc_lo_k_sw128(smem_u32(smem));
+        const uint32_t aex_lo0 = desc_lo_k_sw128(smem_u32(sAex)) | DESC_LO_K_NOSW_LBO;
+        const uint32_t wb_lo0 = desc_lo_k_sw128(smem_u32(smem + P2_XB_BYTES + P2_V_BYTES)) | DESC_LO_K_NOSW_LBO;
         uint32_t g = 0;
         // S_b(gt) = [hi_i | lo_i] . hi_j over the 64 particles of j-half k: 8 TS MMAs (N = 64)
         auto issue_s = [&](int b, uint32_t gt) -> bool {
             const int w = b >> 1, k = b & 1;
             const uint32_t slot = gt % P2_STAGES, use = gt / P2_STAGES;
-            if (b == 0 && !mbar_wait(full + slot, use & 1, p.err, 21)) return false;
+            if (k == 0 && !mbar_wait(full + slot, use & 1, p.err, 21)) return false;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t dS = tmem + b * 64, aT = tmem + P2_COL_A + w * 64;
@@ -262,6 +293,9 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dS, aT + 40, bl + 2, idesc);
                 umma_f16_ts2<true>(dS, aT + 48, bl + 4, idesc);
                 umma_f16_ts2<true>(dS, aT + 56, bl + 6, idesc);
+                // + u_i + w_j: the 16-column exponent-offset chunks (no-swizzle operands, both from shared memory)
+                umma_f16_ss_desc(dS, aex_lo0 + w * (P2_AEX_BYTES >> 4), DESC_HI_K_NOSW,
+                                 wb_lo0 + slot * (P2_STAGE >> 4) + k * (2048 >> 4), DESC_HI_K_NOSW, idesc);
                 umma_commit(s_full + b);
             }
             __syncwarp();
@@ -284,8 +318,8 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
                 umma_f16_ts2<true>(dP, e + 16, vl + 4, idesc);
                 umma_f16_ts2<true>(dP, e + 24, vl + 6, idesc);
-                if (b == 3) umma_commit(empty + slot);
-                if (b == 3 && last) umma_commit(phi_full);
+                if (k == 1) umma_commit(empty + slot);
+                if (k == 1 && last) umma_commit(phi_full + w);
             }
             __syncwarp();
             return true;
@@ -295,20 +329,16 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         bool ok = true;
         for (uint32_t seg = 0; ok && p2_segment(p, pos, u_end, sg); ++seg) {
             const int nt = sg.je - sg.jb;
-            if (!mbar_wait(a_ready, seg & 1, p.err, 20)) { ok = false; break; }
-            // unit order b = 0, 2, 1, 3: (tile 0, half 0), (tile 1, half 0), (tile 0, half 1), (tile 1, half 1)
-            ok = issue_s(0, g) && issue_s(2, g) && issue_s(1, g) && issue_s(3, g);
+            if (!mbar_wait(a_ready + wm, seg & 1, p.err, 20)) { ok = false; break; }
+            const int b0 = 2 * wm, b1 = b0 + 1; // this tile's units: j-half 0 and 1
+            ok = issue_s(b0, g) && issue_s(b1, g);
             for (int t = 0; ok && t < nt; ++t) {
                 const bool more = t + 1 < nt, last = !more;
-                if (lane == 0) TC_TRACE(0, g + t, 0);
-                ok = issue_pv(0, g + t, t == 0, last) && (!more || issue_s(0, g + t + 1));
-                if (lane == 0) TC_TRACE(0, g + t, 1);
-                ok = ok && issue_pv(2, g + t, t == 0, last) && (!more || issue_s(2, g + t + 1));
-                if (lane == 0) TC_TRACE(0, g + t, 2);
-                ok = ok && issue_pv(1, g + t, t == 0, last) && (!more || issue_s(1, g + t + 1));
-                if (lane == 0) TC_TRACE(0, g + t, 3);
-                ok = ok && issue_pv(3, g + t, t == 0, last) && (!more || issue_s(3, g + t + 1));
-                if (lane == 0) TC_TRACE(0, g + t, 4);
+                if (lane == 0 && wm == 0) TC_TRACE(0, g + t, 0);
+                ok = issue_pv(b0, g + t, t == 0, last) && (!more || issue_s(b0, g + t + 1));
+                if (lane == 0 && wm == 0) TC_TRACE(0, g + t, 1);
+                ok = ok && issue_pv(b1, g + t, t == 0, last) && (!more || issue_s(b1, g + t + 1));
+                if (lane == 0 && wm == 0) TC_TRACE(0, g + t, 2);
             }
             g += nt;
         }
@@ -338,16 +368,21 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     }
                     tmem_st16(tA + 16 * k, v);
                 }
+                // ... and its exponent-offset chunk [u0 u1 u2 1 1 1 0..] -> shared memory, core-matrix order (SS operand)
+                const uint4 *usrc = reinterpret_cast<const uint4 *>(p.UA + i * 16);
+                const uint32_t aex = smem_u32(sAex + w * P2_AEX_BYTES) + p2_ex_offset((uint32_t)row, 0);
+                const uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex), "r"(ua0.x), "r"(ua0.y), "r"(ua0.z), "r"(ua0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex + 128u), "r"(ua1.x), "r"(ua1.y), "r"(ua1.z), "r"(ua1.w) : "memory");
+                fence_proxy_async(); // generic-proxy stores -> visible to the MMA's async-proxy reads
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);
+                if (lane == 0) mbar_arrive(a_ready + w);
             }
-            const float ui = __ldg(p.u + i);
             float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f; // row sum of the rounded E (4 independent chains)
             for (int t = 0; ok && t < nt; ++t) {
-                const uint32_t gt = g + t, slot = gt % P2_STAGES, use = gt / P2_STAGES;
-                if (!mbar_wait(full + slot, use & 1, p.err, 32 + w)) { ok = false; break; } // w_j visible to this thread
+                const uint32_t gt = g + t;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int b = 2 * w + k;
@@ -355,7 +390,6 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     const int64_t j0 = (int64_t)(sg.jb + t) * TC_TILE + 64 * k;
                     const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this half tile, if inside [0,64)
                     const bool has_diag = (j0 < iw0 + TC_TILE) && (j0 + 64 > iw0);
-                    const uint32_t w_addr = smem_u32(smem + slot * P2_STAGE + P2_XB_BYTES + P2_V_BYTES) + 256u * k;
                     if (row == 0) TC_TRACE(1 + w, gt, 1 + 3 * k);
                     if (!mbar_wait(s_full + b, gt & 1, p.err, 40 + b)) { ok = false; break; }
                     if (row == 0) TC_TRACE(1 + w, gt, 2 + 3 * k);
@@ -371,14 +405,8 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                             const int dq = dcol - c * 32;
 #pragma unroll
                             for (int q4 = 0; q4 < 8; ++q4) {
-                                float w0, w1, w2, w3;
-                                lds128(w_addr + c * 128 + q4 * 16, w0, w1, w2, w3);
-                                float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
-                                float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
-                                add2(w0, w1, ui, ui);
-                                add2(w2, w3, ui, ui);
-                                add2(x0, x1, w0, w1);
-                                add2(x2, x3, w2, w3);
+                                const float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
+                                const float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
                                 float e0, e1, e2, e3;
                                 if (2 * q4 < POLY) { e0 = ex2_poly(x0); e1 = ex2_poly(x1); } else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
                                 if (2 * q4 + 1 < POLY) { e2 = ex2_poly(x2); e3 = ex2_poly(x3); } else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
@@ -418,7 +446,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 }
             }
             g += nt;
-            if (!ok || !mbar_wait(phi_full, seg & 1, p.err, 50)) { ok = false; break; }
+            if (!ok || !mbar_wait(phi_full + w, seg & 1, p.err, 50)) { ok = false; break; }
             tc_fence_after();
             { // ---- flush Phi_w and the row sum: TMEM -> global partial sums
                 const bool valid = i < p.row0 + p.n_rows;

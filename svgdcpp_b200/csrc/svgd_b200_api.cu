@@ -137,7 +137,7 @@ struct svgdb_ctx {
     CUtensorMap mapA{}, mapB{}, mapV{};
     // persistent pair-interaction kernel (kernels_phi_tc.cuh): fp16 row / column operands, exponent offsets, V^T
     __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
-    float *u2 = nullptr, *w2 = nullptr;
+    __half *UA2 = nullptr, *WB2 = nullptr; // exponent-offset K chunks (row / column side)
     CUtensorMap mapB2{}, mapV2{};
     int phi_version = 2; // SVGDB_PHI_KERNEL=1 selects the first (SS-mode, one CTA per j-split) kernel
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
@@ -241,9 +241,9 @@ int free_sharded(svgdb_ctx *ctx)
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
     cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
-    cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->u2); cudaFree(ctx->w2);
+    cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->UA2); cudaFree(ctx->WB2);
     ctx->XA2 = ctx->XB2 = ctx->VT2 = nullptr;
-    ctx->u2 = ctx->w2 = nullptr;
+    ctx->UA2 = ctx->WB2 = nullptr;
     ctx->tc_trace = nullptr;
     ctx->XA = ctx->XB = nullptr;
     ctx->VT = nullptr;
@@ -307,10 +307,10 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->XA2, (np + 256) * P2_A_LD * 2));
     CU(cudaMalloc(&ctx->XB2, np * 64 * 2));
     CU(cudaMalloc(&ctx->VT2, (size_t)128 * np * 2));
-    CU(cudaMalloc(&ctx->u2, (np + 256) * 4));
-    CU(cudaMalloc(&ctx->w2, np * 4));
+    CU(cudaMalloc(&ctx->UA2, (np + 256) * 16 * 2));
+    CU(cudaMalloc(&ctx->WB2, np / 128 * P2_W_BYTES));
     CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * P2_A_LD * 2, ctx->stream));
-    CU(cudaMemsetAsync(ctx->u2, 0, (np + 256) * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->UA2, 0, (np + 256) * 16 * 2, ctx->stream));
     TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_KERNEL")) ctx->phi_version = std::atoi(e) == 1 ? 1 : 2;
@@ -784,7 +784,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
     if (ctx->phi_version == 2) {
         const int64_t rows_a = ctx->n_pad128 + 256;
         split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a,
-                                                                                  ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->u2, ctx->w2);
+                                                                                  ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
         KERNEL_CHECK();
         make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d,
                                                                                  ctx->VT2);
@@ -792,8 +792,8 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
         Phi2Args a{};
         a.phi_buf = ctx->phi_buf;
         a.XA2 = ctx->XA2;
-        a.u = ctx->u2;
-        a.w = ctx->w2;
+        a.UA = ctx->UA2;
+        a.WB = ctx->WB2;
         a.row0 = ctx->row0;
         a.n_rows = ctx->n_rows;
         a.n_jtiles = (int)(ctx->n_pad128 / 128);
@@ -805,7 +805,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
         const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units);
         a.dbg = ctx->phi_dbg_mode;
 #define SVGDB_PHI2_CASE(P)                                                                                \
-    case P: phi2_tc32_kernel<P><<<grid, 320, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
+    case P: phi2_tc32_kernel<P><<<grid, P2_THREADS, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
         switch (ctx->phi_poly) {
             SVGDB_PHI2_CASE(0)
             SVGDB_PHI2_CASE(2)
