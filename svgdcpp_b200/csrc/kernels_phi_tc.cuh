@@ -381,70 +381,91 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (lane == 0) mbar_arrive(a_ready + w);
             }
             float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f; // row sum of the rounded E (4 independent chains)
-            for (int t = 0; ok && t < nt; ++t) {
-                const uint32_t gt = g + t;
+            // Units of this tile in order (j-tile t, half k).  The S of the NEXT unit is fetched from TMEM while the E of this
+            // one is still being stored, so the tcgen05.ld / tcgen05.st round trips overlap instead of adding up.
+            const uint32_t nunits = 2u * (uint32_t)nt;
+            uint32_t r0[32], r1[32];
+            {
+                if (row == 0) TC_TRACE(1 + w, g, 1);
+                if (!mbar_wait(s_full + 2 * w, g & 1, p.err, 40 + 2 * w)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t tS0 = tmem + (2 * w) * 64 + lane_base;
+                tmem_ld32(tS0, r0);
+                tmem_ld32(tS0 + 32, r1);
+            }
+            for (uint32_t q = 0; ok && q < nunits; ++q) {
+                const int k = (int)(q & 1u);
+                const uint32_t gt = g + (q >> 1);
+                const int b = 2 * w + k;
+                const uint32_t tS = tmem + b * 64 + lane_base;
+                const int64_t j0 = (int64_t)(sg.jb + (int)(q >> 1)) * TC_TILE + 64 * k;
+                const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this half tile, if inside [0,64)
+                const bool has_diag = (j0 < iw0 + TC_TILE) && (j0 + 64 > iw0);
+                tmem_ld_wait();
+                if (row == 0) TC_TRACE(1 + w, gt, 2 + 3 * k);
+                uint32_t pk0[16], pk1[16];
+                // 32-column chunk ch: exponentials of rr[] -> fp16 pairs, E columns [16 ch, 16 ch + 16) (over the S columns already read)
+                auto exp_chunk = [&](const uint32_t (&rr)[32], uint32_t (&packed)[16], int ch, auto diag_tag) {
+                    constexpr bool DIAG = decltype(diag_tag)::value;
+                    const int dq = dcol - ch * 32;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int b = 2 * w + k;
-                    const uint32_t tS = tmem + b * 64 + lane_base;
-                    const int64_t j0 = (int64_t)(sg.jb + t) * TC_TILE + 64 * k;
-                    const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this half tile, if inside [0,64)
-                    const bool has_diag = (j0 < iw0 + TC_TILE) && (j0 + 64 > iw0);
-                    if (row == 0) TC_TRACE(1 + w, gt, 1 + 3 * k);
-                    if (!mbar_wait(s_full + b, gt & 1, p.err, 40 + b)) { ok = false; break; }
-                    if (row == 0) TC_TRACE(1 + w, gt, 2 + 3 * k);
-                    tc_fence_after();
-                    if (p.dbg != 1) {
-                        uint32_t r0[32], r1[32];
-                        tmem_ld32(tS, r0);
-                        tmem_ld32(tS + 32, r1);
-                        // 32-column chunk c: exponentials of rr[] -> fp16 pairs over S columns [16c, 16c+16) (already read)
-                        auto exp_chunk = [&](const uint32_t (&rr)[32], int c, auto diag_tag) {
-                            constexpr bool DIAG = decltype(diag_tag)::value;
-                            uint32_t packed[16];
-                            const int dq = dcol - c * 32;
-#pragma unroll
-                            for (int q4 = 0; q4 < 8; ++q4) {
-                                const float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
-                                const float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
-                                float e0, e1, e2, e3;
-                                if (2 * q4 < POLY) { e0 = ex2_poly(x0); e1 = ex2_poly(x1); } else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
-                                if (2 * q4 + 1 < POLY) { e2 = ex2_poly(x2); e3 = ex2_poly(x3); } else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
-                                if (DIAG) { // k(x_i, x_i) = exp(0) exactly, like the reference (2^15 after the fp16 scaling)
-                                    if (dq == 4 * q4) e0 = 32768.0f;
-                                    if (dq == 4 * q4 + 1) e1 = 32768.0f;
-                                    if (dq == 4 * q4 + 2) e2 = 32768.0f;
-                                    if (dq == 4 * q4 + 3) e3 = 32768.0f;
-                                }
-                                packed[2 * q4] = pack_f16x2(e0, e1);
-                                packed[2 * q4 + 1] = pack_f16x2(e2, e3);
-                                acc_f16x2(rs0, rs1, packed[2 * q4]);
-                                acc_f16x2(rs2, rs3, packed[2 * q4 + 1]);
-                            }
-                            tmem_st16(tS + c * 16, packed);
-                        };
-                        tmem_ld_wait();
-                        if (p.dbg == 2) {
-                            uint32_t pk[16];
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) pk[q] = r0[q] ^ r1[2 * q];
-                            tmem_st16(tS, pk);
-                            tmem_st16(tS + 16, pk);
-                        } else if (has_diag) {
-                            exp_chunk(r0, 0, std::true_type{});
-                            exp_chunk(r1, 1, std::true_type{});
-                        } else {
-                            exp_chunk(r0, 0, std::false_type{});
-                            exp_chunk(r1, 1, std::false_type{});
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
+                        const float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
+                        float e0, e1, e2, e3;
+                        if (2 * q4 < POLY) { e0 = ex2_poly(x0); e1 = ex2_poly(x1); } else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
+                        if (2 * q4 + 1 < POLY) { e2 = ex2_poly(x2); e3 = ex2_poly(x3); } else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
+                        if (DIAG) { // k(x_i, x_i) = exp(0) exactly, like the reference (2^15 after the fp16 scaling)
+                            if (dq == 4 * q4) e0 = 32768.0f;
+                            if (dq == 4 * q4 + 1) e1 = 32768.0f;
+                            if (dq == 4 * q4 + 2) e2 = 32768.0f;
+                            if (dq == 4 * q4 + 3) e3 = 32768.0f;
                         }
-                        tmem_st_wait();
+                        packed[2 * q4] = pack_f16x2(e0, e1);
+                        packed[2 * q4 + 1] = pack_f16x2(e2, e3);
+                        acc_f16x2(rs0, rs1, packed[2 * q4]);
+                        acc_f16x2(rs2, rs3, packed[2 * q4 + 1]);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(e_ready + b);
-                    if (row == 0) TC_TRACE(1 + w, gt, 3 + 3 * k);
+                };
+                if (p.dbg != 0) {
+#pragma unroll
+                    for (int z = 0; z < 16; ++z) { pk0[z] = r0[z] ^ r1[2 * z]; pk1[z] = r0[z + 16]; }
+                } else if (has_diag) {
+                    exp_chunk(r0, pk0, 0, std::true_type{});
+                    exp_chunk(r1, pk1, 1, std::true_type{});
+                } else {
+                    exp_chunk(r0, pk0, 0, std::false_type{});
+                    exp_chunk(r1, pk1, 1, std::false_type{});
+                }
+                tmem_st16(tS, pk0);
+                tmem_st16(tS + 16, pk1);
+                // fetch the next unit's S (the other buffer of this tile) while the stores drain -- only if it is already
+                // complete: waiting here would hold back this unit's e_ready and with it the MMAs that produce that S
+                const bool more = q + 1 < nunits;
+                const int kn = (int)((q + 1) & 1u);
+                const uint32_t gn = g + ((q + 1) >> 1);
+                const uint32_t tSn = tmem + (2 * w + kn) * 64 + lane_base;
+                bool fetched = false;
+                if (more && __all_sync(0xffffffffu, mbar_try_wait(s_full + 2 * w + kn, gn & 1))) {
+                    tc_fence_after();
+                    tmem_ld32(tSn, r0);
+                    tmem_ld32(tSn + 32, r1);
+                    fetched = true;
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e_ready + b);
+                if (row == 0) TC_TRACE(1 + w, gt, 3 + 3 * k);
+                if (more && !fetched) {
+                    if (row == 0) TC_TRACE(1 + w, gn, 1 + 3 * kn);
+                    if (!mbar_wait(s_full + 2 * w + kn, gn & 1, p.err, 40 + 2 * w + kn)) { ok = false; break; }
+                    tc_fence_after();
+                    tmem_ld32(tSn, r0);
+                    tmem_ld32(tSn + 32, r1);
                 }
             }
+            if (ok) tmem_ld_wait();
             g += nt;
             if (!ok || !mbar_wait(phi_full + w, seg & 1, p.err, 50)) { ok = false; break; }
             tc_fence_after();
