@@ -147,6 +147,13 @@ int svgdb_time_steps(svgdb_ctx *ctx, int64_t iters, float *ms_out);
 int svgdb_host_alloc(void **out, size_t bytes);
 int svgdb_host_free(void *ptr);
 
+/* Measurement aid (SVGDB_PRECISION_TC32): average time in ms of `reps` back-to-back launches of one hot kernel on the
+ * context's current particles, CUDA events on the context's stream.  which = 0: the tensor-core distance pass of the
+ * median bandwidth (GaussianRBFKernel.hpp:168-188), collecting the bracket median * (1 +- rel_halfwidth) of the last
+ * step (variant 0 = product path, 1 = no counting, 2 = counting without collecting); which = 1: the pair-interaction
+ * pass (SVGD.hpp:407-454) with its operand preparation.  Particles and optimizer state are not modified. */
+int svgdb_time_kernel(svgdb_ctx *ctx, int which, int reps, int variant, double rel_halfwidth, float *ms_out);
+
 /* Micro-probes for roofline denominators the driver does not measure.  what = 0: FP64 DMMA
  * (mma.sync m8n8k4) TFLOP/s from a register-resident issue loop on every SM. */
 int svgdb_probe_peak(int device, int what, double *out);

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +24,7 @@
 #ifdef SVGDB_WITH_TC32
 #include "kernels_tc32.cuh"
 #include "kernels_phi_tc.cuh"
+#include "kernels_dist_tc.cuh"
 #endif
 
 using namespace svgdb;
@@ -139,6 +141,11 @@ struct svgdb_ctx {
     __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
     __half *UA2 = nullptr, *WB2 = nullptr; // exponent-offset K chunks (row / column side)
     CUtensorMap mapB2{}, mapV2{};
+    __nv_bfloat16 *XBD = nullptr; // column operand [hi | lo] of the persistent distance pass (kernels_dist_tc.cuh)
+    CUtensorMap mapBD{};
+    int dist_version = 2; // SVGDB_DIST_KERNEL=1 selects the first (SS-mode) distance kernel
+    int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
+    uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_version = 2; // SVGDB_PHI_KERNEL=1 selects the first (SS-mode, one CTA per j-split) kernel
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
     int phi_split = 1;   // SVGDB_PHI_SPLIT=0: one exp warpgroup per i-tile instead of both on the same tile
@@ -241,6 +248,8 @@ int free_sharded(svgdb_ctx *ctx)
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
     cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
+    cudaFree(ctx->XBD);
+    ctx->XBD = nullptr;
     cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->UA2); cudaFree(ctx->WB2);
     ctx->XA2 = ctx->XB2 = ctx->VT2 = nullptr;
     ctx->UA2 = ctx->WB2 = nullptr;
@@ -311,6 +320,9 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->WB2, np / 128 * P2_W_BYTES));
     CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * P2_A_LD * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->UA2, 0, (np + 256) * 16 * 2, ctx->stream));
+    CU(cudaMalloc(&ctx->XBD, np * 128 * 2));
+    TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
+    if (const char *e = std::getenv("SVGDB_DIST_KERNEL")) ctx->dist_version = std::atoi(e) == 1 ? 1 : 2;
     TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_KERNEL")) ctx->phi_version = std::atoi(e) == 1 ? 1 : 2;
@@ -583,6 +595,10 @@ int median_scale(svgdb_ctx *ctx)
                                                           ctx->medres, ctx->a_dev);
         KERNEL_CHECK();
     } else {
+#ifdef SVGDB_WITH_TC32
+        // the persistent tensor-core pass collects a contiguous range [lo, hi') with hi' slightly past hi
+        if (ctx->precision == SVGDB_PRECISION_TC32 && ctx->dist_version == 2 && ctx->collect_hi_ext > hi) hi = ctx->collect_hi_ext;
+#endif
         TRY(run_select(ctx, lo, hi, kk, even, log_n));
     }
     CU(cudaMemcpyAsync(&ctx->hs->med, ctx->medres, sizeof(MedianResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -698,6 +714,14 @@ int launch_tc_split(svgdb_ctx *ctx, int mode)
         colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
         KERNEL_CHECK();
     }
+    if (mode == SPLIT_DIST && ctx->dist_version == 2) {
+        const int64_t rows_a = ctx->n_pad128 + 256;
+        split_dist2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(
+            ctx->X[ctx->cur], ctx->colsum, ctx->N, rows_a, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
+            reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
+        KERNEL_CHECK();
+        return SVGDB_OK;
+    }
     split_kernel<<<(unsigned)((ctx->n_pad128 + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128,
                                                                                  ctx->d, mode, ctx->XA, ctx->XB, ctx->rt);
     KERNEL_CHECK();
@@ -742,7 +766,53 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
     const int n_ipairs_all = (int)((ctx->N + 255) / 256);
     const int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
-    if (n_ipairs > 0) {
+    if (n_ipairs > 0 && ctx->dist_version == 2) {
+        Dist2Args b{};
+        b.XA2 = reinterpret_cast<const __nv_bfloat16 *>(ctx->XA2);
+        b.UA = reinterpret_cast<const __nv_bfloat16 *>(ctx->UA2);
+        b.WB = reinterpret_cast<const __nv_bfloat16 *>(ctx->WB2);
+        b.n_total = ctx->N;
+        b.n_jtiles = a.n_jtiles;
+        b.pair_offset = ctx->rank;
+        b.pair_stride = ctx->world;
+        b.n_ipairs = n_ipairs;
+        b.lo_f = a.lo_f;
+        b.hi_f = a.hi_f;
+        b.open_low = std::isinf(a.lo_f) ? 1 : 0;
+        {
+            float wdt = std::isinf(a.lo_f) || std::isinf(a.hi_f) ? INFINITY : (float)((double)a.hi_f - (double)a.lo_f);
+            if ((double)wdt < (double)a.hi_f - (double)a.lo_f) wdt = std::nextafterf(wdt, INFINITY);
+            wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
+            if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
+            uint32_t wb;
+            std::memcpy(&wb, &wdt, 4);
+            b.width_bits = wb;
+            // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
+            float hi_ext = std::isinf(wdt) || std::isinf(a.lo_f) ? a.hi_f : (float)((double)a.lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
+            hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
+            ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
+        }
+        b.lo_key = lo;
+        b.shift = shift;
+        b.below = ctx->below;
+        b.hist = ctx->hist;
+        b.cand = ctx->cand;
+        b.cand_count = ctx->cand_count;
+        b.capacity = ctx->capacity;
+        b.err = ctx->tc_err;
+        b.dbg = ctx->dist_dbg_mode;
+        long long units = 0;
+        for (int l = 0; l < n_ipairs; ++l) units += std::max(0, b.n_jtiles - 2 * (b.pair_offset + b.pair_stride * l));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
+        if (mode == MODE_HIST) {
+            CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
+            dist2_tc32_kernel<MODE_HIST><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+        } else {
+            CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
+            dist2_tc32_kernel<MODE_COLLECT><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+        }
+        KERNEL_CHECK();
+    } else if (n_ipairs > 0) {
         unsigned grid = (unsigned)(n_ipairs * a.jsplit);
         if (mode == MODE_HIST) {
             CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
@@ -1021,6 +1091,8 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         SVGDB_PHI2_ATTR(6)
         SVGDB_PHI2_ATTR(8)
 #undef SVGDB_PHI2_ATTR
+        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
+        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
         CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_HIST));
         CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_BASE));
     }
@@ -1373,6 +1445,49 @@ int svgdb_host_alloc(void **out, size_t bytes)
 }
 
 int svgdb_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SVGDB_OK : SVGDB_ERR_CUDA; }
+
+int svgdb_time_kernel(svgdb_ctx *ctx, int which, int reps, int variant, double rel_halfwidth, float *ms_out)
+{
+    if (!ctx || !ms_out || reps < 1) return SVGDB_ERR_INVALID;
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision != SVGDB_PRECISION_TC32) return fail(ctx, SVGDB_ERR_INVALID, "svgdb_time_kernel needs SVGDB_PRECISION_TC32");
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    int rc = SVGDB_OK;
+    if (which == 0) { // distance pass, collecting a bracket of the given relative half-width around the last median
+        if (ctx->n_hist < 1) return fail(ctx, SVGDB_ERR_UNSET, "svgdb_time_kernel: no median yet (run a step first)");
+        const double m = ctx->med_hist[0];
+        const uint64_t klo = key_of(std::max(m * (1.0 - rel_halfwidth), 0.0)), khi = key_of(m * (1.0 + rel_halfwidth)) + 1;
+        rc = launch_tc_split(ctx, svgdb::tc::SPLIT_DIST);
+        ctx->dist_dbg_mode = variant;
+        if (rc == SVGDB_OK) rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0); // warm-up
+        cudaEventRecord(e0, ctx->stream);
+        for (int r = 0; rc == SVGDB_OK && r < reps; ++r) rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0);
+        cudaEventRecord(e1, ctx->stream);
+        ctx->dist_dbg_mode = 0;
+    } else if (which == 1) { // pair-interaction kernel (with its operand preparation and the optimizer epilogue kernel), no state change
+        rc = launch_phi_tc32(ctx, true);
+        cudaEventRecord(e0, ctx->stream);
+        for (int r = 0; rc == SVGDB_OK && r < reps; ++r) rc = launch_phi_tc32(ctx, true);
+        cudaEventRecord(e1, ctx->stream);
+    } else {
+        rc = fail(ctx, SVGDB_ERR_INVALID, "svgdb_time_kernel: unknown kernel id");
+    }
+    if (rc == SVGDB_OK && cudaEventSynchronize(e1) != cudaSuccess) rc = fail(ctx, SVGDB_ERR_CUDA, "svgdb_time_kernel: synchronize failed");
+    float ms = 0.f;
+    if (rc == SVGDB_OK) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == SVGDB_OK) rc = check_tc_err(ctx);
+    *ms_out = ms / (float)reps;
+    return rc;
+#else
+    (void)which; (void)variant; (void)rel_halfwidth;
+    return fail(ctx, SVGDB_ERR_INVALID, "this build has no TC32 (tcgen05) path");
+#endif
+}
 
 int svgdb_probe_peak(int device, int what, double *out)
 {

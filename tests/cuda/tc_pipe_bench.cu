@@ -197,6 +197,50 @@ static void runb(long long *dout, int *derr, float *sink)
            (double)h[0] / steps, (double)h[1] / steps);
 }
 
+// tcgen05.ld bandwidth: NW warps (lane quadrant = warp % 4) stream 32x32b.x32 loads (4 KB each) with no math in between.
+template <int NW, int PER_WAIT>
+__global__ void __launch_bounds__(NW * 32 + 32) ldtm_kernel(int iters, long long *out, unsigned *sink)
+{
+    __shared__ uint32_t holder;
+    const int warp = threadIdx.x >> 5;
+    if (warp == NW) tmem_alloc(&holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = holder;
+    if (warp < NW) {
+        const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 32;
+        unsigned acc = 0;
+        long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            uint32_t r[PER_WAIT][32];
+#pragma unroll
+            for (int k = 0; k < PER_WAIT; ++k) tmem_ld32(base + ((it + k) & 3) * 128, r[k]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < PER_WAIT; ++k) acc ^= r[k][0] ^ r[k][31];
+        }
+        long long t1 = clock64();
+        if (acc == 0x12345u) sink[threadIdx.x] = acc;
+        if (threadIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NW) tmem_dealloc(tmem, 512);
+}
+template <int NW, int PER_WAIT>
+static void runl(long long *dout, float *sink)
+{
+    const int iters = 256;
+    ldtm_kernel<NW, PER_WAIT><<<1, NW * 32 + 32>>>(iters, dout, (unsigned *)sink);
+    ldtm_kernel<NW, PER_WAIT><<<1, NW * 32 + 32>>>(iters, dout, (unsigned *)sink);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost));
+    printf("tcgen05.ld x32: %2d warps, %d loads per wait: %7.1f B/clk/SM  (%.0f cycles per 4 KB load per warp)\n", NW, PER_WAIT,
+           (double)NW * iters * PER_WAIT * 4096.0 / (double)h, (double)h / (iters * PER_WAIT));
+}
+
 int main()
 {
     long long *dout;
@@ -207,6 +251,7 @@ int main()
     CK(cudaMalloc(&sink, 4096));
     CK(cudaMemset(derr, 0, 4));
     CK(cudaMemset(dout, 0, 24));
+    runl<4, 1>(dout, sink); runl<4, 2>(dout, sink); runl<8, 1>(dout, sink); runl<8, 2>(dout, sink); runl<16, 1>(dout, sink); runl<16, 2>(dout, sink);
     // issue-rate floor: tiny MMAs
     run<8, 16, 0, false, 0>(dout, derr, sink);
     run<16, 16, 0, false, 0>(dout, derr, sink);
@@ -231,7 +276,6 @@ int main()
     run<64, 16, 8, true, 7>(dout, derr, sink);
     // the same pattern through the kernel's blocks of 8 (elect + commit per block)
     runb<0>(dout, derr, sink);
-    runb<1>(dout, derr, sink);
     int herr = 0;
     CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
     printf("timeout tag %d\n", herr);
