@@ -245,7 +245,10 @@ def main():
     barrier()
     sp = stats()
     check(lib.svgdb_set_profiling(ctx, 0))
-    phi_ms = sp.ms_phi / max(1, sp.phi_launches)
+    phi_phase_ms = sp.ms_phi / max(1, sp.phi_launches)           # operand preparation + kernel + optimizer kernel
+    phi_ms = sp.ms_phi_kernel / max(1, sp.phi_launches)          # the pair-interaction kernel alone (events around its launch)
+    if not phi_ms > 0.0:
+        phi_ms = phi_phase_ms
     prof_iters = max(1, int(sp.iterations))
     phase_ms = {"median": sp.ms_median / prof_iters, "grad": sp.ms_grad / prof_iters, "phi": sp.ms_phi / prof_iters,
                 "comm_and_misc": sp.ms_comm / prof_iters}
@@ -291,7 +294,8 @@ def main():
                 traffic = json.load(f).get("tc32_phi" if precision == _capi.PRECISION_TC32 else "f64_phi")
         roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
-                "kernel": "phi (pair interaction + optimizer epilogue)", "kernel_ms": phi_ms,
+                "kernel": "phi2_tc32_kernel (pair interaction)" if precision == _capi.PRECISION_TC32 else "phi_f64_kernel (pair interaction + optimizer epilogue)",
+                "kernel_ms": phi_ms, "phase_ms_with_operand_prep_and_optimizer": phi_phase_ms,
                 "algorithmic_flops_per_launch": phi_flops, "peak_source": peaks["source"] + ", dense bf16 sustained",
                 "whole_step_algorithmic_tflops": step_tf / max(world, 1), "phase_ms_per_step": phase_ms}
         if precision == _capi.PRECISION_F64:

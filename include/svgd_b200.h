@@ -68,6 +68,7 @@ typedef struct {
     double last_scale;            /* a of the last iteration (A = a I, GaussianRBFKernel.hpp:187) */
     double ms_median, ms_grad, ms_phi, ms_comm; /* accumulated CUDA-event time per phase, if profiling */
     uint64_t phi_launches;        /* launches of the pair-interaction kernel inside ms_phi */
+    double ms_phi_kernel;         /* ... of which the pair-interaction kernel alone (events around its launch) */
 } svgdb_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */

@@ -154,7 +154,7 @@ struct svgdb_ctx {
     // measurement
     svgdb_stats stats{};
     bool profiling = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [5], [6]: around the pair-interaction kernel
 
     std::string err;
 };
@@ -398,6 +398,7 @@ size_t dist_smem_bytes(int d, bool hist)
 #ifdef SVGDB_WITH_TC32
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift);
 #endif
+void prof_mark(svgdb_ctx *ctx, int i);
 
 int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
@@ -662,8 +663,10 @@ template <int DC>
 int launch_phi_dc(svgdb_ctx *ctx, const PhiArgs &a)
 {
     dim3 grid((unsigned)((ctx->n_rows + 63) / 64), (unsigned)((ctx->d + DC - 1) / DC));
+    prof_mark(ctx, 5);
     phi_f64_kernel<DC><<<grid, 128, phi_smem_bytes(ctx->d, DC), ctx->stream>>>(a);
     KERNEL_CHECK();
+    prof_mark(ctx, 6);
     ++ctx->stats.phi_launches;
     return SVGDB_OK;
 }
@@ -876,6 +879,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
         a.dbg = ctx->phi_dbg_mode;
 #define SVGDB_PHI2_CASE(P)                                                                                \
     case P: phi2_tc32_kernel<P><<<grid, P2_THREADS, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
+        prof_mark(ctx, 5);
         switch (ctx->phi_poly) {
             SVGDB_PHI2_CASE(0)
             SVGDB_PHI2_CASE(2)
@@ -886,6 +890,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
         }
 #undef SVGDB_PHI2_CASE
         KERNEL_CHECK();
+        prof_mark(ctx, 6);
     } else {
         TRY(launch_tc_split(ctx, SPLIT_PHI)); // the operands now carry the bandwidth: the accumulator is the exponent
         make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
@@ -901,8 +906,10 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
         a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
         a.err = ctx->tc_err;
         a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
+        prof_mark(ctx, 5);
         phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
         KERNEL_CHECK();
+        prof_mark(ctx, 6);
     }
     ++ctx->stats.phi_launches;
     if (ctx->tc_trace) {
@@ -1013,6 +1020,7 @@ int one_step(svgdb_ctx *ctx)
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_grad += ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_comm += ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_phi += ms;
+        if (ctx->n_rows > 0 && cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->stats.ms_phi_kernel += ms;
         cudaEventElapsedTime(&ms, ctx->ev[4], end); ctx->stats.ms_comm += ms;
         cudaEventDestroy(end);
     }

@@ -144,6 +144,34 @@ def test_bounds_and_fixed_scale(sv, oracle):
     svgd.close()
 
 
+def test_device_hook_reproduces_reference_svgd_test(sv, oracle):
+    """The reference's own SVGD test (tests/test_svgd.cpp:65-204): user model a cos(x0) + b cos(x1) + c x0 x1 + d through the
+    device-gradient hook (the replacement for CppAD-taped Model lambdas), fixed-bandwidth kernel exp(-|x - x'|^2), Adam, box
+    bounds, Eigen::MatrixXd::Random start, 15 iterations -- against the known answer of SURVEY.md section 8c item 3."""
+    import ctypes as C
+
+    import helpers
+
+    hook_lib = C.CDLL(helpers.build_cos_hook())
+
+    class CosParams(C.Structure):
+        _fields_ = [("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("d", C.c_double)]
+
+    params = CosParams(*helpers.COS_PARAMS)
+    n, d, iters = 10, 2, 15
+    x0 = np.asfortranarray(oracle.eigen_random(d, n, 1.0, reseed=True, seed=1).T)  # d x n, column-major like Eigen
+    model = sv.Model(d)
+    model.SetDeviceGradient(C.cast(hook_lib.cos_model_grad, C.c_void_p), C.cast(C.pointer(params), C.c_void_p))
+    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Fixed, model, fixed_scale=1.0)
+    svgd = sv.SVGD(d, iters, x0, kernel, model, sv.Adam(d, n, 0.1, 0.9, 0.999), bound_lower=[-1.0, -1.0], bound_upper=[1.0, 1.0])
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    err = max(np.max(np.abs(x0[0] - helpers.COS_KAT_ROW0)), np.max(np.abs(x0[1] - helpers.COS_KAT_ROW1)))
+    print("device hook, test_svgd.cpp scenario: max abs err vs the known answer %.3g" % err)
+    assert err < 5e-12  # the known answer carries 12 digits
+
+
 def test_mixture_gradient_log_sum_exp(sv, oracle):
     """16-D, 5-component sum of Gaussians incl. far-away components (config-4 style)."""
     from svgdcpp_b200 import synth

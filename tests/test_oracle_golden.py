@@ -125,3 +125,18 @@ def test_cpu_baselines_agree_with_literal(oracle):
         secs, X = oracle.timed_iterations(X0, 3, mu, cov, shape=shape, threads=2)
         assert secs >= 0
         assert np.max(np.abs(X - ref)) < 1e-10
+
+
+def test_reference_svgd_test_scenario_known_answer(oracle):
+    """tests/test_svgd.cpp:65-204 of the reference (cosine user model, fixed-bandwidth kernel, Adam, box bounds,
+    Eigen::MatrixXd::Random start, 15 iterations): the oracle's phi / optimizer restatement reproduces the known answer
+    of SURVEY.md section 8c item 3 to its 12 printed digits."""
+    import helpers
+
+    X = np.array(oracle.eigen_random(2, 10, 1.0, reseed=True, seed=1), order="C", copy=True)  # particle-major 10 x 2
+    opt = oracle.OptState(oracle.OPT_ADAM, X.shape, 0.1)
+    for _ in range(15):
+        X = X + opt.step(oracle.phi(X, helpers.cos_model_grad(X), 1.0))
+        X = np.maximum(np.minimum(X, 1.0), -1.0)  # min-then-max clamp of SVGD.hpp:396-399
+    assert np.max(np.abs(X[:, 0] - helpers.COS_KAT_ROW0)) < 5e-12
+    assert np.max(np.abs(X[:, 1] - helpers.COS_KAT_ROW1)) < 5e-12
