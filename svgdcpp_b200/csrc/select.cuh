@@ -12,13 +12,17 @@
 
 namespace svgdb {
 
+constexpr int SELECT_MAX_BITS = 12;              // widest digit (tensor-core keys: 24 significant bits = 2 passes)
+constexpr int SELECT_MAX_BINS = 1 << SELECT_MAX_BITS;
+
 struct SelectState {
     unsigned long long prefix;    // bits of the answer decided so far
     unsigned long long mask;      // which bits of `prefix` are decided
     unsigned long long rank;      // rank of the answer among the keys matching prefix/mask
     unsigned long long n_less;    // candidates strictly below every key matching prefix/mask
     unsigned long long max_less;  // largest candidate < prefix once all bits are decided
-    unsigned long long hist[256];
+    unsigned long long need_scan; // the predecessor is not in the answer's last digit group: select_max_less_kernel must scan
+    unsigned long long hist[SELECT_MAX_BINS];
 };
 
 struct MedianResult {
@@ -31,48 +35,80 @@ struct MedianResult {
 __global__ void select_init_kernel(SelectState *st, unsigned long long prefix, unsigned long long mask,
                                    unsigned long long rank)
 {
-    int t = threadIdx.x;
-    if (t < 256) st->hist[t] = 0ull;
-    if (t == 0) { st->prefix = prefix; st->mask = mask; st->rank = rank; st->n_less = 0ull; st->max_less = 0ull; }
+    for (int t = threadIdx.x; t < SELECT_MAX_BINS; t += blockDim.x) st->hist[t] = 0ull;
+    if (threadIdx.x == 0) { st->prefix = prefix; st->mask = mask; st->rank = rank; st->n_less = 0ull; st->max_less = 0ull; st->need_scan = 1ull; }
 }
 
+// histogram of the `bits`-wide digit at `shift` over the candidates that match the decided prefix
 __global__ void __launch_bounds__(256)
-select_hist_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, int shift, SelectState *st)
+select_hist_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, int shift, int bits, SelectState *st)
 {
-    __shared__ unsigned int sh[256];
-    sh[threadIdx.x] = 0u;
+    __shared__ unsigned int sh[SELECT_MAX_BINS];
+    const int nbins = 1 << bits;
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0u;
     __syncthreads();
-    const unsigned long long prefix = st->prefix, mask = st->mask;
+    const unsigned long long prefix = st->prefix, mask = st->mask, dmask = (unsigned long long)(nbins - 1);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < m;
          t += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long key = cand[t];
-        if ((key & mask) == prefix) atomicAdd(&sh[(unsigned int)((key >> shift) & 255ull)], 1u);
+        if ((key & mask) == prefix) atomicAdd(&sh[(unsigned int)((key >> shift) & dmask)], 1u);
     }
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (sh[b]) atomicAdd(&st->hist[b], (unsigned long long)sh[b]);
 }
 
-// one thread: pick the digit holding `rank`, extend the prefix, reset the histogram
-__global__ void select_pick_kernel(SelectState *st, int shift)
+// one block: pick the digit holding `rank`, extend the prefix, reset the histogram.  On the last digit (`last` != 0) the
+// predecessor of the answer among the candidates is the largest non-empty smaller digit of the same group, if there is
+// one; otherwise need_scan stays set and select_max_less_kernel looks for it among the smaller groups.
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, int shift, int bits, int last)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long rank = st->rank, cum = 0ull;
-    int digit = 255;
-    for (int b = 0; b < 256; ++b) {
-        unsigned long long c = st->hist[b];
-        if (rank < cum + c) { digit = b; break; }
-        cum += c;
+    __shared__ unsigned long long sh[SELECT_MAX_BINS];
+    __shared__ unsigned long long part[256];
+    const int nbins = 1 << bits, per = nbins / 256 > 0 ? nbins / 256 : 1, t = threadIdx.x;
+    for (int b = t; b < nbins; b += 256) sh[b] = st->hist[b];
+    __syncthreads();
+    unsigned long long mine = 0ull; // thread t owns bins [t * per, t * per + per)
+    if (t * per < nbins)
+        for (int b = t * per; b < t * per + per; ++b) mine += sh[b];
+    part[t] = mine;
+    __syncthreads();
+    if (t == 0) {
+        const unsigned long long rank = st->rank;
+        unsigned long long cum = 0ull;
+        int seg = 255;
+        for (int q = 0; q < 256; ++q) {
+            if (rank < cum + part[q]) { seg = q; break; }
+            cum += part[q];
+        }
+        int digit = nbins - 1;
+        const int b0 = seg * per < nbins ? seg * per : nbins - per;
+        for (int b = b0; b < b0 + per; ++b) {
+            if (rank < cum + sh[b]) { digit = b; break; }
+            cum += sh[b];
+        }
+        int pred = -1;
+        for (int b = digit - 1; b >= 0; --b)
+            if (sh[b] != 0ull) { pred = b; break; }
+        st->rank = rank - cum;
+        st->n_less += cum;
+        const unsigned long long np = st->prefix | (((unsigned long long)digit) << shift);
+        st->prefix = np;
+        st->mask |= ((unsigned long long)(nbins - 1)) << shift;
+        if (last && pred >= 0) {
+            st->max_less = (np & ~(((unsigned long long)(nbins - 1)) << shift)) | (((unsigned long long)pred) << shift);
+            st->need_scan = 0ull;
+        }
     }
-    st->rank = rank - cum;
-    st->n_less += cum;
-    st->prefix |= ((unsigned long long)digit) << shift;
-    st->mask |= 255ull << shift;
-    for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
+    __syncthreads();
+    for (int b = t; b < nbins; b += 256) st->hist[b] = 0ull;
 }
 
+// largest candidate below the answer, only when the last pick could not tell (the answer is the smallest key of its group)
 __global__ void __launch_bounds__(256)
 select_max_less_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, SelectState *st)
 {
+    if (st->need_scan == 0ull) return;
     const unsigned long long key_hi = st->prefix;
     unsigned long long best = 0ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < m;

@@ -82,6 +82,9 @@ struct svgdb_ctx {
     int d = 0;
     int precision = SVGDB_PRECISION_F64;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t side_stream = nullptr;                 // grad log p runs here, next to the median pass (it only needs X)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool grad_pending = false;
     int sm_count = 148;
 
     // sharding
@@ -399,6 +402,7 @@ size_t dist_smem_bytes(int d, bool hist)
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift);
 #endif
 void prof_mark(svgdb_ctx *ctx, int i);
+int kick_grad(svgdb_ctx *ctx);
 
 int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
@@ -443,6 +447,7 @@ int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shi
         KERNEL_CHECK();
     }
     ++ctx->stats.median_passes;
+    TRY(kick_grad(ctx));
     TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
     TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
     if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
@@ -480,29 +485,30 @@ int read_pass_results(svgdb_ctx *ctx, int mode, uint64_t *mid_total)
 int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n)
 {
     uint64_t m_local = std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
-    // digits above the highest differing bit of [lo, hi) are common to every candidate
-    uint64_t diff = lo ^ (hi - 1);
-    uint64_t prefix = 0, mask = 0;
-    int first_shift = 56;
-    while (first_shift >= 0 && ((diff >> first_shift) & 255ull) == 0ull) {
-        prefix |= lo & (255ull << first_shift);
-        mask |= 255ull << first_shift;
-        first_shift -= 8;
-    }
-    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, prefix, mask, kk);
+    // bits above the highest differing bit of [lo, hi) are common to every candidate; keys of the tensor-core path are
+    // fp32 distances widened to double: their low 29 bits are zero and cannot change anything
+    const uint64_t diff = lo ^ (hi - 1);
+    int top = 64; // number of low bits that may differ
+    while (top > 0 && ((diff >> (top - 1)) & 1ull) == 0ull) --top;
+    const int bottom = ctx->precision == SVGDB_PRECISION_TC32 ? 29 : 0;
+    if (top < bottom + 1) top = bottom + 1;
+    const uint64_t low_mask = top >= 64 ? ~0ull : ((1ull << top) - 1ull);
+    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, lo & ~low_mask, ~low_mask, kk);
     KERNEL_CHECK();
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m_local + 2047) / 2048, (uint64_t)ctx->sm_count * 8));
-    // keys of the tensor-core path are fp32 distances widened to double: their low 29 bits are zero, so the three
-    // lowest digit passes cannot change anything (prefix bits stay 0 there)
-    const int last_shift = ctx->precision == SVGDB_PRECISION_TC32 ? 24 : 0;
-    for (int shift = first_shift; shift >= last_shift; shift -= 8) {
-        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, ctx->sel);
+    // digits of up to SELECT_MAX_BITS bits from the top differing bit down to `bottom`
+    int hi_bit = top;
+    while (hi_bit > bottom) {
+        const int bits = std::min(SELECT_MAX_BITS, hi_bit - bottom), shift = hi_bit - bits;
+        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, bits, ctx->sel);
         KERNEL_CHECK();
-        TRY(allreduce_u64(ctx, ctx->sel->hist, 256, ncclSum));
-        select_pick_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, shift);
+        TRY(allreduce_u64(ctx, ctx->sel->hist, (size_t)1 << bits, ncclSum));
+        select_pick_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, shift, bits, shift == bottom ? 1 : 0);
         KERNEL_CHECK();
+        hi_bit = shift;
     }
     if (even) {
+        // multi-GPU: each rank decides need_scan from the same all-reduced histogram, the candidates are rank-local
         select_max_less_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, ctx->sel);
         KERNEL_CHECK();
         TRY(allreduce_u64(ctx, &ctx->sel->max_less, 1, ncclMax));
@@ -635,20 +641,32 @@ int compute_scale_dev(svgdb_ctx *ctx)
     return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is not implemented on the device path yet");
 }
 
-int launch_grad(svgdb_ctx *ctx)
+int launch_grad(svgdb_ctx *ctx, cudaStream_t stream)
 {
     if (ctx->n_rows <= 0) return SVGDB_OK;
     if (ctx->model_kind == MODEL_HOOK) {
-        int rc = ctx->hook(ctx->X[ctx->cur], ctx->G, ctx->N, ctx->d, ctx->row0, ctx->n_rows, (void *)ctx->stream, ctx->hook_user);
+        int rc = ctx->hook(ctx->X[ctx->cur], ctx->G, ctx->N, ctx->d, ctx->row0, ctx->n_rows, (void *)stream, ctx->hook_user);
         if (rc != 0) return fail(ctx, SVGDB_ERR_INVALID, "device gradient hook returned " + std::to_string(rc));
         return SVGDB_OK;
     }
     constexpr int PT = 16;
     size_t smem = ((size_t)3 * PT * ctx->d + 5 * PT) * sizeof(double);
     unsigned blocks = (unsigned)((ctx->n_rows + PT - 1) / PT);
-    mvn_sum_grad_f64_kernel<PT><<<blocks, 128, smem, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->row0, ctx->n_rows,
+    mvn_sum_grad_f64_kernel<PT><<<blocks, 128, smem, stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->row0, ctx->n_rows,
                                                                      ctx->C, ctx->means_dev, ctx->prec_dev, ctx->G);
     KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+// Enqueue grad log p on the side stream, ordered after everything the main stream has been given so far.
+int kick_grad(svgdb_ctx *ctx)
+{
+    if (!ctx->grad_pending) return SVGDB_OK;
+    ctx->grad_pending = false;
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    TRY(launch_grad(ctx, ctx->side_stream));
+    CU(cudaEventRecord(ctx->ev_join, ctx->side_stream));
     return SVGDB_OK;
 }
 
@@ -827,6 +845,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
         KERNEL_CHECK();
     }
     ++ctx->stats.median_passes;
+    TRY(kick_grad(ctx));
     TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
     TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
     if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
@@ -977,13 +996,17 @@ void prof_mark(svgdb_ctx *ctx, int i)
 int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
 {
     prof_mark(ctx, 0);
+    // grad log p only needs X: it runs on the side stream next to the bandwidth computation, enqueued right behind the
+    // (persistent, GPU-filling) distance pass so that it overlaps the select kernels, which leave most of the GPU idle
+    ctx->grad_pending = true; // kicked off behind the first distance pass (kick_grad), or below if there is none
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx, svgdb::tc::SPLIT_DIST));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     prof_mark(ctx, 1);
-    TRY(launch_grad(ctx));
+    TRY(kick_grad(ctx));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     prof_mark(ctx, 2);
     TRY(launch_make_v(ctx));
     prof_mark(ctx, 3);
@@ -1069,6 +1092,9 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
+    CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char *s = std::getenv("SVGDB_CAND_CAPACITY")) {
         long long v = std::atoll(s);
         if (v >= 64) ctx->capacity = (uint64_t)v;
@@ -1135,6 +1161,9 @@ void svgdb_destroy(svgdb_ctx *ctx)
     cudaFree(ctx->sel); cudaFree(ctx->medres);
     if (ctx->hs) cudaFreeHost(ctx->hs);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1355,7 +1384,7 @@ int svgdb_compute_log_model_grad(svgdb_ctx *ctx, double *G)
     if (!ctx || !G) return fail(ctx, SVGDB_ERR_INVALID, "null output");
     if (ctx->model_kind == MODEL_UNSET) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
     CU(cudaSetDevice(ctx->device));
-    TRY(launch_grad(ctx));
+    TRY(launch_grad(ctx, ctx->stream));
     double *tmp = ctx->V;
     if (ctx->n_rows > 0)
         CU(cudaMemcpyAsync(tmp + (size_t)ctx->row0 * ctx->d, ctx->G, (size_t)ctx->n_rows * ctx->d * sizeof(double),
