@@ -172,6 +172,71 @@ def test_device_hook_reproduces_reference_svgd_test(sv, oracle):
     assert err < 5e-12  # the known answer carries 12 digits
 
 
+def test_baseline_config_variants(sv, oracle):
+    """BASELINE.json configs[0] / configs[1] as worded there (C1 = the MVN example's target with N=100 and Adam,
+    C2 = three Gaussians, N=1000, AdaGrad), 1000 iterations, final particles against the oracle."""
+    from svgdcpp_b200 import synth
+
+    g1, g2 = load_golden("mvn_example"), load_golden("gmm_example")
+    # C1: 2-D MVN target of mvn_example.cpp, 100 particles, X0 = 3 U(-1,1) (seed 1001), Adam(0.1, 0.9, 0.999)
+    n, d, iters = 100, 2, 1000
+    mu, cov = np.asarray(g1["means"][0], dtype=np.float64), np.asarray(g1["covs"][0], dtype=np.float64)
+    x0 = np.asfortranarray(3.0 * synth.uniform_pm1(1001, (n, d)).T)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = sv.MultivariateNormal(mu, cov)
+    svgd = sv.SVGD(d, iters, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999))
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, iters, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1)
+    print("C1 variant: final rel err %.3g" % _rel(x0.T, ref))
+    assert _rel(x0.T, ref) < FINAL_RTOL
+    # C2: the two components of gmm_example.cpp plus a third one, 1000 particles, X0 = 8 U(-1,1) (seed 1002), AdaGrad(0.1)
+    n, iters = 1000, 1000
+    means = np.array(list(g2["means"]) + [[-3.0, -3.5]], dtype=np.float64)
+    covs = np.array(list(g2["covs"]) + [g1["covs"][0]], dtype=np.float64)
+    x0 = np.asfortranarray(8.0 * synth.uniform_pm1(1002, (n, d)).T)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = None
+    for k in range(3):
+        m = sv.MultivariateNormal(means[k], covs[k])
+        model = m if model is None else model + m
+    svgd = sv.SVGD(d, iters, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1))
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, iters, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+    print("C2 variant: final rel err %.3g" % _rel(x0.T, ref))
+    assert _rel(x0.T, ref) < FINAL_RTOL
+
+
+def test_config4_slice(sv, oracle):
+    """BASELINE configs[3] on a slice the oracle can do (d=256, 16 components, N=1024): one ComputePhi, kernel scale and
+    mixture gradient against the oracle (the far components underflow: log-sum-exp form), then 3 AdaGrad steps."""
+    from svgdcpp_b200 import synth
+
+    n, d, C = 1024, 256, 16
+    x0, means, covs = synth.gmm_problem(n, d, C)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = None
+    for k in range(C):
+        m = sv.MultivariateNormal(means[k], covs[k])
+        model = m if model is None else model + m
+    svgd = sv.SVGD(d, 3, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1))
+    phi, a = svgd.ComputePhi()
+    a_ref = oracle.rbf_median_scale(X0)
+    G_ref = oracle.mvn_sum_logp_grad(X0, means, covs, lse=True)
+    phi_ref = oracle.phi(X0, G_ref, a_ref)
+    print("C4 slice: a rel err %.3g, phi rel err %.3g" % (abs(a - a_ref) / a_ref, _rel(phi.T, phi_ref)))
+    assert abs(a - a_ref) <= PHI_RTOL * a_ref
+    assert _rel(phi.T, phi_ref) < 1e-10
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, 3, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+    assert _rel(x0.T, ref) < FINAL_RTOL
+
+
 def test_mixture_gradient_log_sum_exp(sv, oracle):
     """16-D, 5-component sum of Gaussians incl. far-away components (config-4 style)."""
     from svgdcpp_b200 import synth

@@ -1,5 +1,5 @@
-"""GPU parity tests of the tensor-core path (SVGDB_PRECISION_TC32: tcgen05 MMA on split-bf16 operands,
-fp32 accumulation in TMEM, fp32 exp) against the FP64 CPU oracle.
+"""GPU parity tests of the tensor-core path (SVGDB_PRECISION_TC32: tcgen05 MMA on split fp16 / bf16 operands,
+fp32 accumulation in TMEM, fp32 exp, fp16 kernel values) against the FP64 CPU oracle.
 
 Stated tolerances (DESIGN.md "Precision modes"):
   * one ComputePhi on identical particles: max|phi - phi_ref| <= 2e-4 * max|phi_ref|
@@ -95,3 +95,37 @@ def test_tc32_median_narrowing_paths(sv, oracle, capacity, monkeypatch):
         print("   8 steps: rms rel err %.3g, median passes %d, bracket hits %d" % (rms, st["median_passes"], st["median_bracket_hits"]))
         assert rms < 1e-3
         svgd.close()
+
+
+def test_tc32_full_size_properties(sv):
+    """BASELINE config 3 (N=65,536, d=64) on the tensor-core path, where the oracle cannot run: the kernel scale against the
+    FP64 device path (exact median of FP64 distances, itself checked against the oracle at small sizes), sampled rows of phi
+    recomputed in O(N d) on the host in FP64, and one Adam step."""
+    from svgdcpp_b200 import synth
+
+    n, d = 65536, 64
+    x0, means, covs = synth.mvn_problem(n, d)
+    X = np.array(x0.T, order="C", copy=True)
+    model = sv.MultivariateNormal(means[0], covs[0])
+    f64 = sv.SVGD(d, 1, x0.copy(order="F"), sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999))
+    a64 = f64.ComputeScale()
+    f64.close()
+    svgd = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999), precision=TC32)
+    phi, a = svgd.ComputePhi()
+    print("N=65536: a rel err vs the FP64 device path %.3g" % (abs(a - a64) / a64))
+    assert abs(a - a64) <= 1e-5 * a64
+    G = -(X - means[0]) @ np.linalg.inv(covs[0])
+    scale = np.max(np.abs(phi))
+    worst = 0.0
+    for i in np.random.default_rng(0).integers(0, n, 12):
+        k = np.exp(-a64 * ((X - X[i]) ** 2).sum(1))
+        ref = (k @ G + (-2 * a64 * (X - X[i]) * k[:, None]).sum(0)) / n
+        worst = max(worst, np.max(np.abs(phi[:, i] - ref)) / scale)
+    print("N=65536: sampled phi rows, max err / max|phi| = %.3g" % worst)
+    assert worst < PHI_TOL
+    before = x0.copy()
+    svgd.Initialize()
+    svgd.Step(1)
+    step = np.abs(x0 - before)
+    assert np.all(np.isfinite(x0)) and np.max(step) <= 0.1 * (1 + 1e-6) and np.mean(step) > 0.05
+    svgd.close()
