@@ -211,7 +211,11 @@ __device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, lo
 // so between the completion of S(b) and the issue of PV(b) lie three other units (1536 tensor-pipe cycles):
 // the commit -> mbarrier -> exp warps -> mbarrier -> MMA warp round trip (~1.5k cycles measured with idle exp
 // warps) no longer starves the tensor pipe, which it did with two 128-column buffers (one unit of slack).
-constexpr int P2_THREADS = 352; // warps 0-3 / 4-7: exp warpgroups of i-tile 0 / 1; 8: TMA producer; 9, 10: MMA issuers of i-tile 0 / 1
+// Sixteen exp warps: warp = (i-tile w, 32-column half h of a unit, row quadrant q) = 8 w + 4 h + q, i.e. four resident exp warps per
+// scheduler (with two, a warp spends ~30 % of its time in dependent-issue and tcgen05.ld/st latencies that nothing fills);
+// then the TMA producer and one MMA issuer per i-tile.
+constexpr int P2_EWARPS = 16;
+constexpr int P2_THREADS = (P2_EWARPS + 3) * 32;
 
 template <int POLY>
 __global__ void __launch_bounds__(P2_THREADS, 1)
@@ -237,17 +241,17 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2); }
-        for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 4); }
-        for (int s = 0; s < 2; ++s) { mbar_init(phi_full + s, 1); mbar_init(a_ready + s, 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(phi_full + s, 1); mbar_init(a_ready + s, 8); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_holder, 512);
+    if (warp == P2_EWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 8) { // ---- TMA producer (whole warp runs the loop, one elected lane issues)
+    if (warp == P2_EWARPS) { // ---- TMA producer (whole warp runs the loop, one elected lane issues)
         long long pos = u_beg;
         P2Seg sg;
         uint32_t g = 0;
@@ -269,8 +273,8 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp >= 9) { // ---- MMA issuer of i-tile wm: warp-uniform control flow, one elected lane issues
-        const int wm = warp - 9;
+    } else if (warp > P2_EWARPS) { // ---- MMA issuer of i-tile wm: warp-uniform control flow, one elected lane issues
+        const int wm = warp - P2_EWARPS - 1;
         const uint32_t idesc = make_idesc_f16(TC_TILE, 64);
         const uint32_t st_lo0 = desc_lo_k_sw128(smem_u32(smem));
         const uint32_t aex_lo0 = desc_lo_k_sw128(smem_u32(sAex)) | DESC_LO_K_NOSW_LBO;
@@ -312,12 +316,12 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 const uint32_t vh = st_lo0 + slot * (P2_STAGE >> 4) + (P2_XB_BYTES >> 4) + k * (P2_VBOX >> 4), vl = vh + 2 * (P2_VBOX >> 4);
                 umma_f16_ts2r(dP, e, vh, idesc, (first && k == 0) ? 0u : 1u);
                 umma_f16_ts2<true>(dP, e + 8, vh + 2, idesc);
-                umma_f16_ts2<true>(dP, e + 16, vh + 4, idesc);
-                umma_f16_ts2<true>(dP, e + 24, vh + 6, idesc);
+                umma_f16_ts2<true>(dP, e + 32, vh + 4, idesc);
+                umma_f16_ts2<true>(dP, e + 40, vh + 6, idesc);
                 umma_f16_ts2<true>(dP, e, vl, idesc);
                 umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
-                umma_f16_ts2<true>(dP, e + 16, vl + 4, idesc);
-                umma_f16_ts2<true>(dP, e + 24, vl + 6, idesc);
+                umma_f16_ts2<true>(dP, e + 32, vl + 4, idesc);
+                umma_f16_ts2<true>(dP, e + 40, vl + 6, idesc);
                 if (k == 1) umma_commit(empty + slot);
                 if (k == 1 && last) umma_commit(phi_full + w);
             }
@@ -342,12 +346,13 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
             }
             g += nt;
         }
-    } else { // ---- exp warpgroups, one i-tile each: thread = TMEM lane = particle row ---------------------------
-        const int w = warp >> 2;
+    } else { // ---- exp warps: thread = (particle row of i-tile w, 32-column half h of every unit) ---------------------
+        const int w = warp >> 3, h = (warp >> 2) & 1;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tP = tmem + P2_COL_PHI + w * 64 + lane_base;
-        const uint32_t tA = tmem + P2_COL_A + w * 64 + lane_base;
+        const uint32_t tP = tmem + P2_COL_PHI + w * 64 + 32 * h + lane_base; // this warp flushes Phi columns [32 h, +32)
+        const uint32_t tA = tmem + P2_COL_A + w * 64 + 32 * h + lane_base;   // ... and loads the hi (h = 0) / lo (h = 1) row operand
+        const bool tracer = row == 0 && h == 0;
         long long pos = u_beg;
         P2Seg sg;
         uint32_t g = 0;
@@ -356,10 +361,10 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
             const int nt = sg.je - sg.jb;
             const int64_t iw0 = p.row0 + (int64_t)sg.ip * (2 * TC_TILE) + w * TC_TILE;
             const int64_t i = iw0 + row;
-            { // row operand [hi | lo] of particle i -> TMEM (the previous segment's MMAs are complete: phi_full)
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.XA2 + i * P2_A_LD);
+            { // row operand of particle i -> TMEM: hi half by the h = 0 warp, lo half by the h = 1 warp (previous segment complete: phi_full)
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.XA2 + i * P2_A_LD + 64 * h);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     uint32_t v[16];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -368,50 +373,49 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     }
                     tmem_st16(tA + 16 * k, v);
                 }
-                // ... and its exponent-offset chunk [u0 u1 u2 1 1 1 0..] -> shared memory, core-matrix order (SS operand)
-                const uint4 *usrc = reinterpret_cast<const uint4 *>(p.UA + i * 16);
-                const uint32_t aex = smem_u32(sAex + w * P2_AEX_BYTES) + p2_ex_offset((uint32_t)row, 0);
-                const uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex), "r"(ua0.x), "r"(ua0.y), "r"(ua0.z), "r"(ua0.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex + 128u), "r"(ua1.x), "r"(ua1.y), "r"(ua1.z), "r"(ua1.w) : "memory");
-                fence_proxy_async(); // generic-proxy stores -> visible to the MMA's async-proxy reads
+                if (h == 0) { // exponent-offset chunk [u0 u1 u2 1 1 1 0..] -> shared memory, core-matrix order (SS operand)
+                    const uint4 *usrc = reinterpret_cast<const uint4 *>(p.UA + i * 16);
+                    const uint32_t aex = smem_u32(sAex + w * P2_AEX_BYTES) + p2_ex_offset((uint32_t)row, 0);
+                    const uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex), "r"(ua0.x), "r"(ua0.y), "r"(ua0.z), "r"(ua0.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex + 128u), "r"(ua1.x), "r"(ua1.y), "r"(ua1.z), "r"(ua1.w) : "memory");
+                    fence_proxy_async(); // generic-proxy stores -> visible to the MMA's async-proxy reads
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready + w);
             }
-            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f; // row sum of the rounded E (4 independent chains)
-            // Units of this tile in order (j-tile t, half k).  The S of the NEXT unit is fetched from TMEM while the E of this
-            // one is still being stored, so the tcgen05.ld / tcgen05.st round trips overlap instead of adding up.
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f; // partial row sum (this warp's columns) of the rounded E, 4 chains
+            // Units of this tile in order (j-tile t, half k); this warp owns columns [32 h, +32) of each.  Its E goes over the
+            // first 16 of the 32 S columns it has just read (E_b = S_b columns [0,16) and [32,48)).  The S of the NEXT unit is
+            // fetched while the E stores of this one drain, if it is already complete.
             const uint32_t nunits = 2u * (uint32_t)nt;
-            uint32_t r0[32], r1[32];
+            uint32_t r0[32];
             {
-                if (row == 0) TC_TRACE(1 + w, g, 1);
+                if (tracer) TC_TRACE(1 + w, g, 1);
                 if (!mbar_wait(s_full + 2 * w, g & 1, p.err, 40 + 2 * w)) { ok = false; break; }
                 tc_fence_after();
-                const uint32_t tS0 = tmem + (2 * w) * 64 + lane_base;
-                tmem_ld32(tS0, r0);
-                tmem_ld32(tS0 + 32, r1);
+                tmem_ld32(tmem + (2 * w) * 64 + 32 * h + lane_base, r0);
             }
             for (uint32_t q = 0; ok && q < nunits; ++q) {
                 const int k = (int)(q & 1u);
                 const uint32_t gt = g + (q >> 1);
                 const int b = 2 * w + k;
-                const uint32_t tS = tmem + b * 64 + lane_base;
-                const int64_t j0 = (int64_t)(sg.jb + (int)(q >> 1)) * TC_TILE + 64 * k;
-                const int dcol = (int)(i - j0); // column of k(x_i, x_i) in this half tile, if inside [0,64)
-                const bool has_diag = (j0 < iw0 + TC_TILE) && (j0 + 64 > iw0);
+                const uint32_t tS = tmem + b * 64 + 32 * h + lane_base;
+                const int64_t j0 = (int64_t)(sg.jb + (int)(q >> 1)) * TC_TILE + 64 * k + 32 * h;
+                const int dq = (int)(i - j0); // column of k(x_i, x_i) among this warp's 32, if inside [0,32)
+                const int64_t r_lo = iw0 + (warp & 3) * 32;       // this warp's rows are [r_lo, r_lo + 32)
+                const bool has_diag = (j0 < r_lo + 32) && (j0 + 32 > r_lo); // warp-uniform
                 tmem_ld_wait();
-                if (row == 0) TC_TRACE(1 + w, gt, 2 + 3 * k);
-                uint32_t pk0[16], pk1[16];
-                // 32-column chunk ch: exponentials of rr[] -> fp16 pairs, E columns [16 ch, 16 ch + 16) (over the S columns already read)
-                auto exp_chunk = [&](const uint32_t (&rr)[32], uint32_t (&packed)[16], int ch, auto diag_tag) {
+                if (tracer) TC_TRACE(1 + w, gt, 2 + 3 * k);
+                uint32_t pk[16];
+                auto exp_chunk = [&](auto diag_tag) {
                     constexpr bool DIAG = decltype(diag_tag)::value;
-                    const int dq = dcol - ch * 32;
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
-                        const float x0 = __uint_as_float(rr[4 * q4]), x1 = __uint_as_float(rr[4 * q4 + 1]);
-                        const float x2 = __uint_as_float(rr[4 * q4 + 2]), x3 = __uint_as_float(rr[4 * q4 + 3]);
+                        const float x0 = __uint_as_float(r0[4 * q4]), x1 = __uint_as_float(r0[4 * q4 + 1]);
+                        const float x2 = __uint_as_float(r0[4 * q4 + 2]), x3 = __uint_as_float(r0[4 * q4 + 3]);
                         float e0, e1, e2, e3;
                         if (2 * q4 < POLY) { e0 = ex2_poly(x0); e1 = ex2_poly(x1); } else { e0 = ex2_approx(x0); e1 = ex2_approx(x1); }
                         if (2 * q4 + 1 < POLY) { e2 = ex2_poly(x2); e3 = ex2_poly(x3); } else { e2 = ex2_approx(x2); e3 = ex2_approx(x3); }
@@ -421,75 +425,67 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                             if (dq == 4 * q4 + 2) e2 = 32768.0f;
                             if (dq == 4 * q4 + 3) e3 = 32768.0f;
                         }
-                        packed[2 * q4] = pack_f16x2(e0, e1);
-                        packed[2 * q4 + 1] = pack_f16x2(e2, e3);
-                        acc_f16x2(rs0, rs1, packed[2 * q4]);
-                        acc_f16x2(rs2, rs3, packed[2 * q4 + 1]);
+                        pk[2 * q4] = pack_f16x2(e0, e1);
+                        pk[2 * q4 + 1] = pack_f16x2(e2, e3);
+                        acc_f16x2(rs0, rs1, pk[2 * q4]);
+                        acc_f16x2(rs2, rs3, pk[2 * q4 + 1]);
                     }
                 };
                 if (p.dbg != 0) {
 #pragma unroll
-                    for (int z = 0; z < 16; ++z) { pk0[z] = r0[z] ^ r1[2 * z]; pk1[z] = r0[z + 16]; }
+                    for (int z = 0; z < 16; ++z) pk[z] = r0[z] ^ r0[z + 16];
                 } else if (has_diag) {
-                    exp_chunk(r0, pk0, 0, std::true_type{});
-                    exp_chunk(r1, pk1, 1, std::true_type{});
+                    exp_chunk(std::true_type{});
                 } else {
-                    exp_chunk(r0, pk0, 0, std::false_type{});
-                    exp_chunk(r1, pk1, 1, std::false_type{});
+                    exp_chunk(std::false_type{});
                 }
-                tmem_st16(tS, pk0);
-                tmem_st16(tS + 16, pk1);
-                // fetch the next unit's S (the other buffer of this tile) while the stores drain -- only if it is already
-                // complete: waiting here would hold back this unit's e_ready and with it the MMAs that produce that S
+                tmem_st16(tS, pk);
                 const bool more = q + 1 < nunits;
                 const int kn = (int)((q + 1) & 1u);
                 const uint32_t gn = g + ((q + 1) >> 1);
-                const uint32_t tSn = tmem + (2 * w + kn) * 64 + lane_base;
+                const uint32_t tSn = tmem + (2 * w + kn) * 64 + 32 * h + lane_base;
                 bool fetched = false;
                 if (more && __all_sync(0xffffffffu, mbar_try_wait(s_full + 2 * w + kn, gn & 1))) {
                     tc_fence_after();
                     tmem_ld32(tSn, r0);
-                    tmem_ld32(tSn + 32, r1);
                     fetched = true;
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(e_ready + b);
-                if (row == 0) TC_TRACE(1 + w, gt, 3 + 3 * k);
+                if (tracer) TC_TRACE(1 + w, gt, 3 + 3 * k);
                 if (more && !fetched) {
-                    if (row == 0) TC_TRACE(1 + w, gn, 1 + 3 * kn);
+                    if (tracer) TC_TRACE(1 + w, gn, 1 + 3 * kn);
                     if (!mbar_wait(s_full + 2 * w + kn, gn & 1, p.err, 40 + 2 * w + kn)) { ok = false; break; }
                     tc_fence_after();
                     tmem_ld32(tSn, r0);
-                    tmem_ld32(tSn + 32, r1);
                 }
             }
-            if (ok) tmem_ld_wait();
             g += nt;
             if (!ok || !mbar_wait(phi_full + w, seg & 1, p.err, 50)) { ok = false; break; }
             tc_fence_after();
-            { // ---- flush Phi_w and the row sum: TMEM -> global partial sums
+            { // ---- flush this warp's half of Phi_w and its partial row sum: TMEM -> global partial sums
                 const bool valid = i < p.row0 + p.n_rows;
-                float *dst = p.phi_buf + i * TC_PHI_LD;
+                float *dst = p.phi_buf + i * TC_PHI_LD + 32 * h;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 16) {
+                for (int c0 = 0; c0 < 32; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(tP + c0, v);
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) atomicAdd(dst + c0 + q, __uint_as_float(v[q]) * TC_E_UNSCALE);
+                        for (int z = 0; z < 16; ++z) atomicAdd(dst + c0 + z, __uint_as_float(v[z]) * TC_E_UNSCALE);
                     }
                 }
-                if (valid) atomicAdd(dst + TC_ONES_ROW, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
+                if (valid) atomicAdd(p.phi_buf + i * TC_PHI_LD + TC_ONES_ROW, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
                 tc_fence_before(); // the a_ready arrival of the next segment orders these loads before its first MMA
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == P2_EWARPS) tmem_dealloc(tmem, 512);
 }
 
 } // namespace tc
