@@ -254,21 +254,27 @@ def main():
                 "comm_and_misc": sp.ms_comm / prof_iters}
 
     # ---- end-to-end leg: host buffers, H2D + step + D2H inside the timed region ------------------
+    # Every rank moves ITS rows of the particle matrix (svgdb_set_particles_rows / _get_particles_rows: with one rank these
+    # are the whole matrix); the other rows arrive over NVLink.  Bytes per step are summed over the ranks.
     host[...] = x0.T
     check(lib.svgdb_set_particles(ctx, host.ctypes.data_as(dp)))
     check(lib.svgdb_initialize(ctx))
+    r0, nr = C.c_int64(0), C.c_int64(0)
+    check(lib.svgdb_local_rows(ctx, C.byref(r0), C.byref(nr)))
+    mine = host[r0.value:r0.value + nr.value]                       # contiguous view of this rank's rows in the pinned buffer
+    mine_p = mine.ctypes.data_as(dp)
     for _ in range(args.warmup):
-        check(lib.svgdb_set_particles(ctx, host.ctypes.data_as(dp)))
+        check(lib.svgdb_set_particles_rows(ctx, mine_p))
         check(lib.svgdb_step(ctx, 1))
-        check(lib.svgdb_get_particles(ctx, host.ctypes.data_as(dp)))
+        check(lib.svgdb_get_particles_rows(ctx, mine_p))
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     f0.record(stream)
     for _ in range(args.steps):
-        check(lib.svgdb_set_particles(ctx, host.ctypes.data_as(dp)))   # H2D of this step's particles
+        check(lib.svgdb_set_particles_rows(ctx, mine_p))   # H2D of this step's particles (this rank's rows)
         check(lib.svgdb_step(ctx, 1))
-        check(lib.svgdb_get_particles(ctx, host.ctypes.data_as(dp)))   # D2H of the result (synchronous)
+        check(lib.svgdb_get_particles_rows(ctx, mine_p))   # D2H of the result (synchronous)
     f1.record(stream)
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_wall) if world == 1 else 0.0)
@@ -276,7 +282,7 @@ def main():
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    finite = bool(np.all(np.isfinite(host)))
+    finite = bool(np.all(np.isfinite(mine)))
 
     if rank == 0:
         peaks = load_peaks()
@@ -319,7 +325,7 @@ def main():
                        "fp32 ex2, FP64 optimizer state (error bound in DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms / args.steps,
-                    "call": "svgdb_set_particles(host) + svgdb_step(1) + svgdb_get_particles(host) == SVGD::Run() with NumIterations=1"},
+                    "call": "svgdb_set_particles_rows(host) + svgdb_step(1) + svgdb_get_particles_rows(host) per rank (== set/get_particles == SVGD::Run() with NumIterations=1 on one GPU); bytes summed over ranks"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -92,6 +92,12 @@ int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique
 /* ---- particles (the shared coordinate matrix, SVGD.hpp:176,393) ---------------------------- */
 int svgdb_set_particles(svgdb_ctx *ctx, const double *X_dxN);
 int svgdb_get_particles(svgdb_ctx *ctx, double *X_dxN);
+/* Row-sharded I/O for multi-rank runs (after svgdb_comm_init): this rank owns particles [row0, row0 + n_rows).
+ * set_particles_rows uploads only those (n_rows x d doubles, particle-contiguous) and all-gathers the rest over NVLink;
+ * get_particles_rows downloads only those.  With one rank they equal svgdb_set_particles / svgdb_get_particles. */
+int svgdb_local_rows(svgdb_ctx *ctx, int64_t *row0, int64_t *n_rows);
+int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local);
+int svgdb_get_particles_rows(svgdb_ctx *ctx, double *rows_local);
 
 /* ---- model: replaces MultivariateNormal (Model/MultivariateNormal.hpp:39-64) and the
  * `mvn1 + mvn2 (+ ...)` sum built with Model::operator+ (Model/Model.hpp:55-92): p = sum_c

@@ -69,7 +69,7 @@ NcclApi &nccl()
 }
 
 struct HostScratch { // pinned
-    unsigned long long below, max_below, cand_count;
+    unsigned long long below, cand_total, max_below, cand_count; // the first three mirror the device's pass_words
     unsigned long long hist[HIST_BINS];
     MedianResult med;
 };
@@ -83,7 +83,8 @@ struct svgdb_ctx {
     int precision = SVGDB_PRECISION_F64;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t side_stream = nullptr;                 // grad log p runs here, next to the median pass (it only needs X)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_med = nullptr;
+    bool med_pending = false; // the last median's result is still on its way to the pinned mirror
     bool grad_pending = false;
     int sm_count = 148;
 
@@ -118,7 +119,8 @@ struct svgdb_ctx {
     bool initialized = false;
 
     // median machinery
-    unsigned long long *below = nullptr, *max_below = nullptr, *hist = nullptr, *cand = nullptr, *cand_count = nullptr;
+    unsigned long long *pass_words = nullptr; // [below, cand_total, max_below] adjacent: one all-reduce, one read-back
+    unsigned long long *below = nullptr, *cand_total = nullptr, *max_below = nullptr, *hist = nullptr, *cand = nullptr, *cand_count = nullptr;
     uint64_t capacity = 1ull << 25;
     SelectState *sel = nullptr;
     MedianResult *medres = nullptr;
@@ -401,6 +403,8 @@ size_t dist_smem_bytes(int d, bool hist)
 #ifdef SVGDB_WITH_TC32
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift);
 #endif
+int reduce_pass_words(svgdb_ctx *ctx, int mode);
+int finish_median(svgdb_ctx *ctx);
 void prof_mark(svgdb_ctx *ctx, int i);
 int kick_grad(svgdb_ctx *ctx);
 
@@ -448,8 +452,17 @@ int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shi
     }
     ++ctx->stats.median_passes;
     TRY(kick_grad(ctx));
-    TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
-    TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
+    TRY(reduce_pass_words(ctx, mode));
+    return SVGDB_OK;
+}
+
+// Global counts of a distance pass: below and the in-bracket total are summed over the ranks in ONE all-reduce (the words
+// are adjacent), the largest value below the bracket (FP64 path only: the tensor-core passes do not track it) by a max.
+int reduce_pass_words(svgdb_ctx *ctx, int mode)
+{
+    if (mode != MODE_HIST) CU(cudaMemcpyAsync(ctx->cand_total, ctx->cand_count, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(allreduce_u64(ctx, ctx->below, mode == MODE_HIST ? 1 : 2, ncclSum));
+    if (ctx->precision != SVGDB_PRECISION_TC32) TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
     if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
     return SVGDB_OK;
 }
@@ -458,30 +471,18 @@ int launch_dist_pass(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shi
 // `cand_count` stays local; hs->below etc. are global.  mid_total gets the global in-bracket count.
 int read_pass_results(svgdb_ctx *ctx, int mode, uint64_t *mid_total)
 {
-    CU(cudaMemcpyAsync(&ctx->hs->below, ctx->below, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->hs->max_below, ctx->max_below, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->hs->below, ctx->pass_words, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream)); // below, cand_total, max_below
     if (mode == MODE_HIST) {
         CU(cudaMemcpyAsync(ctx->hs->hist, ctx->hist, HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     } else {
-        CU(cudaMemcpyAsync(&ctx->hs->cand_count, ctx->cand_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&ctx->hs->cand_count, ctx->cand_count, 8, cudaMemcpyDeviceToHost, ctx->stream)); // stays rank-local
         CU(cudaStreamSynchronize(ctx->stream));
-        uint64_t total = ctx->hs->cand_count;
-        if (ctx->world > 1) {
-            // global in-bracket count: reuse `below` as a scratch word after it has been read
-            CU(cudaMemcpyAsync(ctx->below, ctx->cand_count, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
-            unsigned long long tmp = 0;
-            CU(cudaMemcpyAsync(&tmp, ctx->below, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            total = tmp;
-        }
-        if (mid_total) *mid_total = total;
+        if (mid_total) *mid_total = ctx->hs->cand_total; // global in-bracket count
     }
     return SVGDB_OK;
 }
 
-// Radix select of rank kk among this rank's candidates (hist all-reduced across ranks), then a.
 int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n)
 {
     uint64_t m_local = std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
@@ -522,6 +523,7 @@ int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even,
 // GaussianRBFKernel::ComputeScale, Median branch (Kernel/GaussianRBFKernel.hpp:168-188), exact.
 int median_scale(svgdb_ctx *ctx)
 {
+    TRY(finish_median(ctx));
     const long double totald = (long double)ctx->N * (long double)ctx->N;
     if (totald > 1.8e19L) return fail(ctx, SVGDB_ERR_INVALID, "n^2 overflows 64 bits");
     const uint64_t total = (uint64_t)ctx->N * (uint64_t)ctx->N;
@@ -608,8 +610,21 @@ int median_scale(svgdb_ctx *ctx)
 #endif
         TRY(run_select(ctx, lo, hi, kk, even, log_n));
     }
+    // The result (needed by the host only for the NEXT bracket prediction and for statistics) is read back without
+    // stopping here: finish_median() picks it up before the next prediction, by which time it has long arrived.
     CU(cudaMemcpyAsync(&ctx->hs->med, ctx->medres, sizeof(MedianResult), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev_med, ctx->stream));
+    ctx->med_pending = true;
+    return SVGDB_OK;
+}
+
+// Completes the bookkeeping of the last median_scale(): bracket prediction state and stats.last_scale.
+int finish_median(svgdb_ctx *ctx)
+{
+    if (!ctx->med_pending) return SVGDB_OK;
+    ctx->med_pending = false;
+    CU(cudaEventSynchronize(ctx->ev_med));
+    const double delta_max = std::min(0.0625, (double)ctx->capacity / (10.0 * (double)ctx->N * (double)ctx->N));
     ctx->stats.last_scale = ctx->hs->med.scale;
     {
         const double m_now = 0.5 * (ctx->hs->med.d2_lo + ctx->hs->med.d2_hi);
@@ -846,9 +861,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     }
     ++ctx->stats.median_passes;
     TRY(kick_grad(ctx));
-    TRY(allreduce_u64(ctx, ctx->below, 1, ncclSum));
-    TRY(allreduce_u64(ctx, ctx->max_below, 1, ncclMax));
-    if (mode == MODE_HIST) TRY(allreduce_u64(ctx, ctx->hist, HIST_BINS, ncclSum));
+    TRY(reduce_pass_words(ctx, mode));
     return SVGDB_OK;
 }
 
@@ -1095,6 +1108,7 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_med, cudaEventDisableTiming));
     if (const char *s = std::getenv("SVGDB_CAND_CAPACITY")) {
         long long v = std::atoll(s);
         if (v >= 64) ctx->capacity = (uint64_t)v;
@@ -1132,8 +1146,10 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     }
 #endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
-    CU(cudaMalloc(&ctx->below, 8));
-    CU(cudaMalloc(&ctx->max_below, 8));
+    CU(cudaMalloc(&ctx->pass_words, 4 * 8));
+    ctx->below = ctx->pass_words;
+    ctx->cand_total = ctx->pass_words + 1;
+    ctx->max_below = ctx->pass_words + 2;
     CU(cudaMalloc(&ctx->cand_count, 8));
     CU(cudaMalloc(&ctx->hist, HIST_BINS * 8));
     CU(cudaMalloc(&ctx->sel, sizeof(SelectState)));
@@ -1157,12 +1173,13 @@ void svgdb_destroy(svgdb_ctx *ctx)
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     free_sharded(ctx);
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
-    cudaFree(ctx->below); cudaFree(ctx->max_below); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
+    cudaFree(ctx->pass_words); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
     cudaFree(ctx->sel); cudaFree(ctx->medres);
     if (ctx->hs) cudaFreeHost(ctx->hs);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_med) cudaEventDestroy(ctx->ev_med);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1219,6 +1236,36 @@ int svgdb_get_particles(svgdb_ctx *ctx, double *X)
 {
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
     CU(cudaMemcpyAsync(X, ctx->X[ctx->cur], (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(check_tc_err(ctx));
+#endif
+    return SVGDB_OK;
+}
+
+int svgdb_local_rows(svgdb_ctx *ctx, int64_t *row0, int64_t *n_rows)
+{
+    if (!ctx || !row0 || !n_rows) return SVGDB_ERR_INVALID;
+    *row0 = ctx->row0;
+    *n_rows = ctx->n_rows;
+    return SVGDB_OK;
+}
+
+int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local)
+{
+    if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    if (ctx->n_rows > 0)
+        CU(cudaMemcpyAsync(ctx->X[ctx->cur] + (size_t)ctx->row0 * ctx->d, rows_local, (size_t)ctx->n_rows * ctx->d * sizeof(double),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    return allgather_rows(ctx, ctx->X[ctx->cur], ctx->d); // every rank needs all particles: NVLink instead of N x PCIe
+}
+
+int svgdb_get_particles_rows(svgdb_ctx *ctx, double *rows_local)
+{
+    if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    if (ctx->n_rows > 0)
+        CU(cudaMemcpyAsync(rows_local, ctx->X[ctx->cur] + (size_t)ctx->row0 * ctx->d, (size_t)ctx->n_rows * ctx->d * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(check_tc_err(ctx));
@@ -1429,6 +1476,7 @@ int svgdb_sync(svgdb_ctx *ctx)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
     CU(cudaStreamSynchronize(ctx->stream));
+    TRY(finish_median(ctx));
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(check_tc_err(ctx));
 #endif
@@ -1445,6 +1493,7 @@ int svgdb_set_profiling(svgdb_ctx *ctx, int enabled)
 int svgdb_get_stats(svgdb_ctx *ctx, svgdb_stats *out)
 {
     if (!ctx || !out) return SVGDB_ERR_INVALID;
+    TRY(finish_median(ctx)); // stats.last_scale
     *out = ctx->stats;
     return SVGDB_OK;
 }
@@ -1494,6 +1543,7 @@ int svgdb_time_kernel(svgdb_ctx *ctx, int which, int reps, int variant, double r
     CU(cudaEventCreate(&e1));
     int rc = SVGDB_OK;
     if (which == 0) { // distance pass, collecting a bracket of the given relative half-width around the last median
+        TRY(finish_median(ctx));
         if (ctx->n_hist < 1) return fail(ctx, SVGDB_ERR_UNSET, "svgdb_time_kernel: no median yet (run a step first)");
         const double m = ctx->med_hist[0];
         const uint64_t klo = key_of(std::max(m * (1.0 - rel_halfwidth), 0.0)), khi = key_of(m * (1.0 + rel_halfwidth)) + 1;
