@@ -13,7 +13,7 @@ lib = _capi.load()
 assert lib.svgdb_step(s._ctx, 6) == 0
 ms = C.c_float()
 for rel in (7.8e-4, 1e-4, 2e-5):
-    for variant in (0, 2, 1):
+    for variant in (0, 2, 1, 3):
         rc = lib.svgdb_time_kernel(s._ctx, 0, 5, variant, rel, C.byref(ms))
         print("dist pass  rel half-width %.1e variant %d: %.3f ms (rc %d)" % (rel, variant, ms.value, rc))
 rc = lib.svgdb_time_kernel(s._ctx, 1, 5, 0, 0.0, C.byref(ms))

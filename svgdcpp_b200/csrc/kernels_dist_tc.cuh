@@ -109,7 +109,7 @@ struct Dist2Args {
     unsigned long long *below, *hist, *cand, *cand_count;
     unsigned long long capacity;
     int *err;
-    int dbg; // measurement aid: 1 = counting warps only hand the buffers back, 2 = count without collecting
+    int dbg; // measurement aid: 1 = counting warps only hand the buffers back, 2 = count without collecting, 3 = 1 + no TMA after priming
 };
 
 // Work list: for this rank's l-th i-pair ip = offset + stride * l, the j-tiles jt in [2 ip, n_jtiles) (tile-level upper
@@ -190,6 +190,11 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
             for (int jt = sg.jb; ok && jt < sg.je; ++jt, ++g) {
                 const uint32_t slot = g % D2_STAGES, use = g / D2_STAGES;
                 if (!mbar_wait(empty + slot, (use & 1) ^ 1, p.err, 50)) { ok = false; break; }
+                if (p.dbg == 3 && g >= D2_STAGES) { // measurement aid: stale operands, no TMA / L2 traffic
+                    if (elect_one()) mbar_arrive(full + slot);
+                    __syncwarp();
+                    continue;
+                }
                 if (elect_one()) {
                     uint8_t *st = smem + slot * D2_STAGE;
                     mbar_arrive_expect_tx(full + slot, D2_TX);
@@ -359,7 +364,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_free + 3 * w + buf); // this warp's part of the accumulator is in registers
-                    if (p.dbg == 1) continue;
+                    if (p.dbg == 1 || p.dbg == 3) continue;
                     if (wgt != cur_wgt) { compact(); cur_wgt = wgt; }
                     if (has_diag) { // |x_i - x_i|^2 = 0 exactly (diagonal tiles only)
 #pragma unroll
