@@ -321,8 +321,8 @@ def main():
                        "l2": "working set (X, V, X_next, optimizer state) = %d MB > 126 MB L2; compute-bound, no flush" % (5 * nbytes // 2 ** 20),
                        "median_passes_per_step": median_passes / max(1, args.steps), "finite": finite,
                        "precision_mode": "F64: DMMA fp64 end to end" if precision == _capi.PRECISION_F64 else
-                       "TC32: tcgen05 kind::f16 MMAs on split-bf16 particles / scaled-fp16 kernel values, fp32 accumulation in TMEM, "
-                       "fp32 ex2, FP64 optimizer state (error bound in DESIGN.md)"},
+                       "TC32: tcgen05 kind::f16 MMAs on split fp16 (pair kernel) / bf16 (median) particles and scaled-fp16 kernel values, "
+                       "fp32 accumulation in TMEM, fp32 ex2, FP64 optimizer state (error bound in DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms / args.steps,
                     "call": "svgdb_set_particles_rows(host) + svgdb_step(1) + svgdb_get_particles_rows(host) per rank (== set/get_particles == SVGD::Run() with NumIterations=1 on one GPU); bytes summed over ranks"},
