@@ -29,7 +29,7 @@ constexpr uint32_t D2_STAGE = D2_XB_BYTES + P2_W_BYTES; // 36 KB
 constexpr uint32_t D2_TX = D2_STAGE;
 constexpr uint32_t D2_SMEM = D2_STAGES * D2_STAGE + 2 * P2_AEX_BYTES + D2_CWARPS * TC_WBUF * 4 + D2_CWARPS * 32 * D2_PRIV * 4 + 256 + 1024;
 constexpr uint32_t D2_COL_A = 384;
-static_assert(HIST_BINS * 4 <= D2_CWARPS * TC_WBUF * 4, "histogram must fit the warp staging area");
+static_assert(HIST_BINS * 8 <= D2_CWARPS * TC_WBUF * 4, "histogram must fit the warp staging area");
 
 // Operand rows for the distance pass, one warp per particle (scale 1):
 //   XA2[row] = -2 [hi | lo] (row operand -> TMEM),  XBD[row] = [hi | lo] (column operand, TMA),
@@ -163,7 +163,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     uint64_t *a_ready = s_free + 6;         // [2] row operand of tile w in TMEM / shared memory (8 warp arrivals)
     uint64_t *seg_done = a_ready + 2;       // [2] every MMA of the segment on tile w complete (commit)
     uint32_t *tmem_holder = (uint32_t *)(seg_done + 2);
-    unsigned int *shist = (unsigned int *)wbuf; // [HIST_BINS] (MODE_HIST only: aliases the warp staging buffers)
+    unsigned long long *shist = (unsigned long long *)wbuf; // [HIST_BINS] 64-bit (a CTA sees > 2^32 pairs at N = 1M); MODE_HIST only: aliases the warp staging buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -173,7 +173,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
         fence_barrier_init();
     }
     if (MODE == MODE_HIST)
-        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) shist[b] = 0u;
+        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) shist[b] = 0ull;
     if (warp == D2_CWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
@@ -271,7 +271,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                 if (MODE == MODE_HIST) {
                     for (uint32_t e = 0; e < mine; ++e) {
                         const unsigned long long bin = (dist_key(lds_f32(priv_base + 128u * e)) - p.lo_key) >> p.shift;
-                        if (bin < (unsigned long long)HIST_BINS) atomicAdd(&shist[(unsigned int)bin], cur_wgt); // the collected range may end just past hi
+                        if (bin < (unsigned long long)HIST_BINS) atomicAdd(&shist[(unsigned int)bin], (unsigned long long)cur_wgt); // the collected range may end just past hi
                     }
                 } else {
                     if (count + tot * cur_wgt > (unsigned int)TC_WBUF) { dist_flush2(mybuf, count, p.cand, p.cand_count, p.capacity); count = 0; }
@@ -422,8 +422,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     __syncthreads();
     if (MODE == MODE_HIST)
         for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) {
-            unsigned int cc = shist[b];
-            if (cc) atomicAdd(&p.hist[b], (unsigned long long)cc);
+            unsigned long long cc = shist[b];
+            if (cc) atomicAdd(&p.hist[b], cc);
         }
     if (warp == D2_CWARPS) tmem_dealloc(tmem, 512);
 }

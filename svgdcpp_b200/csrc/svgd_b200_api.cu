@@ -129,6 +129,7 @@ struct svgdb_ctx {
     int n_hist = 0;              // valid entries of med_hist (most recent first)
     double med_hist[3] = {0.0, 0.0, 0.0};
     double delta = 0.0;          // relative half-width of the predicted bracket
+    double density = 2.0;        // candidates per (pair x unit relative width of D2) seen by the last predicted pass
     double resid[2] = {0.0, 0.0}; // recent relative prediction errors
     double last_pred = 0.0;
     bool have_pred = false;
@@ -520,6 +521,14 @@ int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even,
     return SVGDB_OK;
 }
 
+// Largest relative half-width whose bracket is expected to fit the candidate buffer with a 2.5x margin, from the
+// density of distances around the median observed by the last predicted pass (high-dimensional particle sets have
+// narrow distance distributions: the same relative width holds many more pairs).
+double bracket_delta_max(const svgdb_ctx *ctx, double total)
+{
+    return std::min(0.0625, 0.4 * (double)ctx->capacity / (2.0 * std::max(ctx->density, 0.25) * total));
+}
+
 // GaussianRBFKernel::ComputeScale, Median branch (Kernel/GaussianRBFKernel.hpp:168-188), exact.
 int median_scale(svgdb_ctx *ctx)
 {
@@ -539,9 +548,9 @@ int median_scale(svgdb_ctx *ctx)
     //    extrapolated (up to quadratically) from the last medians; the bracket half-width follows the recent
     //    extrapolation error and is capped by what the candidate buffer can hold.  The prediction is only a hint:
     //    the exact counts returned by the pass decide whether it held.
-    const double delta_max = std::min(0.0625, (double)ctx->capacity / (10.0 * (double)total));
+    double delta_max = bracket_delta_max(ctx, (double)total);
     double predicted = 0.0;
-    if (ctx->n_hist > 0 && total > ctx->capacity) {
+    if (ctx->n_hist > 0 && total > 65536ull) { // (tiny problems: one pass collecting everything is cheaper than any logic)
         const double *m = ctx->med_hist;
         predicted = ctx->n_hist >= 3 ? 3.0 * m[0] - 3.0 * m[1] + m[2] : ctx->n_hist == 2 ? 2.0 * m[0] - m[1] : m[0];
         if (!(predicted > 0.0) || !std::isfinite(predicted)) predicted = m[0];
@@ -550,6 +559,8 @@ int median_scale(svgdb_ctx *ctx)
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
         TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
         uint64_t b = ctx->hs->below;
+        ctx->density = std::max(0.25, (double)mid / (2.0 * dl * (double)total)); // exact in-bracket count, even on overflow
+        delta_max = bracket_delta_max(ctx, (double)total);
         // the tensor-core pass does not track the largest value below the bracket, so for an even count the lower
         // middle element must be a candidate as well (b < k_hi)
         const bool need_both = even && ctx->precision == SVGDB_PRECISION_TC32;
@@ -624,7 +635,7 @@ int finish_median(svgdb_ctx *ctx)
     if (!ctx->med_pending) return SVGDB_OK;
     ctx->med_pending = false;
     CU(cudaEventSynchronize(ctx->ev_med));
-    const double delta_max = std::min(0.0625, (double)ctx->capacity / (10.0 * (double)ctx->N * (double)ctx->N));
+    const double delta_max = bracket_delta_max(ctx, (double)ctx->N * (double)ctx->N);
     ctx->stats.last_scale = ctx->hs->med.scale;
     {
         const double m_now = 0.5 * (ctx->hs->med.d2_lo + ctx->hs->med.d2_hi);
@@ -1109,6 +1120,12 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_med, cudaEventDisableTiming));
+    {
+        // candidate buffer of the median select: 2^25 keys up to N = 92K, then N^2 / 256 keys (the bracket that fits it keeps
+        // the same relative width), at most 2^31 keys (16 GiB)
+        const long double want = (long double)n_total * (long double)n_total / 256.0L;
+        if (want > (long double)ctx->capacity) ctx->capacity = (uint64_t)std::min<long double>(want, 2147483648.0L);
+    }
     if (const char *s = std::getenv("SVGDB_CAND_CAPACITY")) {
         long long v = std::atoll(s);
         if (v >= 64) ctx->capacity = (uint64_t)v;
