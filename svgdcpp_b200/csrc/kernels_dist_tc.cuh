@@ -142,7 +142,9 @@ __device__ __forceinline__ long long d2_total_units(const Dist2Args &p)
     return tot;
 }
 
-template <int MODE>
+// GATED: the bracket is expected to hold so few distances that most 32 x 32 chunks contain none -- count and test with 3
+// instructions per distance and take the collecting path only for chunks where some lane saw a hit.
+template <int MODE, bool GATED>
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Dist2Args p)
 {
@@ -393,6 +395,43 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     if (p.dbg == 2) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) cnt4[q & 3] += __float_as_uint(__uint_as_float(r0[q]) - lo) >> 31;
+                    } else if (GATED && !open_low) {
+                        // t = d2 - lo; count += sign(t); flag |= bits(t) <u bits(width): FADD, LEA.HI, ISETP.OR per distance
+                        unsigned int flag;
+#define D2_F4(a, b, c, d)                                                                                                          \
+    "sub.rn.f32 t, %" #a ", %37; mov.b32 u, t; shr.u32 s, u, 31; add.u32 %0, %0, s; setp.lt.or.u32 pf, u, %38, pf;\n\t"                  \
+    "sub.rn.f32 t, %" #b ", %37; mov.b32 u, t; shr.u32 s, u, 31; add.u32 %1, %1, s; setp.lt.or.u32 pf, u, %38, pf;\n\t"                  \
+    "sub.rn.f32 t, %" #c ", %37; mov.b32 u, t; shr.u32 s, u, 31; add.u32 %2, %2, s; setp.lt.or.u32 pf, u, %38, pf;\n\t"                  \
+    "sub.rn.f32 t, %" #d ", %37; mov.b32 u, t; shr.u32 s, u, 31; add.u32 %3, %3, s; setp.lt.or.u32 pf, u, %38, pf;\n\t"
+                        asm volatile("{\n\t.reg .pred pf;\n\t.reg .f32 t;\n\t.reg .b32 u, s;\n\t"
+                                     "setp.ne.u32 pf, 0, 0;\n\t"
+                                     D2_F4(5, 6, 7, 8) D2_F4(9, 10, 11, 12) D2_F4(13, 14, 15, 16) D2_F4(17, 18, 19, 20)
+                                     D2_F4(21, 22, 23, 24) D2_F4(25, 26, 27, 28) D2_F4(29, 30, 31, 32) D2_F4(33, 34, 35, 36)
+                                     "selp.u32 %4, 1, 0, pf;\n\t}"
+                                     : "+r"(cnt4[0]), "+r"(cnt4[1]), "+r"(cnt4[2]), "+r"(cnt4[3]), "=r"(flag)
+                                     : "f"(__uint_as_float(r0[0])), "f"(__uint_as_float(r0[1])), "f"(__uint_as_float(r0[2])), "f"(__uint_as_float(r0[3])),
+                                       "f"(__uint_as_float(r0[4])), "f"(__uint_as_float(r0[5])), "f"(__uint_as_float(r0[6])), "f"(__uint_as_float(r0[7])),
+                                       "f"(__uint_as_float(r0[8])), "f"(__uint_as_float(r0[9])), "f"(__uint_as_float(r0[10])), "f"(__uint_as_float(r0[11])),
+                                       "f"(__uint_as_float(r0[12])), "f"(__uint_as_float(r0[13])), "f"(__uint_as_float(r0[14])), "f"(__uint_as_float(r0[15])),
+                                       "f"(__uint_as_float(r0[16])), "f"(__uint_as_float(r0[17])), "f"(__uint_as_float(r0[18])), "f"(__uint_as_float(r0[19])),
+                                       "f"(__uint_as_float(r0[20])), "f"(__uint_as_float(r0[21])), "f"(__uint_as_float(r0[22])), "f"(__uint_as_float(r0[23])),
+                                       "f"(__uint_as_float(r0[24])), "f"(__uint_as_float(r0[25])), "f"(__uint_as_float(r0[26])), "f"(__uint_as_float(r0[27])),
+                                       "f"(__uint_as_float(r0[28])), "f"(__uint_as_float(r0[29])), "f"(__uint_as_float(r0[30])), "f"(__uint_as_float(r0[31])),
+                                       "f"(lo), "r"(wbits));
+#undef D2_F4
+                        if (__any_sync(0xffffffffu, flag != 0u)) { // some distance of this warp's chunk lies in [lo, hi'): collect with the same test
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                asm volatile("{\n\t.reg .pred pi;\n\t.reg .f32 t;\n\t.reg .b32 u;\n\t"
+                                             "sub.rn.f32 t, %1, %2;\n\t"
+                                             "mov.b32 u, t;\n\t"
+                                             "setp.lt.u32 pi, u, %3;\n\t"
+                                             "@pi st.shared.f32 [%0], %1;\n\t"
+                                             "@pi add.u32 %0, %0, 128;\n\t}"
+                                             : "+r"(paddr)
+                                             : "f"(__uint_as_float(r0[q])), "f"(lo), "r"(wbits)
+                                             : "memory");
+                        }
                     } else if (!open_low) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) visit(__uint_as_float(r0[q]), cnt4[q & 3]);
