@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # A/B run of the pair-interaction kernel variants: short bench lines per variant.
-#   usage: gpu_phi2.sh <tag> "<kernel poly split dbg>" ...
+#   usage: gpu_phi2.sh <tag> "<poly dbg>" ...   (SVGDB_PHI_POLY: exponential pairs per chunk on the FMA pipe; SVGDB_PHI_DBG: see Phi2Args::dbg)
 set -u
 TAG=${1:-phi2}; shift
 OUT=gpurun_out/$TAG
@@ -11,9 +11,9 @@ if [ "${PYTEST:-1}" = "1" ]; then
 fi
 for cfg in "$@"; do
   set -- $cfg
-  F="$OUT/bench_k$1_p$2_s$3_d$4"
-  SVGDB_PHI_KERNEL=$1 SVGDB_PHI_POLY=$2 SVGDB_PHI_SPLIT=$3 SVGDB_PHI_DBG=$4 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$F.json" 2> "$F.err"
-  echo "kernel $1 poly $2 split $3 dbg $4: exit $?"; python - "$F.json" <<'PY'
+  F="$OUT/bench_p$1_d$2"
+  SVGDB_PHI_POLY=$1 SVGDB_PHI_DBG=$2 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$F.json" 2> "$F.err"
+  echo "poly $1 dbg $2: exit $?"; python - "$F.json" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read())

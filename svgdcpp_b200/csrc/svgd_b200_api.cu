@@ -136,26 +136,20 @@ struct svgdb_ctx {
 
     // tensor-core path (SVGDB_PRECISION_TC32)
     int64_t n_pad128 = 0;
-    __nv_bfloat16 *XA = nullptr, *XB = nullptr;
-    __half *VT = nullptr;
-    float *beta = nullptr, *rf = nullptr, *phi_buf = nullptr;
+    float *phi_buf = nullptr;
     double *rt = nullptr, *colsum = nullptr;
     int *tc_err = nullptr;
     long long *tc_trace = nullptr; // SVGDB_TC_TRACE=<file>: timeline of CTA 0 of the pair-interaction kernel
-    CUtensorMap mapA{}, mapB{}, mapV{};
     // persistent pair-interaction kernel (kernels_phi_tc.cuh): fp16 row / column operands, exponent offsets, V^T
     __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
     __half *UA2 = nullptr, *WB2 = nullptr; // exponent-offset K chunks (row / column side)
     CUtensorMap mapB2{}, mapV2{};
     __nv_bfloat16 *XBD = nullptr; // column operand [hi | lo] of the persistent distance pass (kernels_dist_tc.cuh)
     CUtensorMap mapBD{};
-    int dist_version = 2; // SVGDB_DIST_KERNEL=1 selects the first (SS-mode) distance kernel
     int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
     int dist_gated = -1;   // SVGDB_DIST_GATED=0/1 forces the flat / gated counting epilogue (default: chosen per pass)
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
-    int phi_version = 2; // SVGDB_PHI_KERNEL=1 selects the first (SS-mode, one CTA per j-split) kernel
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
-    int phi_split = 1;   // SVGDB_PHI_SPLIT=0: one exp warpgroup per i-tile instead of both on the same tile
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
 
     // measurement
@@ -253,7 +247,7 @@ int free_sharded(svgdb_ctx *ctx)
     cudaFree(ctx->X[0]); cudaFree(ctx->X[1]); cudaFree(ctx->V); cudaFree(ctx->G); cudaFree(ctx->r);
     cudaFree(ctx->s1); cudaFree(ctx->s2); cudaFree(ctx->phi_dbg);
     ctx->X[0] = ctx->X[1] = ctx->V = ctx->G = ctx->r = ctx->s1 = ctx->s2 = ctx->phi_dbg = nullptr;
-    cudaFree(ctx->XA); cudaFree(ctx->XB); cudaFree(ctx->VT); cudaFree(ctx->beta); cudaFree(ctx->rf); cudaFree(ctx->phi_buf);
+    cudaFree(ctx->phi_buf);
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
     cudaFree(ctx->XBD);
     ctx->XBD = nullptr;
@@ -261,9 +255,7 @@ int free_sharded(svgdb_ctx *ctx)
     ctx->XA2 = ctx->XB2 = ctx->VT2 = nullptr;
     ctx->UA2 = ctx->WB2 = nullptr;
     ctx->tc_trace = nullptr;
-    ctx->XA = ctx->XB = nullptr;
-    ctx->VT = nullptr;
-    ctx->beta = ctx->rf = ctx->phi_buf = nullptr;
+    ctx->phi_buf = nullptr;
     ctx->rt = ctx->colsum = nullptr;
     ctx->tc_err = nullptr;
     return SVGDB_OK;
@@ -300,9 +292,6 @@ int alloc_tc32(svgdb_ctx *ctx)
     using namespace svgdb::tc;
     ctx->n_pad128 = (ctx->N + 127) / 128 * 128;
     const size_t np = (size_t)ctx->n_pad128;
-    CU(cudaMalloc(&ctx->XA, np * TC_KTOT * 2));
-    CU(cudaMalloc(&ctx->XB, np * TC_KTOT * 2));
-    CU(cudaMalloc(&ctx->VT, (size_t)TC_NV * np * 2));
     CU(cudaMalloc(&ctx->rt, np * 8));
     CU(cudaMalloc(&ctx->colsum, 64 * 8));
     CU(cudaMalloc(&ctx->tc_err, 4));
@@ -312,13 +301,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     }
     // rows of a tile may reach past the last rank-local row: keep a tile of slack
     CU(cudaMalloc(&ctx->phi_buf, (np + 256) * TC_PHI_LD * 4));
-    CU(cudaMemsetAsync(ctx->XA, 0, np * TC_KTOT * 2, ctx->stream));
-    CU(cudaMemsetAsync(ctx->XB, 0, np * TC_KTOT * 2, ctx->stream));
-    CU(cudaMemsetAsync(ctx->VT, 0, (size_t)TC_NV * np * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream));
-    TRY(make_bf16_map(ctx, &ctx->mapA, ctx->XA, np, TC_KTOT, 128));
-    TRY(make_bf16_map(ctx, &ctx->mapB, ctx->XB, np, TC_KTOT, 128));
-    TRY(make_bf16_map(ctx, &ctx->mapV, ctx->VT, TC_NV, np, TC_NVH));
     // persistent kernel operands (16-bit elements: the bf16 tensor-map type moves fp16 bit patterns unchanged)
     CU(cudaMalloc(&ctx->XA2, (np + 256) * P2_A_LD * 2));
     CU(cudaMalloc(&ctx->XB2, np * 64 * 2));
@@ -329,13 +312,10 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMemsetAsync(ctx->UA2, 0, (np + 256) * 16 * 2, ctx->stream));
     CU(cudaMalloc(&ctx->XBD, np * 128 * 2));
     TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
-    if (const char *e = std::getenv("SVGDB_DIST_KERNEL")) ctx->dist_version = std::atoi(e) == 1 ? 1 : 2;
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
     TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
-    if (const char *e = std::getenv("SVGDB_PHI_KERNEL")) ctx->phi_version = std::atoi(e) == 1 ? 1 : 2;
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
-    if (const char *e = std::getenv("SVGDB_PHI_SPLIT")) ctx->phi_split = std::atoi(e) != 0;
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     return SVGDB_OK;
 }
@@ -622,7 +602,7 @@ int median_scale(svgdb_ctx *ctx)
     } else {
 #ifdef SVGDB_WITH_TC32
         // the persistent tensor-core pass collects a contiguous range [lo, hi') with hi' slightly past hi
-        if (ctx->precision == SVGDB_PRECISION_TC32 && ctx->dist_version == 2 && ctx->collect_hi_ext > hi) hi = ctx->collect_hi_ext;
+        if (ctx->precision == SVGDB_PRECISION_TC32 && ctx->collect_hi_ext > hi) hi = ctx->collect_hi_ext;
 #endif
         TRY(run_select(ctx, lo, hi, kk, even, log_n));
     }
@@ -758,25 +738,17 @@ int launch_make_v(svgdb_ctx *ctx)
 }
 
 #ifdef SVGDB_WITH_TC32
-// centred bf16-split operand rows for the distance pass (mode 0) or the pair-interaction pass (mode 1, needs a)
-int launch_tc_split(svgdb_ctx *ctx, int mode)
+// column sums (for centring) and the centred bf16-split operand rows of the distance pass
+int launch_dist_operands(svgdb_ctx *ctx)
 {
     using namespace svgdb::tc;
-    if (mode == SPLIT_DIST) {
-        CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
-        colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
-        KERNEL_CHECK();
-    }
-    if (mode == SPLIT_DIST && ctx->dist_version == 2) {
-        const int64_t rows_a = ctx->n_pad128 + 256;
-        split_dist2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(
-            ctx->X[ctx->cur], ctx->colsum, ctx->N, rows_a, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
-            reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
-        KERNEL_CHECK();
-        return SVGDB_OK;
-    }
-    split_kernel<<<(unsigned)((ctx->n_pad128 + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128,
-                                                                                 ctx->d, mode, ctx->XA, ctx->XB, ctx->rt);
+    CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
+    colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
+    KERNEL_CHECK();
+    const int64_t rows_a = ctx->n_pad128 + 256;
+    split_dist2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(
+        ctx->X[ctx->cur], ctx->colsum, ctx->N, rows_a, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
+        reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
     KERNEL_CHECK();
     return SVGDB_OK;
 }
@@ -795,53 +767,36 @@ float key_to_float_ceil(uint64_t key)
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
     using namespace svgdb::tc;
-    DistTcArgs a{};
-    a.n_total = ctx->N;
-    a.row0 = 0; // symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks
-    a.n_rows = ctx->N;
-    a.sym = 1;
-    a.pair_offset = ctx->rank;
-    a.pair_stride = ctx->world;
-    a.n_jtiles = (int)(ctx->n_pad128 / 128);
-    a.jsplit = std::max(1, std::min(8, a.n_jtiles / 8));
-    a.lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
-    a.hi_f = key_to_float_ceil(hi);
-    a.lo_key = lo;
-    a.shift = shift;
-    a.below = ctx->below;
-    a.hist = ctx->hist;
-    a.cand = ctx->cand;
-    a.cand_count = ctx->cand_count;
-    a.capacity = ctx->capacity;
-    a.err = ctx->tc_err;
-    a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? ctx->tc_trace : nullptr;
+    const float lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
+    const float hi_f = key_to_float_ceil(hi);
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
+    // symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks
     const int n_ipairs_all = (int)((ctx->N + 255) / 256);
     const int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
-    if (n_ipairs > 0 && ctx->dist_version == 2) {
+    if (n_ipairs > 0) {
         Dist2Args b{};
         b.XA2 = reinterpret_cast<const __nv_bfloat16 *>(ctx->XA2);
         b.UA = reinterpret_cast<const __nv_bfloat16 *>(ctx->UA2);
         b.WB = reinterpret_cast<const __nv_bfloat16 *>(ctx->WB2);
         b.n_total = ctx->N;
-        b.n_jtiles = a.n_jtiles;
+        b.n_jtiles = (int)(ctx->n_pad128 / 128);
         b.pair_offset = ctx->rank;
         b.pair_stride = ctx->world;
         b.n_ipairs = n_ipairs;
-        b.lo_f = a.lo_f;
-        b.hi_f = a.hi_f;
-        b.open_low = std::isinf(a.lo_f) ? 1 : 0;
+        b.lo_f = lo_f;
+        b.hi_f = hi_f;
+        b.open_low = std::isinf(lo_f) ? 1 : 0;
         {
-            float wdt = std::isinf(a.lo_f) || std::isinf(a.hi_f) ? INFINITY : (float)((double)a.hi_f - (double)a.lo_f);
-            if ((double)wdt < (double)a.hi_f - (double)a.lo_f) wdt = std::nextafterf(wdt, INFINITY);
+            float wdt = std::isinf(lo_f) || std::isinf(hi_f) ? INFINITY : (float)((double)hi_f - (double)lo_f);
+            if ((double)wdt < (double)hi_f - (double)lo_f) wdt = std::nextafterf(wdt, INFINITY);
             wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
             if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
             uint32_t wb;
             std::memcpy(&wb, &wdt, 4);
             b.width_bits = wb;
             // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
-            float hi_ext = std::isinf(wdt) || std::isinf(a.lo_f) ? a.hi_f : (float)((double)a.lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
+            float hi_ext = std::isinf(wdt) || std::isinf(lo_f) ? hi_f : (float)((double)lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
             hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
             ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
         }
@@ -876,16 +831,6 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             else dist2_tc32_kernel<MODE_COLLECT, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
         }
         KERNEL_CHECK();
-    } else if (n_ipairs > 0) {
-        unsigned grid = (unsigned)(n_ipairs * a.jsplit);
-        if (mode == MODE_HIST) {
-            CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
-            dist_tc32_kernel<MODE_HIST><<<grid, 320, TC_DIST_SMEM_HIST, ctx->stream>>>(ctx->mapA, ctx->mapB, a);
-        } else {
-            CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
-            dist_tc32_kernel<MODE_COLLECT><<<grid, 320, TC_DIST_SMEM_BASE, ctx->stream>>>(ctx->mapA, ctx->mapB, a);
-        }
-        KERNEL_CHECK();
     }
     ++ctx->stats.median_passes;
     TRY(kick_grad(ctx));
@@ -893,84 +838,47 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     return SVGDB_OK;
 }
 
-// Split of the j range so that (i-pairs x splits) fills the SMs in whole waves: minimise
-// waves * (tiles per unit * t_tile + per-unit prologue/flush), both in tensor-pipe cycles.
-int pick_jsplit(int n_units_i, int n_jtiles, int sms)
-{
-    int best = 1;
-    double best_cost = 1e300;
-    for (int s = 1; s <= std::min(n_jtiles, 64); ++s) {
-        long units = (long)n_units_i * s;
-        long waves = (units + sms - 1) / sms;
-        long tiles = (n_jtiles + s - 1) / s;
-        double cost = (double)waves * ((double)tiles * 1400.0 + 8000.0);
-        if (cost < best_cost * 0.98) { best_cost = cost; best = s; }
-    }
-    return best;
-}
-
 int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
     CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, ctx->stream));
-    if (ctx->phi_version == 2) {
-        const int64_t rows_a = ctx->n_pad128 + 256;
-        split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a,
-                                                                                  ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
-        KERNEL_CHECK();
-        make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d,
-                                                                                 ctx->VT2);
-        KERNEL_CHECK();
-        Phi2Args a{};
-        a.phi_buf = ctx->phi_buf;
-        a.XA2 = ctx->XA2;
-        a.UA = ctx->UA2;
-        a.WB = ctx->WB2;
-        a.row0 = ctx->row0;
-        a.n_rows = ctx->n_rows;
-        a.n_jtiles = (int)(ctx->n_pad128 / 128);
-        a.n_ipairs = (int)((ctx->n_rows + 255) / 256);
-        a.poly = ctx->phi_poly;
-        a.err = ctx->tc_err;
-        a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
-        const long long units = (long long)a.n_ipairs * a.n_jtiles;
-        const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units);
-        a.dbg = ctx->phi_dbg_mode;
-#define SVGDB_PHI2_CASE(P)                                                                                \
+    // operands: the bandwidth is folded into them, so the accumulator of the first contraction is the exponent
+    const int64_t rows_a = ctx->n_pad128 + 256;
+    split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a,
+                                                                              ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
+    KERNEL_CHECK();
+    make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
+    KERNEL_CHECK();
+    Phi2Args a{};
+    a.phi_buf = ctx->phi_buf;
+    a.XA2 = ctx->XA2;
+    a.UA = ctx->UA2;
+    a.WB = ctx->WB2;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.n_jtiles = (int)(ctx->n_pad128 / 128);
+    a.n_ipairs = (int)((ctx->n_rows + 255) / 256);
+    a.poly = ctx->phi_poly;
+    a.dbg = ctx->phi_dbg_mode;
+    a.err = ctx->tc_err;
+    a.trace = ctx->tc_trace;
+    const long long units = (long long)a.n_ipairs * a.n_jtiles;
+    const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units); // persistent: one CTA per SM
+    prof_mark(ctx, 5);
+#define SVGDB_PHI2_CASE(P) \
     case P: phi2_tc32_kernel<P><<<grid, P2_THREADS, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
-        prof_mark(ctx, 5);
-        switch (ctx->phi_poly) {
-            SVGDB_PHI2_CASE(0)
-            SVGDB_PHI2_CASE(2)
-            SVGDB_PHI2_CASE(4)
-            SVGDB_PHI2_CASE(6)
-            SVGDB_PHI2_CASE(8)
-        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
-        }
-#undef SVGDB_PHI2_CASE
-        KERNEL_CHECK();
-        prof_mark(ctx, 6);
-    } else {
-        TRY(launch_tc_split(ctx, SPLIT_PHI)); // the operands now carry the bandwidth: the accumulator is the exponent
-        make_vt_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->rt, ctx->a_dev, ctx->N, ctx->n_pad128,
-                                                                                ctx->d, ctx->VT);
-        KERNEL_CHECK();
-        PhiTcArgs a{};
-        a.phi_buf = ctx->phi_buf;
-        a.n_total = ctx->N;
-        a.row0 = ctx->row0;
-        a.n_rows = ctx->n_rows;
-        a.n_jtiles = (int)(ctx->n_pad128 / 128);
-        const int n_ipairs = (int)((ctx->n_rows + 255) / 256);
-        a.jsplit = pick_jsplit(n_ipairs, a.n_jtiles, ctx->sm_count);
-        a.err = ctx->tc_err;
-        a.trace = std::getenv("SVGDB_TC_TRACE_DIST") ? nullptr : ctx->tc_trace;
-        prof_mark(ctx, 5);
-        phi_tc32_kernel<<<(unsigned)(n_ipairs * a.jsplit), 320, TC_PHI_SMEM, ctx->stream>>>(ctx->mapA, ctx->mapB, ctx->mapV, a);
-        KERNEL_CHECK();
-        prof_mark(ctx, 6);
+    switch (ctx->phi_poly) {
+        SVGDB_PHI2_CASE(0)
+        SVGDB_PHI2_CASE(2)
+        SVGDB_PHI2_CASE(4)
+        SVGDB_PHI2_CASE(6)
+        SVGDB_PHI2_CASE(8)
+    default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
     }
+#undef SVGDB_PHI2_CASE
+    KERNEL_CHECK();
+    prof_mark(ctx, 6);
     ++ctx->stats.phi_launches;
     if (ctx->tc_trace) {
         std::vector<long long> h(3 * 64 * 8);
@@ -1041,7 +949,7 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
     // (persistent, GPU-filling) distance pass so that it overlaps the select kernels, which leave most of the GPU idle
     ctx->grad_pending = true; // kicked off behind the first distance pass (kick_grad), or below if there is none
 #ifdef SVGDB_WITH_TC32
-    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx, svgdb::tc::SPLIT_DIST));
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
@@ -1164,7 +1072,6 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     if (precision_mode == SVGDB_PRECISION_TC32) {
         if (d > svgdb::tc::TC_D)
             return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
-        CU(cudaFuncSetAttribute(svgdb::tc::phi_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_PHI_SMEM));
 #define SVGDB_PHI2_ATTR(P) \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2_SMEM));
         SVGDB_PHI2_ATTR(0)
@@ -1176,8 +1083,6 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
-        CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_HIST));
-        CU(cudaFuncSetAttribute(svgdb::tc::dist_tc32_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::TC_DIST_SMEM_BASE));
     }
 #endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
@@ -1450,7 +1355,7 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
     if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
     CU(cudaSetDevice(ctx->device));
 #ifdef SVGDB_WITH_TC32
-    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_tc_split(ctx, svgdb::tc::SPLIT_DIST));
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
@@ -1582,7 +1487,7 @@ int svgdb_time_kernel(svgdb_ctx *ctx, int which, int reps, int variant, double r
         if (ctx->n_hist < 1) return fail(ctx, SVGDB_ERR_UNSET, "svgdb_time_kernel: no median yet (run a step first)");
         const double m = ctx->med_hist[0];
         const uint64_t klo = key_of(std::max(m * (1.0 - rel_halfwidth), 0.0)), khi = key_of(m * (1.0 + rel_halfwidth)) + 1;
-        rc = launch_tc_split(ctx, svgdb::tc::SPLIT_DIST);
+        rc = launch_dist_operands(ctx);
         ctx->dist_dbg_mode = variant;
         if (rc == SVGDB_OK) rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0); // warm-up
         cudaEventRecord(e0, ctx->stream);
