@@ -838,16 +838,25 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     return SVGDB_OK;
 }
 
-int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi)
+// The particle-side operands of the pair kernel (they need X and the bandwidth, not V) and the zeroed accumulator.
+int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
-    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, ctx->stream));
-    // operands: the bandwidth is folded into them, so the accumulator of the first contraction is the exponent
+    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, stream));
+    // the bandwidth is folded into the operands, so the accumulator of the first contraction is the exponent
     const int64_t rows_a = ctx->n_pad128 + 256;
-    split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a,
-                                                                              ctx->n_pad128, ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
+    split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a, ctx->n_pad128,
+                                                                         ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
     KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
+int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false)
+{
+    using namespace svgdb::tc;
+    if (ctx->n_rows <= 0) return SVGDB_OK;
+    if (!x_operands_done) TRY(launch_phi_x_operands(ctx, ctx->stream));
     make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
     KERNEL_CHECK();
     Phi2Args a{};
@@ -957,15 +966,23 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
     TRY(kick_grad(ctx));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     prof_mark(ctx, 2);
-    TRY(launch_make_v(ctx));
-    prof_mark(ctx, 3);
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) {
-        TRY(launch_phi_tc32(ctx, debug_phi));
+        // the particle-side operands do not need V: they are built on the side stream while V is formed and all-gathered
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        TRY(launch_phi_x_operands(ctx, ctx->side_stream));
+        CU(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        TRY(launch_make_v(ctx));
+        prof_mark(ctx, 3);
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        TRY(launch_phi_tc32(ctx, debug_phi, true));
         prof_mark(ctx, 4);
         return SVGDB_OK;
     }
 #endif
+    TRY(launch_make_v(ctx));
+    prof_mark(ctx, 3);
     TRY(launch_phi(ctx, debug_phi));
     prof_mark(ctx, 4);
     return SVGDB_OK;
