@@ -109,23 +109,33 @@ __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__
     }
 }
 
-// V^T (fp16, [128][ldn]): rows [0,64) v_hi, [64,128) v_lo of v~ = V + 2 a mean (V = G - 2 a X, uncentred).
-// One block = 64 particles, transposed through shared memory.
+// v~ = g - 2 a (x - mean) for this rank's rows, rounded once to fp32 (24 bits: more than the two fp16 terms it is split
+// into keep); centred here, in FP64, so that a far-off particle cloud costs no precision.  V32 is indexed by global row:
+// it is what the ranks all-gather (half the bytes of the FP64 V of the other precision mode).
+__global__ void make_v32_kernel(const double *__restrict__ X, const double *__restrict__ G, const double *__restrict__ colsum,
+                                const double *__restrict__ a_ptr, int64_t n, int64_t row0, int64_t n_rows, int d, float *__restrict__ V32)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * d) return;
+    const int c = (int)(idx % d);
+    const double a = *a_ptr;
+    V32[row0 * d + idx] = (float)(G[idx] - 2.0 * a * (X[row0 * d + idx] - colsum[c] / (double)n));
+}
+
+// V^T (fp16, [128][ldn]): rows [0,64) v_hi, [64,128) v_lo of v~.  One block = 64 particles, transposed through shared memory.
 __global__ void __launch_bounds__(256)
-make_vt2_kernel(const double *__restrict__ V, const double *__restrict__ colsum, const double *__restrict__ a_ptr, int64_t n,
-                int64_t ldn, int d, __half *__restrict__ VT)
+make_vt2_kernel(const float *__restrict__ V32, int64_t n, int64_t ldn, int d, __half *__restrict__ VT)
 {
     __shared__ __half tile[128][64 + 2];
-    const double a = *a_ptr;
     const int64_t j0 = (int64_t)blockIdx.x * 64;
     for (int t = threadIdx.x; t < 64 * 64; t += blockDim.x) {
         const int jl = t >> 6, c = t & 63;
         const int64_t j = j0 + jl;
         __half hi = __float2half_rn(0.f), lo = hi;
         if (j < n && c < d) {
-            const double v = V[j * d + c] + 2.0 * a * (colsum[c] / (double)n);
-            hi = __double2half(v);
-            lo = __double2half(v - (double)__half2float(hi));
+            const float v = V32[j * d + c];
+            hi = __float2half_rn(v);
+            lo = __float2half_rn(v - __half2float(hi));
         }
         tile[c][jl] = hi;
         tile[64 + c][jl] = lo;

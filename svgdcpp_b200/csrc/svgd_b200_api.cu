@@ -142,6 +142,7 @@ struct svgdb_ctx {
     long long *tc_trace = nullptr; // SVGDB_TC_TRACE=<file>: timeline of CTA 0 of the pair-interaction kernel
     // persistent pair-interaction kernel (kernels_phi_tc.cuh): fp16 row / column operands, exponent offsets, V^T
     __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
+    float *V32 = nullptr; // v~ = g - 2 a (x - mean) in fp32, [n_pad][d]: what the ranks all-gather in this mode
     __half *UA2 = nullptr, *WB2 = nullptr; // exponent-offset K chunks (row / column side)
     CUtensorMap mapB2{}, mapV2{};
     __nv_bfloat16 *XBD = nullptr; // column operand [hi | lo] of the persistent distance pass (kernels_dist_tc.cuh)
@@ -251,6 +252,8 @@ int free_sharded(svgdb_ctx *ctx)
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
     cudaFree(ctx->XBD);
     ctx->XBD = nullptr;
+    cudaFree(ctx->V32);
+    ctx->V32 = nullptr;
     cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->UA2); cudaFree(ctx->WB2);
     ctx->XA2 = ctx->XB2 = ctx->VT2 = nullptr;
     ctx->UA2 = ctx->WB2 = nullptr;
@@ -310,6 +313,8 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->WB2, np / 128 * P2_W_BYTES));
     CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * P2_A_LD * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->UA2, 0, (np + 256) * 16 * 2, ctx->stream));
+    CU(cudaMalloc(&ctx->V32, (size_t)ctx->n_pad * ctx->d * sizeof(float)));
+    CU(cudaMemsetAsync(ctx->V32, 0, (size_t)ctx->n_pad * ctx->d * sizeof(float), ctx->stream));
     CU(cudaMalloc(&ctx->XBD, np * 128 * 2));
     TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
@@ -728,6 +733,21 @@ int launch_phi(svgdb_ctx *ctx, bool debug_phi)
 
 int launch_make_v(svgdb_ctx *ctx)
 {
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) { // centred, fp32: see make_v32_kernel
+        if (ctx->n_rows > 0) {
+            int64_t cnt = ctx->n_rows * ctx->d;
+            svgdb::tc::make_v32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->G, ctx->colsum, ctx->a_dev, ctx->N,
+                                                                                              ctx->row0, ctx->n_rows, ctx->d, ctx->V32);
+            KERNEL_CHECK();
+        }
+        if (ctx->world > 1) {
+            size_t chunk = (size_t)ctx->rows_per_rank * ctx->d;
+            NC(nccl().AllGather(ctx->V32 + (size_t)ctx->rank * chunk, ctx->V32, chunk, ncclFloat, ctx->comm, ctx->stream));
+        }
+        return SVGDB_OK;
+    }
+#endif
     if (ctx->n_rows > 0) {
         int64_t cnt = ctx->n_rows * ctx->d;
         make_v_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->G, ctx->a_dev, ctx->row0,
@@ -857,7 +877,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
     if (!x_operands_done) TRY(launch_phi_x_operands(ctx, ctx->stream));
-    make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V, ctx->colsum, ctx->a_dev, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
+    make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
     KERNEL_CHECK();
     Phi2Args a{};
     a.phi_buf = ctx->phi_buf;
