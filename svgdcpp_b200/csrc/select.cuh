@@ -16,11 +16,13 @@ constexpr int SELECT_MAX_BITS = 12;              // widest digit (tensor-core ke
 constexpr int SELECT_MAX_BINS = 1 << SELECT_MAX_BITS;
 
 struct SelectState {
-    unsigned long long prefix;    // bits of the answer decided so far
+    unsigned long long base;      // every candidate is selected on key - base (the bracket's lower end): a narrow bracket has few
+                                  // significant bits whatever power-of-two boundaries its raw bit patterns straddle
+    unsigned long long prefix;    // bits of the answer (as key - base) decided so far
     unsigned long long mask;      // which bits of `prefix` are decided
     unsigned long long rank;      // rank of the answer among the keys matching prefix/mask
     unsigned long long n_less;    // candidates strictly below every key matching prefix/mask
-    unsigned long long max_less;  // largest candidate < prefix once all bits are decided
+    unsigned long long max_less;  // largest candidate (as key - base) below the answer once all bits are decided
     unsigned long long need_scan; // the predecessor is not in the answer's last digit group: select_max_less_kernel must scan
     unsigned long long hist[SELECT_MAX_BINS];
 };
@@ -32,11 +34,11 @@ struct MedianResult {
     double scale;                      // a
 };
 
-__global__ void select_init_kernel(SelectState *st, unsigned long long prefix, unsigned long long mask,
+__global__ void select_init_kernel(SelectState *st, unsigned long long base, unsigned long long prefix, unsigned long long mask,
                                    unsigned long long rank)
 {
     for (int t = threadIdx.x; t < SELECT_MAX_BINS; t += blockDim.x) st->hist[t] = 0ull;
-    if (threadIdx.x == 0) { st->prefix = prefix; st->mask = mask; st->rank = rank; st->n_less = 0ull; st->max_less = 0ull; st->need_scan = 1ull; }
+    if (threadIdx.x == 0) { st->base = base; st->prefix = prefix; st->mask = mask; st->rank = rank; st->n_less = 0ull; st->max_less = 0ull; st->need_scan = 1ull; }
 }
 
 // histogram of the `bits`-wide digit at `shift` over the candidates that match the decided prefix
@@ -47,10 +49,10 @@ select_hist_kernel(const unsigned long long *__restrict__ cand, unsigned long lo
     const int nbins = 1 << bits;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0u;
     __syncthreads();
-    const unsigned long long prefix = st->prefix, mask = st->mask, dmask = (unsigned long long)(nbins - 1);
+    const unsigned long long base = st->base, prefix = st->prefix, mask = st->mask, dmask = (unsigned long long)(nbins - 1);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < m;
          t += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long key = cand[t];
+        unsigned long long key = cand[t] - base;
         if ((key & mask) == prefix) atomicAdd(&sh[(unsigned int)((key >> shift) & dmask)], 1u);
     }
     __syncthreads();
@@ -109,12 +111,12 @@ __global__ void __launch_bounds__(256)
 select_max_less_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, SelectState *st)
 {
     if (st->need_scan == 0ull) return;
-    const unsigned long long key_hi = st->prefix;
+    const unsigned long long base = st->base, key_hi = st->prefix;
     unsigned long long best = 0ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < m;
          t += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long key = cand[t];
-        if (key < key_hi && key > best) best = key;
+        unsigned long long key = cand[t] - base;
+        if (key < key_hi && key >= best) best = key; // (key - base may be 0: the atomicMax below still records it)
     }
     for (int o = 16; o; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
@@ -131,11 +133,11 @@ __global__ void median_finalize_kernel(const SelectState *st, unsigned long long
                                        double *a_out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long key_hi = direct ? direct_key : st->prefix;
+    unsigned long long key_hi = direct ? direct_key : st->base + st->prefix;
     unsigned long long key_lo = key_hi;
     if (even) {
         if (kk == 0ull) key_lo = *max_below_global;                 // predecessor lies below the bracket
-        else if (!direct && st->n_less == kk) key_lo = st->max_less; // predecessor is a smaller candidate
+        else if (!direct && st->n_less == kk) key_lo = st->base + st->max_less; // predecessor is a smaller candidate
         // otherwise the predecessor ties with key_hi
     }
     double d_lo = __longlong_as_double((long long)key_lo), d_hi = __longlong_as_double((long long)key_hi);

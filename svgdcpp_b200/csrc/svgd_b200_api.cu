@@ -474,15 +474,18 @@ int read_pass_results(svgdb_ctx *ctx, int mode, uint64_t *mid_total)
 int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n)
 {
     uint64_t m_local = std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
-    // bits above the highest differing bit of [lo, hi) are common to every candidate; keys of the tensor-core path are
-    // fp32 distances widened to double: their low 29 bits are zero and cannot change anything
-    const uint64_t diff = lo ^ (hi - 1);
-    int top = 64; // number of low bits that may differ
-    while (top > 0 && ((diff >> (top - 1)) & 1ull) == 0ull) --top;
+    // The candidates are selected on key - base, base = the bracket's lower end: its span, not the raw bit patterns, decides
+    // how many bits matter (a bracket of relative width 2e-4 spans ~2^11 fp32 values: one 12-bit pass).  Keys of the
+    // tensor-core path are fp32 distances widened to double: their low 29 bits are zero, and so are those of key - base
+    // once base is rounded down to a multiple of 2^29.
     const int bottom = ctx->precision == SVGDB_PRECISION_TC32 ? 29 : 0;
+    const uint64_t base = bottom ? (lo & ~((1ull << bottom) - 1ull)) : lo;
+    const uint64_t span = (hi - 1) - base;
+    int top = 0; // number of low bits of key - base that may be set
+    while (top < 64 && (span >> top) != 0ull) ++top;
     if (top < bottom + 1) top = bottom + 1;
     const uint64_t low_mask = top >= 64 ? ~0ull : ((1ull << top) - 1ull);
-    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, lo & ~low_mask, ~low_mask, kk);
+    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, base, 0ull, ~low_mask, kk);
     KERNEL_CHECK();
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m_local + 2047) / 2048, (uint64_t)ctx->sm_count * 8));
     // digits of up to SELECT_MAX_BITS bits from the top differing bit down to `bottom`
