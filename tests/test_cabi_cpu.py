@@ -95,3 +95,21 @@ def test_mini_eigen_prints_like_eigen(built_lib, tmp_path):
     expected = ("  2.04113    1.6986   2.46988 -0.988663  -1.33335 -0.135618 -0.811293   2.71338   0.81427  -2.15038\n"
                 "-0.633702   1.79064  -1.81469   1.60938   0.32382  0.773226 0.0804055   2.49717   1.30378  0.641813\n")
     assert out == expected
+
+
+def test_bracket_predictor_order_on_recorded_trajectory():
+    """The median bracket is predicted by cubic extrapolation of the last four medians (median_scale in svgd_b200_api.cu).
+    On the trajectory recorded at the bench shape the cubic predictor must beat the quadratic one by a clear margin in the Adam
+    transient and stay below the smallest bracket half-width (2e-5) in the stationary phase."""
+    import json
+    import os
+
+    import numpy as np
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "median_trajectory.json")
+    m = np.array(json.load(open(path))["med2"])
+    quad = np.abs(3 * m[2:-1] - 3 * m[1:-2] + m[:-3] - m[3:]) / m[3:]              # predicts m[k] from m[k-1..k-3]
+    cub = np.abs(4 * m[3:-1] - 6 * m[2:-2] + 4 * m[1:-3] - m[:-4] - m[4:]) / m[4:]   # ... from m[k-1..k-4]
+    transient_q, transient_c = np.median(quad[2:22]), np.median(cub[1:21])            # steps 5..25
+    assert transient_c < 0.3 * transient_q, (transient_q, transient_c)
+    assert np.median(cub[60:]) < 2e-5
