@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libsvgd_oracle.so")
 
 OPT_ADAGRAD, OPT_ADAM, OPT_RMSPROP = 0, 1, 2
-SCALE_MEDIAN, SCALE_FIXED = 0, 2
+SCALE_MEDIAN, SCALE_HESSIAN, SCALE_FIXED = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 
@@ -56,6 +56,9 @@ def lib():
         L.oracle_mvn_sum_logp_grad.argtypes = [_dp, C.c_long, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
         L.oracle_phi.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, _dp]
         L.oracle_phi.restype = None
+        L.oracle_rbf_hessian_scale.argtypes = [_dp, C.c_long, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
+        L.oracle_phi_matrix.argtypes = [_dp, _dp, C.c_long, C.c_int, _dp, _dp]
+        L.oracle_phi_matrix.restype = None
         L.oracle_opt_step.argtypes = [C.c_int, C.c_size_t, _dp, C.c_double, C.c_double, C.c_double,
                                       C.c_double, C.POINTER(C.c_uint64), _dp, _dp, _dp]
         L.oracle_opt_step.restype = None
@@ -115,6 +118,26 @@ def mvn_sum_logp_grad(X, means, covs, lse=False):
     if lib().oracle_mvn_sum_logp_grad(_p(X), n, d, Cn, _p(means), _p(covs), int(lse), _p(G)):
         raise ValueError("singular covariance")
     return G
+
+
+def rbf_hessian_scale(X, means, covs, lse=False):
+    """ScaleMethod::Hessian: A = 1/(2 d n) sum_i -Hessian(log p)(x_i), d x d."""
+    X = _f64(X)
+    n, d = X.shape
+    means, covs = _f64(np.atleast_2d(means)), _f64(np.asarray(covs).reshape(-1, d, d))
+    A = np.zeros((d, d))
+    rc = lib().oracle_rbf_hessian_scale(_p(X), n, d, means.shape[0], _p(means), _p(covs), int(lse), _p(A))
+    if rc:
+        raise RuntimeError("oracle_rbf_hessian_scale failed")
+    return A
+
+
+def phi_matrix(X, G, A):
+    X, G, A = _f64(X), _f64(G), _f64(A)
+    n, d = X.shape
+    out = np.empty_like(X)
+    lib().oracle_phi_matrix(_p(X), _p(G), n, d, _p(A), _p(out))
+    return out
 
 
 def phi(X, G, a):

@@ -224,6 +224,84 @@ void oracle_phi(const double *X, const double *G, long n, int d, double a, doubl
     }
 }
 
+int oracle_rbf_hessian_scale(const double *X, long n, int d, int C, const double *means, const double *covs, int lse,
+                             double *A)
+{
+    double *prec = (double *)malloc(sizeof(double) * (size_t)C * d * d);
+    double *y = (double *)malloc(sizeof(double) * (size_t)C * d);
+    double *h = (double *)malloc(sizeof(double) * (size_t)C);
+    double *ybar = (double *)malloc(sizeof(double) * (size_t)d);
+    if (!prec || !y || !h || !ybar) { free(prec); free(y); free(h); free(ybar); return -1; }
+    for (int c = 0; c < C; ++c)
+        if (oracle_lu_inverse(covs + (size_t)c * d * d, d, prec + (size_t)c * d * d)) { free(prec); free(y); free(h); free(ybar); return -1; }
+    for (size_t t = 0; t < (size_t)d * d; ++t) A[t] = 0.0;
+    for (long i = 0; i < n; ++i) { /* GaussianRBFKernel.hpp:203-206: hessian_sum += -EvaluateLogModelHessian(x_i) */
+        const double *x = X + i * d;
+        for (int c = 0; c < C; ++c) {
+            const double *P = prec + (size_t)c * d * d, *mu = means + (size_t)c * d;
+            double q = 0.0;
+            for (int r = 0; r < d; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < d; ++k) s += P[r * d + k] * (x[k] - mu[k]);
+                y[c * d + r] = s;
+                q += (x[r] - mu[r]) * s;
+            }
+            h[c] = -0.5 * q;
+        }
+        double shift = 0.0, tot = 0.0;
+        if (lse) { shift = h[0]; for (int c = 1; c < C; ++c) if (h[c] > shift) shift = h[c]; }
+        for (int c = 0; c < C; ++c) { h[c] = exp(h[c] - shift); tot += h[c]; }
+        for (int r = 0; r < d; ++r) {
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += (h[c] / tot) * y[c * d + r];
+            ybar[r] = s;
+        }
+        for (int r = 0; r < d; ++r)
+            for (int k = 0; k < d; ++k) {
+                double s = ybar[r] * ybar[k];
+                for (int c = 0; c < C; ++c) {
+                    /* the symmetric part of P_c is what a Hessian sees */
+                    const double *P = prec + (size_t)c * d * d;
+                    s += (h[c] / tot) * (0.5 * (P[r * d + k] + P[k * d + r]) - y[c * d + r] * y[c * d + k]);
+                }
+                A[r * d + k] += s;
+            }
+    }
+    for (size_t t = 0; t < (size_t)d * d; ++t) A[t] *= 1.0 / (2.0 * (double)d * (double)n); /* :208 */
+    free(prec); free(y); free(h); free(ybar);
+    return 0;
+}
+
+void oracle_phi_matrix(const double *X, const double *G, long n, int d, const double *A, double *phi)
+{
+#pragma omp parallel
+    {
+        double *acc = (double *)malloc(sizeof(double) * d);
+        double *df = (double *)malloc(sizeof(double) * d);
+        double *Ad = (double *)malloc(sizeof(double) * d);
+#pragma omp for schedule(static)
+        for (long i = 0; i < n; ++i) {
+            const double *xi = X + i * d;
+            for (int k = 0; k < d; ++k) acc[k] = 0.0;
+            for (long j = 0; j < n; ++j) {
+                const double *xj = X + j * d;
+                double q = 0.0;
+                for (int k = 0; k < d; ++k) df[k] = xj[k] - xi[k];
+                for (int r = 0; r < d; ++r) { /* (A + A^T) diff, and diff^T A diff */
+                    double s = 0.0, st = 0.0;
+                    for (int k = 0; k < d; ++k) { s += A[r * d + k] * df[k]; st += A[k * d + r] * df[k]; }
+                    Ad[r] = s + st;
+                    q += df[r] * s;
+                }
+                double kv = exp(-q);
+                for (int k = 0; k < d; ++k) acc[k] += G[j * d + k] * kv - Ad[k] * kv;
+            }
+            for (int k = 0; k < d; ++k) phi[i * d + k] = (1.0 / (double)n) * acc[k];
+        }
+        free(acc); free(df); free(Ad);
+    }
+}
+
 void oracle_opt_step(int kind, size_t count, const double *phi, double lr, double beta1,
                      double beta2, double eps, uint64_t *counter, double *s1, double *s2,
                      double *delta)
@@ -275,20 +353,28 @@ int oracle_svgd_run(const oracle_config *cfg, double *X, double *a_trace, double
     double *work = cfg->scale_method == ORACLE_SCALE_MEDIAN ? (double *)malloc(sizeof(double) * (size_t)n * n) : NULL;
     uint64_t counter = 0;
     int rc = 0;
+    double *Amat = NULL;
     if (!G || !phi || !delta || !s1 || !s2) rc = -1;
     for (int it = 0; it < cfg->iters && !rc; ++it) {
         /* SVGD::Step: kernel Step (bandwidth from the CURRENT X) happens before ComputePhi, SVGD.hpp:378-393 */
         double a = cfg->scale_method == ORACLE_SCALE_MEDIAN ? oracle_rbf_median_scale(X, n, d, work) : cfg->fixed_a;
+        if (cfg->scale_method == ORACLE_SCALE_HESSIAN) {
+            if (!Amat) Amat = (double *)malloc(sizeof(double) * (size_t)d * d);
+            rc = Amat ? oracle_rbf_hessian_scale(X, n, d, cfg->n_components, cfg->means, cfg->covs, cfg->lse, Amat) : -1;
+            if (rc) break;
+            a = Amat[0];
+        }
         if (a_trace) a_trace[it] = a;
         rc = oracle_mvn_sum_logp_grad(X, n, d, cfg->n_components, cfg->means, cfg->covs, cfg->lse, G);
         if (rc) break;
-        oracle_phi(X, G, n, d, a, phi);
+        if (cfg->scale_method == ORACLE_SCALE_HESSIAN) oracle_phi_matrix(X, G, n, d, Amat, phi);
+        else oracle_phi(X, G, n, d, a, phi);
         oracle_opt_step(cfg->opt_kind, cnt, phi, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, &counter, s1, s2, delta);
         for (size_t t = 0; t < cnt; ++t) X[t] += delta[t];
         if (cfg->lb && cfg->ub) oracle_clamp(X, n, d, cfg->lb, cfg->ub);
     }
     if (phi_last && !rc) memcpy(phi_last, phi, sizeof(double) * cnt);
-    free(G); free(phi); free(delta); free(s1); free(s2); free(work);
+    free(G); free(phi); free(delta); free(s1); free(s2); free(work); free(Amat);
     return rc;
 }
 

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 enum { ORACLE_OPT_ADAGRAD = 0, ORACLE_OPT_ADAM = 1, ORACLE_OPT_RMSPROP = 2 };
-enum { ORACLE_SCALE_MEDIAN = 0, ORACLE_SCALE_FIXED = 2 };
+enum { ORACLE_SCALE_MEDIAN = 0, ORACLE_SCALE_HESSIAN = 1, ORACLE_SCALE_FIXED = 2 };
 
 /* Eigen::MatrixXd::Random(rows, cols) * scale with the unseeded glibc rand() the
  * reference examples rely on (examples/multivariate_normal/mvn_example.cpp:23). */
@@ -57,6 +57,19 @@ int oracle_mvn_sum_logp_grad(const double *X, long n, int d, int C, const double
  * (Kernel/GaussianRBFKernel.hpp:75-81) and grad_{x_j} k = -2 a (x_j - x_i) k. */
 void oracle_phi(const double *X, const double *G, long n, int d, double a, double *phi);
 
+/* GaussianRBFKernel::ComputeScale, ScaleMethod::Hessian (Kernel/GaussianRBFKernel.hpp:189-210):
+ * A = 1/(2 d n) sum_i -Hessian(log p)(x_i), a full d x d matrix.  The reference tapes the Hessian with CppAD
+ * (Model.hpp:366-370); for the sum of Gaussians it is, in closed form, with y_c = P_c (x - mu_c) and softmax weights w_c,
+ *   -Hessian(log p) = sum_c w_c P_c - sum_c w_c y_c y_c^T + ybar ybar^T,  ybar = sum_c w_c y_c.
+ * Parity of this branch is NOT pinned by any reference output: the closed form is checked against
+ * finite differences of oracle_mvn_sum_logp_grad in tests/test_oracle_golden.py. */
+int oracle_rbf_hessian_scale(const double *X, long n, int d, int C, const double *means, const double *covs, int lse,
+                             double *A);
+
+/* SVGD::ComputePhi with a matrix-valued kernel scale: k(x, x') = exp(-(x - x')^T A (x - x')),
+ * grad_x k = -(A + A^T)(x - x') k  (Kernel/GaussianRBFKernel.hpp:75-81 taped by CppAD). */
+void oracle_phi_matrix(const double *X, const double *G, long n, int d, const double *A, double *phi);
+
 /* Optimizer increments (the driver ADDS the result, SVGD.hpp:393).
  * Optimizer/Adam.hpp:75-96, AdaGrad.hpp:60-65, RMSProp.hpp:69-74.
  * state1 = sum of squares / 2nd moment, state2 = 1st moment (Adam only). */
@@ -75,7 +88,7 @@ typedef struct {
     const double *means;    /* C x d */
     const double *covs;     /* C x d x d */
     int lse;                /* evaluate mixture gradient through log-sum-exp */
-    int scale_method;       /* ORACLE_SCALE_MEDIAN | ORACLE_SCALE_FIXED */
+    int scale_method;       /* ORACLE_SCALE_MEDIAN | ORACLE_SCALE_HESSIAN | ORACLE_SCALE_FIXED */
     double fixed_a;
     int opt_kind;
     double lr, beta1, beta2, eps;

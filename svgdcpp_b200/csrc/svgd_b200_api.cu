@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "kernels_f64.cuh"
+#include "kernels_hessian.cuh"
 #include "select.cuh"
 #ifdef SVGDB_WITH_TC32
 #include "kernels_tc32.cuh"
@@ -107,10 +108,15 @@ struct svgdb_ctx {
     svgdb_grad_fn hook = nullptr;
     void *hook_user = nullptr;
 
+    std::vector<double> prec_host, means_host; // host copies of the model parameters (Hessian scale)
+
     // kernel
     bool kernel_set = false;
     int scale_method = SVGDB_SCALE_MEDIAN;
     double fixed_a = 0.0;
+    // ScaleMethod::Hessian (kernels_hessian.cuh): scale matrix A = R^T R, transformed particles / gradients
+    std::vector<double> A_host;
+    double *Hsum_dev = nullptr, *Wsum_dev = nullptr, *R_dev = nullptr, *Rinv_dev = nullptr, *Y_dev = nullptr, *GH_dev = nullptr;
 
     // optimizer
     bool opt_set = false;
@@ -658,7 +664,7 @@ int compute_scale_dev(svgdb_ctx *ctx)
         ctx->stats.last_scale = ctx->fixed_a;
         return SVGDB_OK;
     }
-    return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is not implemented on the device path yet");
+    return fail(ctx, SVGDB_ERR_INVALID, "internal: the Hessian scale is computed by hessian_scale_dev");
 }
 
 int launch_grad(svgdb_ctx *ctx, cudaStream_t stream)
@@ -973,9 +979,153 @@ void prof_mark(svgdb_ctx *ctx, int i)
     if (ctx->profiling) cudaEventRecord(ctx->ev[i], ctx->stream);
 }
 
+// ---- ScaleMethod::Hessian (kernels_hessian.cuh) -----------------------------------------------------------------------
+// Cholesky A = R^T R with R upper triangular; returns false if A is not positive definite.  Rinv = R^-1.
+bool cholesky_upper(const std::vector<double> &A, int d, std::vector<double> &R, std::vector<double> &Rinv)
+{
+    R.assign((size_t)d * d, 0.0);
+    for (int j = 0; j < d; ++j) {
+        double s = A[(size_t)j * d + j];
+        for (int k = 0; k < j; ++k) s -= R[(size_t)k * d + j] * R[(size_t)k * d + j];
+        if (!(s > 0.0) || !std::isfinite(s)) return false;
+        const double rjj = std::sqrt(s);
+        R[(size_t)j * d + j] = rjj;
+        for (int c = j + 1; c < d; ++c) {
+            double t = A[(size_t)j * d + c];
+            for (int k = 0; k < j; ++k) t -= R[(size_t)k * d + j] * R[(size_t)k * d + c];
+            R[(size_t)j * d + c] = t / rjj;
+        }
+    }
+    Rinv.assign((size_t)d * d, 0.0); // back substitution, column by column: R Rinv = I
+    for (int c = 0; c < d; ++c)
+        for (int r = c; r >= 0; --r) {
+            double t = (r == c) ? 1.0 : 0.0;
+            for (int k = r + 1; k <= c; ++k) t -= R[(size_t)r * d + k] * Rinv[(size_t)k * d + c];
+            Rinv[(size_t)r * d + c] = t / R[(size_t)r * d + r];
+        }
+    return true;
+}
+
+// A = 1/(2 d n) sum_i -Hessian(log p)(x_i) on the host (GaussianRBFKernel.hpp:189-210), its factor R and R^-1 on the device.
+int hessian_scale_dev(svgdb_ctx *ctx)
+{
+    if (ctx->model_kind != MODEL_MVN_SUM)
+        return fail(ctx, SVGDB_ERR_UNSET, "ScaleMethod::Hessian needs a model with a device Hessian (MultivariateNormal or a sum of them)");
+    const int d = ctx->d, C = ctx->C;
+    const size_t dd = (size_t)d * d;
+    if (!ctx->Hsum_dev) {
+        CU(cudaMalloc(&ctx->Hsum_dev, dd * sizeof(double)));
+        CU(cudaMalloc(&ctx->Wsum_dev, (size_t)std::max(C, 1) * sizeof(double)));
+        CU(cudaMalloc(&ctx->R_dev, dd * sizeof(double)));
+        CU(cudaMalloc(&ctx->Rinv_dev, dd * sizeof(double)));
+        CU(cudaMalloc(&ctx->Y_dev, (size_t)ctx->n_pad * d * sizeof(double)));
+        CU(cudaMalloc(&ctx->GH_dev, (size_t)ctx->rows_per_rank * d * sizeof(double)));
+        CU(cudaMemsetAsync(ctx->Y_dev, 0, (size_t)ctx->n_pad * d * sizeof(double), ctx->stream));
+    }
+    CU(cudaMemsetAsync(ctx->Hsum_dev, 0, dd * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->Wsum_dev, 0, (size_t)C * sizeof(double), ctx->stream));
+    if (ctx->n_rows > 0) {
+        const int tiles = (d + 63) / 64;
+        const size_t smem = ((size_t)(C + 1) * d + 2 * (size_t)C) * sizeof(double);
+        if (smem > 200 * 1024) return fail(ctx, SVGDB_ERR_DIMENSION, "ScaleMethod::Hessian: components x dimension too large for the Hessian kernel");
+        CU(cudaFuncSetAttribute(mvn_sum_hessian_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)std::min<int64_t>(ctx->n_rows, (int64_t)ctx->sm_count * 8), (unsigned)(tiles * tiles));
+        mvn_sum_hessian_f64_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->X[ctx->cur], d, ctx->row0, ctx->n_rows, C, ctx->means_dev, ctx->prec_dev,
+                                                                       tiles, ctx->Hsum_dev, ctx->Wsum_dev);
+        KERNEL_CHECK();
+    }
+    if (ctx->world > 1) {
+        NC(nccl().AllReduce(ctx->Hsum_dev, ctx->Hsum_dev, dd, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        NC(nccl().AllReduce(ctx->Wsum_dev, ctx->Wsum_dev, (size_t)C, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    }
+    std::vector<double> H(dd), W((size_t)C), R, Rinv;
+    CU(cudaMemcpyAsync(H.data(), ctx->Hsum_dev, dd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(W.data(), ctx->Wsum_dev, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->A_host.assign(dd, 0.0);
+    const double scale = 1.0 / (2.0 * (double)d * (double)ctx->N);
+    for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c) {
+            double s = 0.5 * (H[(size_t)r * d + c] + H[(size_t)c * d + r]);
+            for (int k = 0; k < C; ++k) s += W[(size_t)k] * ctx->prec_host[((size_t)k * d + r) * d + c]; // prec_host is symmetrised
+            ctx->A_host[(size_t)r * d + c] = s * scale;
+        }
+    if (!cholesky_upper(ctx->A_host, d, R, Rinv))
+        return fail(ctx, SVGDB_ERR_NUMERIC, "ScaleMethod::Hessian: the scale matrix (mean negative Hessian of log p over the particles) is not positive definite");
+    CU(cudaMemcpyAsync(ctx->R_dev, R.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->Rinv_dev, Rinv.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // R, Rinv are locals
+    ctx->stats.last_scale = ctx->A_host[0];
+    return SVGDB_OK;
+}
+
+int launch_phi(svgdb_ctx *ctx, bool debug_phi);
+int launch_make_v(svgdb_ctx *ctx);
+
+// One Hessian-scaled phi (and update): the scalar-bandwidth pair kernel with a = 1 on y = R x, g^ = R^-T g, then phi = R^T phi^.
+int prepare_and_phi_hessian(svgdb_ctx *ctx, bool debug_phi)
+{
+    const int d = ctx->d;
+    prof_mark(ctx, 0);
+    TRY(hessian_scale_dev(ctx));
+    prof_mark(ctx, 1);
+    TRY(launch_grad(ctx, ctx->stream));
+    prof_mark(ctx, 2);
+    // Y = X R^T (all rows: every rank holds X), G^ = G R^-1 (local rows).  Row-vector form: y_i = x_i R^T, g^_i = g_i R^-1.
+    std::vector<double> Rt((size_t)d * d);
+    {   // R^T on the device: reuse Hsum_dev as scratch for the transposed factor
+        std::vector<double> R((size_t)d * d);
+        CU(cudaMemcpyAsync(R.data(), ctx->R_dev, R.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c) Rt[(size_t)r * d + c] = R[(size_t)c * d + r];
+        CU(cudaMemcpyAsync(ctx->Hsum_dev, Rt.data(), Rt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        const int64_t cnt = ctx->N * d;
+        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->Hsum_dev, ctx->N, d, ctx->Y_dev);
+        KERNEL_CHECK();
+    }
+    if (ctx->n_rows > 0) {
+        const int64_t cnt = ctx->n_rows * d;
+        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->G, ctx->Rinv_dev, ctx->n_rows, d, ctx->GH_dev);
+        KERNEL_CHECK();
+    }
+    // the scalar-bandwidth machinery on the transformed quantities, a = 1, writing phi^ for the local rows into phi_dbg
+    const double one = 1.0;
+    CU(cudaMemcpyAsync(ctx->a_dev, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double *X_keep = ctx->X[ctx->cur], *G_keep = ctx->G;
+    ctx->X[ctx->cur] = ctx->Y_dev;
+    ctx->G = ctx->GH_dev;
+    int rc = launch_rownorm(ctx);
+    if (rc == SVGDB_OK) rc = launch_make_v(ctx);
+    prof_mark(ctx, 3);
+    if (rc == SVGDB_OK) rc = launch_phi(ctx, true);
+    ctx->X[ctx->cur] = X_keep;
+    ctx->G = G_keep;
+    TRY(rc);
+    // phi = phi^ R (rows), through GH_dev as scratch, back into phi_dbg
+    if (ctx->n_rows > 0) {
+        const int64_t cnt = ctx->n_rows * d;
+        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->phi_dbg, ctx->R_dev, ctx->n_rows, d, ctx->GH_dev);
+        KERNEL_CHECK();
+        CU(cudaMemcpyAsync(ctx->phi_dbg, ctx->GH_dev, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (!debug_phi) {
+            opt_apply_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->phi_dbg, ctx->row0, ctx->n_rows, d, ctx->opt,
+                                                                                      ctx->s1, ctx->s2, ctx->lb, ctx->ub, ctx->X[ctx->cur ^ 1]);
+            KERNEL_CHECK();
+        }
+    }
+    ++ctx->stats.phi_launches;
+    prof_mark(ctx, 4);
+    return SVGDB_OK;
+}
+
 // phi (and everything it needs) for the current X; leaves V, r, a on the device
 int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
 {
+    if (ctx->scale_method == SVGDB_SCALE_HESSIAN) return prepare_and_phi_hessian(ctx, debug_phi);
     prof_mark(ctx, 0);
     // grad log p only needs X: it runs on the side stream next to the bandwidth computation, enqueued right behind the
     // (persistent, GPU-filling) distance pass so that it overlaps the select kernels, which leave most of the GPU idle
@@ -1153,6 +1303,7 @@ void svgdb_destroy(svgdb_ctx *ctx)
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     free_sharded(ctx);
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
+    cudaFree(ctx->Hsum_dev); cudaFree(ctx->Wsum_dev); cudaFree(ctx->R_dev); cudaFree(ctx->Rinv_dev); cudaFree(ctx->Y_dev); cudaFree(ctx->GH_dev);
     cudaFree(ctx->pass_words); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
     cudaFree(ctx->sel); cudaFree(ctx->medres);
     if (ctx->hs) cudaFreeHost(ctx->hs);
@@ -1273,6 +1424,8 @@ int svgdb_set_model_mvn_sum(svgdb_ctx *ctx, int32_t C, const double *means, cons
     CU(cudaStreamSynchronize(ctx->stream)); // prec is a local
     ctx->C = C;
     ctx->model_kind = MODEL_MVN_SUM;
+    ctx->prec_host = prec;
+    ctx->means_host.assign(means, means + (size_t)C * d);
     return SVGDB_OK;
 }
 
@@ -1296,8 +1449,8 @@ int svgdb_set_kernel_rbf(svgdb_ctx *ctx, int scale_method, double fixed_a)
     if (!ctx) return SVGDB_ERR_INVALID;
     if (scale_method != SVGDB_SCALE_MEDIAN && scale_method != SVGDB_SCALE_FIXED && scale_method != SVGDB_SCALE_HESSIAN)
         return fail(ctx, SVGDB_ERR_INVALID, "[Argument error] Invalid scale method Enum provided.");
-    if (scale_method == SVGDB_SCALE_HESSIAN)
-        return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is not implemented on the device path yet");
+    if (scale_method == SVGDB_SCALE_HESSIAN && ctx->precision != SVGDB_PRECISION_F64)
+        return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is available in SVGDB_PRECISION_F64 only");
     if (scale_method == SVGDB_SCALE_FIXED && !(fixed_a > 0.0) ) return fail(ctx, SVGDB_ERR_INVALID, "fixed kernel scale must be positive");
     ctx->scale_method = scale_method;
     ctx->fixed_a = fixed_a;
@@ -1397,12 +1550,32 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
 #endif
+    if (ctx->scale_method == SVGDB_SCALE_HESSIAN) { // matrix-valued: A(0,0) here, the whole matrix through svgdb_get_scale_matrix
+        TRY(hessian_scale_dev(ctx));
+        if (scale_out) *scale_out = ctx->A_host[0];
+        return SVGDB_OK;
+    }
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     double a = 0.0;
     CU(cudaMemcpyAsync(&a, ctx->a_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (scale_out) *scale_out = a;
+    return SVGDB_OK;
+}
+
+int svgdb_get_scale_matrix(svgdb_ctx *ctx, double *A_dxd)
+{
+    if (!ctx || !A_dxd) return SVGDB_ERR_INVALID;
+    if (ctx->scale_method != SVGDB_SCALE_HESSIAN) {
+        TRY(finish_median(ctx));
+        const double a = ctx->scale_method == SVGDB_SCALE_FIXED ? ctx->fixed_a : ctx->stats.last_scale;
+        for (int r = 0; r < ctx->d; ++r)
+            for (int c = 0; c < ctx->d; ++c) A_dxd[(size_t)r * ctx->d + c] = r == c ? a : 0.0;
+        return SVGDB_OK;
+    }
+    if (ctx->A_host.size() != (size_t)ctx->d * ctx->d) return fail(ctx, SVGDB_ERR_UNSET, "the kernel scale has not been computed yet");
+    std::copy(ctx->A_host.begin(), ctx->A_host.end(), A_dxd);
     return SVGDB_OK;
 }
 

@@ -326,6 +326,12 @@ class SVGD:
         self._check(self._lib.svgdb_compute_phi(self._ctx, _ptr(phi), C.byref(a)))
         return phi.T.copy(), a.value
 
+    def GetScaleMatrix(self):
+        """The kernel's inverse scale matrix (GaussianRBFKernel::GetParameters()[0]) of the last Step / Compute call."""
+        A = np.zeros((self.dimension_, self.dimension_))
+        self._check(self._lib.svgdb_get_scale_matrix(self._ctx, _ptr(A)))
+        return A
+
     def ComputeScale(self):
         self._upload()
         a = C.c_double(0.0)

@@ -85,6 +85,53 @@ def main():
             ok = e_a < tol[0] and e_phi < tol[1] and e_x < tol[2] and cnt.value == iters and np.all(np.isfinite(s1))
             print("world=%d %s n=%d d=%d: a err %.2e, phi err %.2e, trajectory rms err %.2e -> %s" % (world, args.precision, n, d, e_a, e_phi, e_x, "OK" if ok else "FAIL"), flush=True)
             failures += 0 if ok else 1
+    if prec == _capi.PRECISION_F64:  # ScaleMethod::Hessian: per-rank Hessian partial sums, one all-reduce
+        n, d, iters = 700, 12, 4
+        rng = np.random.default_rng(7)
+        A = rng.standard_normal((d, d))
+        cov = np.ascontiguousarray(A @ A.T / d + 0.5 * np.eye(d))
+        mu = np.ascontiguousarray(rng.standard_normal(d))
+        X0 = np.ascontiguousarray(2.0 * rng.standard_normal((n, d)))
+        ctx = C.c_void_p()
+
+        def check(rc):
+            if rc != 0:
+                raise RuntimeError(lib.svgdb_last_error(ctx).decode())
+
+        check(lib.svgdb_create(C.byref(ctx), local, n, d, prec))
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            assert lib.svgdb_nccl_unique_id(uid.ctypes.data_as(C.c_void_p), 128) == 0
+        t = torch.from_numpy(uid).cuda()
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
+        check(lib.svgdb_comm_init(ctx, world, rank, uid.ctypes.data_as(C.c_void_p), 128))
+        check(lib.svgdb_set_model_mvn(ctx, mu.ctypes.data_as(dp), cov.ctypes.data_as(dp)))
+        check(lib.svgdb_set_kernel_rbf(ctx, _capi.SCALE_HESSIAN, 0.0))
+        check(lib.svgdb_set_optimizer(ctx, _capi.OPT_ADAM, 0.1, 0.9, 0.999, 1e-8))
+        check(lib.svgdb_set_particles(ctx, X0.ctypes.data_as(dp)))
+        check(lib.svgdb_initialize(ctx))
+        phi = np.empty_like(X0)
+        a = C.c_double(0.0)
+        check(lib.svgdb_compute_phi(ctx, phi.ctypes.data_as(dp), C.byref(a)))
+        Amat = np.empty((d, d))
+        check(lib.svgdb_get_scale_matrix(ctx, Amat.ctypes.data_as(dp)))
+        check(lib.svgdb_step(ctx, iters))
+        X = np.empty_like(X0)
+        check(lib.svgdb_get_particles(ctx, X.ctypes.data_as(dp)))
+        lib.svgdb_destroy(ctx)
+        if rank == 0:
+            import oracle_binding as oracle
+
+            A_ref = oracle.rbf_hessian_scale(X0, mu[None], cov[None])
+            phi_ref = oracle.phi_matrix(X0, oracle.mvn_sum_logp_grad(X0, mu[None], cov[None]), A_ref)
+            X_ref = oracle.svgd_run(X0, iters, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1, scale_method=oracle.SCALE_HESSIAN)
+            e_a = np.max(np.abs(Amat - A_ref)) / np.max(np.abs(A_ref))
+            e_phi = np.max(np.abs(phi - phi_ref)) / np.max(np.abs(phi_ref))
+            e_x = np.sqrt(np.mean((X - X_ref) ** 2)) / np.sqrt(np.mean(X_ref ** 2))
+            ok = e_a < 1e-12 and e_phi < 1e-11 and e_x < 1e-9
+            print("world=%d f64 Hessian scale n=%d d=%d: A err %.2e, phi err %.2e, trajectory rms err %.2e -> %s" % (world, n, d, e_a, e_phi, e_x, "OK" if ok else "FAIL"), flush=True)
+            failures += 0 if ok else 1
     f = torch.tensor([failures], device="cuda")
     dist.broadcast(f, 0)
     dist.destroy_process_group()

@@ -237,6 +237,48 @@ def test_config4_slice(sv, oracle):
     assert _rel(x0.T, ref) < FINAL_RTOL
 
 
+def test_hessian_scale(sv, oracle):
+    """ScaleMethod::Hessian (GaussianRBFKernel.hpp:189-210; SURVEY.md 8f rank 1): scale matrix, phi and a short trajectory against
+    the oracle, for one Gaussian (A = Sigma^-1 / (2 d)) and for a sum of two well-overlapping Gaussians.  The device path runs
+    the scalar-bandwidth pair kernel on y = R x (A = R^T R), so the scale matrix must be positive definite."""
+    rng = np.random.default_rng(5)
+    for n, d, C in [(300, 8, 1), (257, 6, 2), (200, 64, 1)]:
+        means = 0.4 * rng.standard_normal((C, d))
+        covs = np.stack([(lambda M: M @ M.T / d + 0.7 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(C)])
+        x0 = np.asfortranarray(1.2 * rng.standard_normal((d, n)))
+        X0 = np.array(x0.T, order="C", copy=True)
+        model = None
+        for k in range(C):
+            m = sv.MultivariateNormal(means[k], covs[k])
+            model = m if model is None else model + m
+        svgd = sv.SVGD(d, 6, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Hessian, model), model, sv.Adam(d, n, 0.05, 0.9, 0.999))
+        phi, _ = svgd.ComputePhi()
+        A = svgd.GetScaleMatrix()
+        A_ref = oracle.rbf_hessian_scale(X0, means, covs, lse=True)
+        phi_ref = oracle.phi_matrix(X0, oracle.mvn_sum_logp_grad(X0, means, covs, lse=True), A_ref)
+        print("hessian scale n=%d d=%d C=%d: A rel err %.3g, phi rel err %.3g" % (n, d, C, _rel(A, A_ref), _rel(phi.T, phi_ref)))
+        assert _rel(A, A_ref) < 1e-12
+        assert _rel(phi.T, phi_ref) < 1e-10
+        svgd.Initialize()
+        svgd.Run()
+        svgd.close()
+        ref = oracle.svgd_run(X0, 6, means, covs, opt_kind=oracle.OPT_ADAM, lr=0.05, scale_method=oracle.SCALE_HESSIAN, lse=True)
+        assert _rel(x0.T, ref) < FINAL_RTOL
+
+
+def test_hessian_scale_rejects_indefinite_matrix(sv):
+    """Far-apart components make the mean negative Hessian indefinite: the device path reports it instead of running a kernel that
+    is not positive definite (the reference would go on with exp(-d^T A d) > 1)."""
+    d, n = 2, 64
+    rng = np.random.default_rng(9)
+    x0 = np.asfortranarray(0.3 * rng.standard_normal((d, n)))
+    model = sv.MultivariateNormal([4.0, 0.0], 0.5 * np.eye(d)) + sv.MultivariateNormal([-4.0, 0.0], 0.5 * np.eye(d))
+    svgd = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Hessian, model), model, sv.AdaGrad(d, n, 0.1))
+    with pytest.raises(RuntimeError, match="not positive definite"):
+        svgd.ComputePhi()
+    svgd.close()
+
+
 def test_mixture_gradient_log_sum_exp(sv, oracle):
     """16-D, 5-component sum of Gaussians incl. far-away components (config-4 style)."""
     from svgdcpp_b200 import synth

@@ -140,3 +140,25 @@ def test_reference_svgd_test_scenario_known_answer(oracle):
         X = np.maximum(np.minimum(X, 1.0), -1.0)  # min-then-max clamp of SVGD.hpp:396-399
     assert np.max(np.abs(X[:, 0] - helpers.COS_KAT_ROW0)) < 5e-12
     assert np.max(np.abs(X[:, 1] - helpers.COS_KAT_ROW1)) < 5e-12
+
+
+def test_hessian_scale_closed_form_matches_finite_differences(oracle):
+    """ScaleMethod::Hessian (GaussianRBFKernel.hpp:189-210) is not pinned by any reference output; the oracle's closed-form
+    Hessian of log p for sums of Gaussians is checked against central differences of its own gradient, the single-Gaussian
+    case against A = Sigma^-1 / (2 d), and the matrix-scale phi against the scalar one for A = a I."""
+    rng = np.random.default_rng(11)
+    d, n, C = 5, 40, 3
+    means = rng.standard_normal((C, d)) * 1.5
+    covs = np.stack([(lambda M: M @ M.T / d + 0.5 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(C)])
+    X = rng.standard_normal((n, d)) * 1.5
+    A = oracle.rbf_hessian_scale(X, means, covs, lse=True)
+    H, eps = np.zeros((d, d)), 1e-5
+    for k in range(d):
+        Xp, Xm = X.copy(), X.copy()
+        Xp[:, k] += eps
+        Xm[:, k] -= eps
+        H[:, k] = -((oracle.mvn_sum_logp_grad(Xp, means, covs, lse=True) - oracle.mvn_sum_logp_grad(Xm, means, covs, lse=True)) / (2 * eps)).sum(0)
+    assert np.max(np.abs(A - H / (2 * d * n))) < 1e-8 * np.max(np.abs(A))
+    assert np.max(np.abs(oracle.rbf_hessian_scale(X, means[:1], covs[:1]) - np.linalg.inv(covs[0]) / (2 * d))) < 1e-14
+    G = oracle.mvn_sum_logp_grad(X, means, covs, lse=True)
+    assert np.max(np.abs(oracle.phi_matrix(X, G, 0.37 * np.eye(d)) - oracle.phi(X, G, 0.37))) < 1e-15
