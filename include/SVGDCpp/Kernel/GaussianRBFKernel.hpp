@@ -1,7 +1,9 @@
 /* GaussianRBFKernel.hpp — k(x, x') = exp(-(x-x')^T A (x-x')), A = a I
  * (reference Kernel/GaussianRBFKernel.hpp:47-88).  ScaleMethod::Median recomputes
  * a = log(n) / median(|x_i - x_j|)^2 from the current particles at every Step (:141-188); on the
- * device that is an exact radix select over all n^2 distances (svgdcpp_b200/csrc/select.cuh). */
+ * device that is an exact radix select over all n^2 distances (svgdcpp_b200/csrc/select.cuh).
+ * ScaleMethod::Hessian (:189-210) makes A the mean negative Hessian of log p over the particles / (2 d); the device
+ * path serves it for the built-in Gaussian models in FP64 precision (svgdcpp_b200/csrc/kernels_hessian.cuh). */
 #ifndef SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
 #define SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
 
