@@ -3,7 +3,7 @@
  * a = log(n) / median(|x_i - x_j|)^2 from the current particles at every Step (:141-188); on the
  * device that is an exact radix select over all n^2 distances (svgdcpp_b200/csrc/select.cuh).
  * ScaleMethod::Hessian (:189-210) makes A the mean negative Hessian of log p over the particles / (2 d); the device
- * path serves it for the built-in Gaussian models in FP64 precision (svgdcpp_b200/csrc/kernels_hessian.cuh). */
+ * path serves it for the built-in Gaussian models (svgdcpp_b200/csrc/kernels_hessian.cuh). */
 #ifndef SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
 #define SVGDCPP_B200_GAUSSIAN_RBF_KERNEL_HPP
 

@@ -133,7 +133,7 @@ int svgdb_compute_phi(svgdb_ctx *ctx, double *phi_dxN, double *scale_out);
 /* GaussianRBFKernel::ComputeScale (Kernel/GaussianRBFKernel.hpp:164-212) on the current X. */
 int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out);
 /* The kernel's inverse scale matrix of the last Step / compute call, d x d (GaussianRBFKernel::GetParameters()[0]):
- * a * I for the median and fixed methods; for SVGDB_SCALE_HESSIAN (SVGDB_PRECISION_F64, MultivariateNormal models)
+ * a * I for the median and fixed methods; for SVGDB_SCALE_HESSIAN (MultivariateNormal models and sums of them)
  * A = 1/(2 d n) sum_i -Hessian(log p)(x_i) (GaussianRBFKernel.hpp:189-210), which must be positive definite. */
 int svgdb_get_scale_matrix(svgdb_ctx *ctx, double *A_dxd);
 

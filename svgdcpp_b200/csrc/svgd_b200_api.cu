@@ -116,7 +116,8 @@ struct svgdb_ctx {
     double fixed_a = 0.0;
     // ScaleMethod::Hessian (kernels_hessian.cuh): scale matrix A = R^T R, transformed particles / gradients
     std::vector<double> A_host;
-    double *Hsum_dev = nullptr, *Wsum_dev = nullptr, *R_dev = nullptr, *Rinv_dev = nullptr, *Y_dev = nullptr, *GH_dev = nullptr;
+    bool hess_const_valid = false; // one Gaussian: the Hessian does not depend on the particles, A and its factors are kept
+    double *Hsum_dev = nullptr, *Wsum_dev = nullptr, *R_dev = nullptr, *Rt_dev = nullptr, *Rinv_dev = nullptr, *Y_dev = nullptr, *GH_dev = nullptr;
 
     // optimizer
     bool opt_set = false;
@@ -1006,6 +1007,48 @@ bool cholesky_upper(const std::vector<double> &A, int d, std::vector<double> &R,
     return true;
 }
 
+// Sum over all particles of the particle-dependent part of -Hessian(log p) and of the softmax weights (kernels_hessian.cuh).
+int hessian_partial_sums(svgdb_ctx *ctx, std::vector<double> &H, std::vector<double> &W)
+{
+    const int d = ctx->d, C = ctx->C;
+    const size_t dd = (size_t)d * d;
+    if (!ctx->Wsum_dev) CU(cudaMalloc(&ctx->Wsum_dev, (size_t)C * sizeof(double))); // released when the model changes
+    CU(cudaMemsetAsync(ctx->Hsum_dev, 0, dd * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->Wsum_dev, 0, (size_t)C * sizeof(double), ctx->stream));
+    if (ctx->n_rows > 0) {
+        const int tiles = (d + 63) / 64;
+        int pt = 16; // particles per group: as many as the shared-memory budget allows
+        while (pt > 1 && hessian_smem_doubles(pt, C, d) * sizeof(double) > 160 * 1024) pt >>= 1;
+        const size_t smem = hessian_smem_doubles(pt, C, d) * sizeof(double);
+        if (smem > 200 * 1024) return fail(ctx, SVGDB_ERR_DIMENSION, "ScaleMethod::Hessian: components x dimension too large for the Hessian kernel");
+        const int64_t groups = (ctx->n_rows + pt - 1) / pt;
+        dim3 grid((unsigned)std::min<int64_t>(groups, (int64_t)ctx->sm_count * 4), (unsigned)(tiles * tiles));
+#define SVGDB_HESS_CASE(PT)                                                                                                           \
+    case PT:                                                                                                                          \
+        CU(cudaFuncSetAttribute(mvn_sum_hessian_f64_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        mvn_sum_hessian_f64_kernel<PT><<<grid, 256, smem, ctx->stream>>>(ctx->X[ctx->cur], d, ctx->row0, ctx->n_rows, C, ctx->means_dev, \
+                                                                         ctx->prec_dev, tiles, ctx->Hsum_dev, ctx->Wsum_dev);         \
+        break;
+        switch (pt) {
+            SVGDB_HESS_CASE(16)
+            SVGDB_HESS_CASE(8)
+            SVGDB_HESS_CASE(4)
+            SVGDB_HESS_CASE(2)
+            SVGDB_HESS_CASE(1)
+        }
+#undef SVGDB_HESS_CASE
+        KERNEL_CHECK();
+    }
+    if (ctx->world > 1) {
+        NC(nccl().AllReduce(ctx->Hsum_dev, ctx->Hsum_dev, dd, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        NC(nccl().AllReduce(ctx->Wsum_dev, ctx->Wsum_dev, (size_t)C, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(H.data(), ctx->Hsum_dev, dd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(W.data(), ctx->Wsum_dev, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
 // A = 1/(2 d n) sum_i -Hessian(log p)(x_i) on the host (GaussianRBFKernel.hpp:189-210), its factor R and R^-1 on the device.
 int hessian_scale_dev(svgdb_ctx *ctx)
 {
@@ -1015,47 +1058,41 @@ int hessian_scale_dev(svgdb_ctx *ctx)
     const size_t dd = (size_t)d * d;
     if (!ctx->Hsum_dev) {
         CU(cudaMalloc(&ctx->Hsum_dev, dd * sizeof(double)));
-        CU(cudaMalloc(&ctx->Wsum_dev, (size_t)std::max(C, 1) * sizeof(double)));
         CU(cudaMalloc(&ctx->R_dev, dd * sizeof(double)));
+        CU(cudaMalloc(&ctx->Rt_dev, dd * sizeof(double)));
         CU(cudaMalloc(&ctx->Rinv_dev, dd * sizeof(double)));
         CU(cudaMalloc(&ctx->Y_dev, (size_t)ctx->n_pad * d * sizeof(double)));
         CU(cudaMalloc(&ctx->GH_dev, (size_t)ctx->rows_per_rank * d * sizeof(double)));
         CU(cudaMemsetAsync(ctx->Y_dev, 0, (size_t)ctx->n_pad * d * sizeof(double), ctx->stream));
     }
-    CU(cudaMemsetAsync(ctx->Hsum_dev, 0, dd * sizeof(double), ctx->stream));
-    CU(cudaMemsetAsync(ctx->Wsum_dev, 0, (size_t)C * sizeof(double), ctx->stream));
-    if (ctx->n_rows > 0) {
-        const int tiles = (d + 63) / 64;
-        const size_t smem = ((size_t)(C + 1) * d + 2 * (size_t)C) * sizeof(double);
-        if (smem > 200 * 1024) return fail(ctx, SVGDB_ERR_DIMENSION, "ScaleMethod::Hessian: components x dimension too large for the Hessian kernel");
-        CU(cudaFuncSetAttribute(mvn_sum_hessian_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)std::min<int64_t>(ctx->n_rows, (int64_t)ctx->sm_count * 8), (unsigned)(tiles * tiles));
-        mvn_sum_hessian_f64_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->X[ctx->cur], d, ctx->row0, ctx->n_rows, C, ctx->means_dev, ctx->prec_dev,
-                                                                       tiles, ctx->Hsum_dev, ctx->Wsum_dev);
-        KERNEL_CHECK();
+    if (ctx->hess_const_valid) return SVGDB_OK;
+    std::vector<double> H(dd, 0.0), W((size_t)C, 0.0), R, Rinv;
+    if (C == 1) {
+        // One Gaussian: w = 1 and ybar = y, so the particle-dependent part of the Hessian vanishes identically (the kernel
+        // would add exact zeros) and sum_i w_i = n: A = P / (2 d) for every X.
+        W[0] = (double)ctx->N;
+    } else {
+        TRY(hessian_partial_sums(ctx, H, W));
     }
-    if (ctx->world > 1) {
-        NC(nccl().AllReduce(ctx->Hsum_dev, ctx->Hsum_dev, dd, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-        NC(nccl().AllReduce(ctx->Wsum_dev, ctx->Wsum_dev, (size_t)C, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-    }
-    std::vector<double> H(dd), W((size_t)C), R, Rinv;
-    CU(cudaMemcpyAsync(H.data(), ctx->Hsum_dev, dd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(W.data(), ctx->Wsum_dev, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
     ctx->A_host.assign(dd, 0.0);
     const double scale = 1.0 / (2.0 * (double)d * (double)ctx->N);
     for (int r = 0; r < d; ++r)
         for (int c = 0; c < d; ++c) {
             double s = 0.5 * (H[(size_t)r * d + c] + H[(size_t)c * d + r]);
-            for (int k = 0; k < C; ++k) s += W[(size_t)k] * ctx->prec_host[((size_t)k * d + r) * d + c]; // prec_host is symmetrised
+            for (int k = 0; k < C; ++k) s += W[(size_t)k] * ctx->prec_host[((size_t)k * d + r) * d + c]; // symmetric up to the rounding of the host inversion
             ctx->A_host[(size_t)r * d + c] = s * scale;
         }
     if (!cholesky_upper(ctx->A_host, d, R, Rinv))
         return fail(ctx, SVGDB_ERR_NUMERIC, "ScaleMethod::Hessian: the scale matrix (mean negative Hessian of log p over the particles) is not positive definite");
+    std::vector<double> Rt(dd);
+    for (int r = 0; r < d; ++r)
+        for (int c = 0; c < d; ++c) Rt[(size_t)r * d + c] = R[(size_t)c * d + r];
     CU(cudaMemcpyAsync(ctx->R_dev, R.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->Rt_dev, Rt.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->Rinv_dev, Rinv.data(), dd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream)); // R, Rinv are locals
+    CU(cudaStreamSynchronize(ctx->stream)); // R, Rt, Rinv are locals
     ctx->stats.last_scale = ctx->A_host[0];
+    ctx->hess_const_valid = C == 1;
     return SVGDB_OK;
 }
 
@@ -1072,24 +1109,10 @@ int prepare_and_phi_hessian(svgdb_ctx *ctx, bool debug_phi)
     TRY(launch_grad(ctx, ctx->stream));
     prof_mark(ctx, 2);
     // Y = X R^T (all rows: every rank holds X), G^ = G R^-1 (local rows).  Row-vector form: y_i = x_i R^T, g^_i = g_i R^-1.
-    std::vector<double> Rt((size_t)d * d);
-    {   // R^T on the device: reuse Hsum_dev as scratch for the transposed factor
-        std::vector<double> R((size_t)d * d);
-        CU(cudaMemcpyAsync(R.data(), ctx->R_dev, R.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (int r = 0; r < d; ++r)
-            for (int c = 0; c < d; ++c) Rt[(size_t)r * d + c] = R[(size_t)c * d + r];
-        CU(cudaMemcpyAsync(ctx->Hsum_dev, Rt.data(), Rt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    {
-        const int64_t cnt = ctx->N * d;
-        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->Hsum_dev, ctx->N, d, ctx->Y_dev);
-        KERNEL_CHECK();
-    }
+    row_times_matrix_f64_kernel<false><<<row_times_matrix_blocks(ctx->N, d), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->Rt_dev, ctx->N, d, ctx->Y_dev, RowApply{});
+    KERNEL_CHECK();
     if (ctx->n_rows > 0) {
-        const int64_t cnt = ctx->n_rows * d;
-        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->G, ctx->Rinv_dev, ctx->n_rows, d, ctx->GH_dev);
+        row_times_matrix_f64_kernel<false><<<row_times_matrix_blocks(ctx->n_rows, d), 256, 0, ctx->stream>>>(ctx->G, ctx->Rinv_dev, ctx->n_rows, d, ctx->GH_dev, RowApply{});
         KERNEL_CHECK();
     }
     // the scalar-bandwidth machinery on the transformed quantities, a = 1, writing phi^ for the local rows into phi_dbg
@@ -1098,22 +1121,36 @@ int prepare_and_phi_hessian(svgdb_ctx *ctx, bool debug_phi)
     double *X_keep = ctx->X[ctx->cur], *G_keep = ctx->G;
     ctx->X[ctx->cur] = ctx->Y_dev;
     ctx->G = ctx->GH_dev;
-    int rc = launch_rownorm(ctx);
-    if (rc == SVGDB_OK) rc = launch_make_v(ctx);
-    prof_mark(ctx, 3);
-    if (rc == SVGDB_OK) rc = launch_phi(ctx, true);
+    int rc = SVGDB_OK;
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) { // the tensor-core pair kernel centres its operands: column sums of Y
+        cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream);
+        svgdb::tc::colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->Y_dev, ctx->N, d, ctx->colsum);
+        rc = launch_phi_x_operands(ctx, ctx->stream);
+        if (rc == SVGDB_OK) rc = launch_make_v(ctx);
+        prof_mark(ctx, 3);
+        if (rc == SVGDB_OK) rc = launch_phi_tc32(ctx, true, true);
+    } else
+#endif
+    {
+        rc = launch_rownorm(ctx);
+        if (rc == SVGDB_OK) rc = launch_make_v(ctx);
+        prof_mark(ctx, 3);
+        if (rc == SVGDB_OK) rc = launch_phi(ctx, true);
+    }
     ctx->X[ctx->cur] = X_keep;
     ctx->G = G_keep;
     TRY(rc);
-    // phi = phi^ R (rows), through GH_dev as scratch, back into phi_dbg
+    // phi = phi^ R (rows): for ComputePhi through GH_dev back into phi_dbg, for a step straight into the optimizer update
     if (ctx->n_rows > 0) {
-        const int64_t cnt = ctx->n_rows * d;
-        row_times_matrix_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->phi_dbg, ctx->R_dev, ctx->n_rows, d, ctx->GH_dev);
-        KERNEL_CHECK();
-        CU(cudaMemcpyAsync(ctx->phi_dbg, ctx->GH_dev, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        if (!debug_phi) {
-            opt_apply_f64_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->phi_dbg, ctx->row0, ctx->n_rows, d, ctx->opt,
-                                                                                      ctx->s1, ctx->s2, ctx->lb, ctx->ub, ctx->X[ctx->cur ^ 1]);
+        const unsigned blocks = row_times_matrix_blocks(ctx->n_rows, d);
+        if (debug_phi) {
+            row_times_matrix_f64_kernel<false><<<blocks, 256, 0, ctx->stream>>>(ctx->phi_dbg, ctx->R_dev, ctx->n_rows, d, ctx->GH_dev, RowApply{});
+            KERNEL_CHECK();
+            CU(cudaMemcpyAsync(ctx->phi_dbg, ctx->GH_dev, (size_t)ctx->n_rows * d * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            RowApply ap{ctx->X[ctx->cur], ctx->X[ctx->cur ^ 1], ctx->row0, ctx->opt, ctx->s1, ctx->s2, ctx->lb, ctx->ub};
+            row_times_matrix_f64_kernel<true><<<blocks, 256, 0, ctx->stream>>>(ctx->phi_dbg, ctx->R_dev, ctx->n_rows, d, nullptr, ap);
             KERNEL_CHECK();
         }
     }
@@ -1303,7 +1340,7 @@ void svgdb_destroy(svgdb_ctx *ctx)
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     free_sharded(ctx);
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
-    cudaFree(ctx->Hsum_dev); cudaFree(ctx->Wsum_dev); cudaFree(ctx->R_dev); cudaFree(ctx->Rinv_dev); cudaFree(ctx->Y_dev); cudaFree(ctx->GH_dev);
+    cudaFree(ctx->Hsum_dev); cudaFree(ctx->Wsum_dev); cudaFree(ctx->R_dev); cudaFree(ctx->Rt_dev); cudaFree(ctx->Rinv_dev); cudaFree(ctx->Y_dev); cudaFree(ctx->GH_dev);
     cudaFree(ctx->pass_words); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
     cudaFree(ctx->sel); cudaFree(ctx->medres);
     if (ctx->hs) cudaFreeHost(ctx->hs);
@@ -1415,8 +1452,9 @@ int svgdb_set_model_mvn_sum(svgdb_ctx *ctx, int32_t C, const double *means, cons
             return fail(ctx, SVGDB_ERR_NUMERIC, "covariance of component " + std::to_string(c) + " is singular");
         std::copy(inv.begin(), inv.end(), prec.begin() + (size_t)c * d * d);
     }
-    cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
-    ctx->means_dev = ctx->prec_dev = nullptr;
+    cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev); cudaFree(ctx->Wsum_dev);
+    ctx->means_dev = ctx->prec_dev = ctx->Wsum_dev = nullptr;
+    ctx->hess_const_valid = false;
     CU(cudaMalloc(&ctx->means_dev, (size_t)C * d * sizeof(double)));
     CU(cudaMalloc(&ctx->prec_dev, prec.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->means_dev, means, (size_t)C * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1449,8 +1487,6 @@ int svgdb_set_kernel_rbf(svgdb_ctx *ctx, int scale_method, double fixed_a)
     if (!ctx) return SVGDB_ERR_INVALID;
     if (scale_method != SVGDB_SCALE_MEDIAN && scale_method != SVGDB_SCALE_FIXED && scale_method != SVGDB_SCALE_HESSIAN)
         return fail(ctx, SVGDB_ERR_INVALID, "[Argument error] Invalid scale method Enum provided.");
-    if (scale_method == SVGDB_SCALE_HESSIAN && ctx->precision != SVGDB_PRECISION_F64)
-        return fail(ctx, SVGDB_ERR_INVALID, "ScaleMethod::Hessian is available in SVGDB_PRECISION_F64 only");
     if (scale_method == SVGDB_SCALE_FIXED && !(fixed_a > 0.0) ) return fail(ctx, SVGDB_ERR_INVALID, "fixed kernel scale must be positive");
     ctx->scale_method = scale_method;
     ctx->fixed_a = fixed_a;
@@ -1547,14 +1583,14 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
     if (!ctx) return SVGDB_ERR_INVALID;
     if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
     CU(cudaSetDevice(ctx->device));
-#ifdef SVGDB_WITH_TC32
-    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
-#endif
     if (ctx->scale_method == SVGDB_SCALE_HESSIAN) { // matrix-valued: A(0,0) here, the whole matrix through svgdb_get_scale_matrix
         TRY(hessian_scale_dev(ctx));
         if (scale_out) *scale_out = ctx->A_host[0];
         return SVGDB_OK;
     }
+#ifdef SVGDB_WITH_TC32
+    if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
+#endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
     TRY(compute_scale_dev(ctx));
     double a = 0.0;

@@ -129,3 +129,34 @@ def test_tc32_full_size_properties(sv):
     step = np.abs(x0 - before)
     assert np.all(np.isfinite(x0)) and np.max(step) <= 0.1 * (1 + 1e-6) and np.mean(step) > 0.05
     svgd.close()
+
+
+def test_tc32_hessian_scale(sv, oracle):
+    """ScaleMethod::Hessian on the tensor-core path (the pair kernel runs with a = 1 on y = R x): scale matrix in FP64,
+    phi and a short trajectory within the TC32 tolerances of the oracle."""
+    rng = np.random.default_rng(11)
+    for n, d, C in [(600, 64, 1), (513, 24, 2)]:
+        means = 0.4 * rng.standard_normal((C, d))
+        covs = np.stack([(lambda M: M @ M.T / d + 0.7 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(C)])
+        x0 = np.asfortranarray(1.2 * rng.standard_normal((d, n)))
+        X0 = np.array(x0.T, order="C", copy=True)
+        model = None
+        for k in range(C):
+            m = sv.MultivariateNormal(means[k], covs[k])
+            model = m if model is None else model + m
+        svgd = sv.SVGD(d, 20, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Hessian, model), model, sv.Adam(d, n, 0.05, 0.9, 0.999), precision=TC32)
+        phi, _ = svgd.ComputePhi()
+        A = svgd.GetScaleMatrix()
+        A_ref = oracle.rbf_hessian_scale(X0, means, covs, lse=True)
+        phi_ref = oracle.phi_matrix(X0, oracle.mvn_sum_logp_grad(X0, means, covs, lse=True), A_ref)
+        e_A = np.max(np.abs(A - A_ref)) / np.max(np.abs(A_ref))
+        e_phi = np.max(np.abs(phi.T - phi_ref)) / np.max(np.abs(phi_ref))
+        svgd.Initialize()
+        svgd.Run()
+        svgd.close()
+        ref = oracle.svgd_run(X0, 20, means, covs, opt_kind=oracle.OPT_ADAM, lr=0.05, scale_method=oracle.SCALE_HESSIAN, lse=True)
+        rms = np.sqrt(np.mean((x0.T - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+        print("tc32 hessian scale n=%d d=%d C=%d: A rel err %.3g, phi max-rel err %.3g, trajectory rms %.3g" % (n, d, C, e_A, e_phi, rms))
+        assert e_A < 1e-12
+        assert e_phi < PHI_TOL
+        assert rms < 1e-3
