@@ -134,9 +134,9 @@ public:
     void Step(size_t iters = 1)
     {
         model_ptr_->Step();
-        Check(svgdb_set_particles(ctx_, coord_matrix_ptr_->data()));
-        Check(svgdb_step(ctx_, static_cast<int64_t>(iters)));
-        Check(svgdb_get_particles(ctx_, coord_matrix_ptr_->data()));
+        if (iters == 0) return;
+        /* upload, iterate, download; the download of the last iteration overlaps its pair kernel (svgdb_step_host) */
+        Check(svgdb_step_host(ctx_, coord_matrix_ptr_->data(), coord_matrix_ptr_->data(), static_cast<int64_t>(iters)));
     }
 
     /* ComputePhi of the reference (:407-454) for inspection: phi is dim x n. */

@@ -125,6 +125,13 @@ int svgdb_initialize(svgdb_ctx *ctx);
 
 /* ---- SVGD::Step x iters == SVGD::Run (SVGD.hpp:338-400).  Asynchronous: X stays on the device. */
 int svgdb_step(svgdb_ctx *ctx, int64_t iters);
+/* The same on host memory, the way the reference's Step works on its coordinate matrix (SVGD.hpp:373-400): uploads this
+ * rank's rows (svgdb_set_particles_rows), runs `iters` >= 1 steps and returns the updated rows in rows_out
+ * (svgdb_get_particles_rows), which may be the same buffer.  Synchronous.  On the tensor-core path the last iteration's
+ * pair kernel runs in four row chunks and each chunk's rows start their device-to-host copy as soon as they are updated, so
+ * most of the PCIe transfer overlaps the remaining pair interactions; pinned host memory (svgdb_host_alloc) is needed for
+ * that overlap, pageable memory works but serialises. */
+int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int64_t iters);
 
 /* SVGD::ComputePhi (SVGD.hpp:407-454) on the current X, no update: writes phi (d x N) and the
  * kernel scale used.  Either output may be NULL.  Synchronous. */

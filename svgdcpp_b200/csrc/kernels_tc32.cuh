@@ -46,7 +46,8 @@ struct OptTcArgs {
     const double *colsum;
     const float *phi_buf;
     const double *a_ptr;
-    int64_t n_total, row0, n_rows;
+    int64_t n_total, row0, n_rows; // rows [row0, row0 + n_rows) of the particle matrix
+    int64_t state_row0;            // first row of this rank: optimizer state and phi_out are indexed from it
     int d;
     OptParams opt;
     double *s1, *s2;
@@ -62,6 +63,7 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
     int64_t li = idx / p.d;
     int c = (int)(idx - li * p.d);
     int64_t i = p.row0 + li;
+    const int64_t sidx = (i - p.state_row0) * p.d + c;
     const double a = *p.a_ptr;
     double x = p.X[i * p.d + c];
     double xc = x - p.colsum[c] / (double)p.n_total;
@@ -69,9 +71,9 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
     double rowsum = (double)p.phi_buf[i * TC_PHI_LD + TC_ONES_ROW];
     double phi = (1.0 / (double)p.n_total) * (acc + 2.0 * a * xc * rowsum);
     if (p.phi_out != nullptr) {
-        p.phi_out[idx] = phi;
+        p.phi_out[sidx] = phi;
     } else {
-        double xn = x + opt_increment(p.opt, phi, p.s1, p.s2, idx);
+        double xn = x + opt_increment(p.opt, phi, p.s1, p.s2, sidx);
         p.X_out[i * p.d + c] = clamp_coord(xn, p.lb, p.ub, c);
     }
 }

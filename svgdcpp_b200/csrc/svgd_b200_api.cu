@@ -83,6 +83,10 @@ struct svgdb_ctx {
     int d = 0;
     int precision = SVGDB_PRECISION_F64;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                 // svgdb_step_host: finished rows leave for the host while the pair kernel works on the rest
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *stream_out = nullptr;                       // host destination of this rank's updated rows during svgdb_step_host
+    bool streamed = false;                              // the last step delivered its rows to stream_out
     cudaStream_t side_stream = nullptr;                 // grad log p runs here, next to the median pass (it only needs X)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_med = nullptr;
     bool med_pending = false; // the last median's result is still on its way to the pinned mirror
@@ -889,69 +893,96 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
     if (!x_operands_done) TRY(launch_phi_x_operands(ctx, ctx->stream));
     make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
     KERNEL_CHECK();
-    Phi2Args a{};
-    a.phi_buf = ctx->phi_buf;
-    a.XA2 = ctx->XA2;
-    a.UA = ctx->UA2;
-    a.WB = ctx->WB2;
-    a.row0 = ctx->row0;
-    a.n_rows = ctx->n_rows;
-    a.n_jtiles = (int)(ctx->n_pad128 / 128);
-    a.n_ipairs = (int)((ctx->n_rows + 255) / 256);
-    a.poly = ctx->phi_poly;
-    a.dbg = ctx->phi_dbg_mode;
-    a.err = ctx->tc_err;
-    a.trace = ctx->tc_trace;
-    const long long units = (long long)a.n_ipairs * a.n_jtiles;
-    const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units); // persistent: one CTA per SM
-    prof_mark(ctx, 5);
+    // Row chunks.  Normally one; when the updated rows are wanted on the host (svgdb_step_host) the rows are processed in four
+    // launches of 3/8, 3/8, 1/8, 1/8 of the i-pairs, each followed by its optimizer kernel and a device-to-host copy on the
+    // copy stream, so that all but the last eighth of the PCIe transfer hides behind the remaining pair interactions.
+    const int n_ipairs_all = (int)((ctx->n_rows + 255) / 256);
+    const bool stream_rows = ctx->stream_out != nullptr && !debug_phi && ctx->phi_dbg_mode == 0 && n_ipairs_all >= 32;
+    const int n_chunks = stream_rows ? 4 : 1;
+    int chunk_ipairs[4] = {n_ipairs_all, 0, 0, 0};
+    if (stream_rows) {
+        chunk_ipairs[0] = chunk_ipairs[1] = (3 * n_ipairs_all) / 8;
+        chunk_ipairs[2] = n_ipairs_all / 8;
+        chunk_ipairs[3] = n_ipairs_all - chunk_ipairs[0] - chunk_ipairs[1] - chunk_ipairs[2];
+    }
+    int ipair0 = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int64_t off = (int64_t)ipair0 * 256;
+        const int64_t rows = std::min<int64_t>((int64_t)chunk_ipairs[ch] * 256, ctx->n_rows - off);
+        ipair0 += chunk_ipairs[ch];
+        if (rows <= 0) continue;
+        Phi2Args a{};
+        a.phi_buf = ctx->phi_buf;
+        a.XA2 = ctx->XA2;
+        a.UA = ctx->UA2;
+        a.WB = ctx->WB2;
+        a.row0 = ctx->row0 + off;
+        a.n_rows = rows;
+        a.n_jtiles = (int)(ctx->n_pad128 / 128);
+        a.n_ipairs = chunk_ipairs[ch];
+        a.poly = ctx->phi_poly;
+        a.dbg = ctx->phi_dbg_mode;
+        a.err = ctx->tc_err;
+        a.trace = ctx->tc_trace;
+        const long long units = (long long)a.n_ipairs * a.n_jtiles;
+        const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units); // persistent: one CTA per SM
+        if (ch == 0) prof_mark(ctx, 5);
 #define SVGDB_PHI2_CASE(P) \
     case P: phi2_tc32_kernel<P><<<grid, P2_THREADS, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
-    switch (ctx->phi_poly) {
-        SVGDB_PHI2_CASE(0)
-        SVGDB_PHI2_CASE(2)
-        SVGDB_PHI2_CASE(4)
-        SVGDB_PHI2_CASE(6)
-        SVGDB_PHI2_CASE(8)
-    default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
-    }
+        switch (ctx->phi_poly) {
+            SVGDB_PHI2_CASE(0)
+            SVGDB_PHI2_CASE(2)
+            SVGDB_PHI2_CASE(4)
+            SVGDB_PHI2_CASE(6)
+            SVGDB_PHI2_CASE(8)
+        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
+        }
 #undef SVGDB_PHI2_CASE
-    KERNEL_CHECK();
-    prof_mark(ctx, 6);
-    ++ctx->stats.phi_launches;
-    if (ctx->tc_trace) {
-        std::vector<long long> h(3 * 64 * 8);
-        CU(cudaMemcpyAsync(h.data(), ctx->tc_trace, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (FILE *f = std::fopen(std::getenv("SVGDB_TC_TRACE"), "w")) {
-            for (size_t k = 0; k < h.size(); ++k) std::fprintf(f, "%lld%c", h[k], (k % 8 == 7) ? '\n' : ' ');
-            std::fclose(f);
+        KERNEL_CHECK();
+        if (ch == n_chunks - 1) prof_mark(ctx, 6);
+        if (ch == 0 && ctx->tc_trace) {
+            std::vector<long long> h(3 * 64 * 8);
+            CU(cudaMemcpyAsync(h.data(), ctx->tc_trace, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (FILE *f = std::fopen(std::getenv("SVGDB_TC_TRACE"), "w")) {
+                for (size_t k = 0; k < h.size(); ++k) std::fprintf(f, "%lld%c", h[k], (k % 8 == 7) ? '\n' : ' ');
+                std::fclose(f);
+            }
+        }
+        const int64_t cnt = rows * ctx->d;
+        if (ctx->phi_dbg_mode != 0 && !debug_phi) { // development: the kernel produced garbage on purpose, keep the particles
+            CU(cudaMemcpyAsync(ctx->X[ctx->cur ^ 1] + a.row0 * ctx->d, ctx->X[ctx->cur] + a.row0 * ctx->d, (size_t)cnt * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+            continue;
+        }
+        OptTcArgs o{};
+        o.X = ctx->X[ctx->cur];
+        o.colsum = ctx->colsum;
+        o.phi_buf = ctx->phi_buf;
+        o.a_ptr = ctx->a_dev;
+        o.n_total = ctx->N;
+        o.row0 = a.row0;
+        o.n_rows = rows;
+        o.state_row0 = ctx->row0;
+        o.d = ctx->d;
+        o.opt = ctx->opt;
+        o.s1 = ctx->s1;
+        o.s2 = ctx->s2;
+        o.lb = ctx->lb;
+        o.ub = ctx->ub;
+        o.X_out = ctx->X[ctx->cur ^ 1];
+        o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+        opt_update_tc32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
+        KERNEL_CHECK();
+        if (stream_rows) {
+            CU(cudaEventRecord(ctx->ev_chunk[ch], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[ch], 0));
+            CU(cudaMemcpyAsync(ctx->stream_out + (size_t)off * ctx->d, ctx->X[ctx->cur ^ 1] + (size_t)a.row0 * ctx->d, (size_t)cnt * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
     }
-    OptTcArgs o{};
-    o.X = ctx->X[ctx->cur];
-    o.colsum = ctx->colsum;
-    o.phi_buf = ctx->phi_buf;
-    o.a_ptr = ctx->a_dev;
-    o.n_total = ctx->N;
-    o.row0 = ctx->row0;
-    o.n_rows = ctx->n_rows;
-    o.d = ctx->d;
-    o.opt = ctx->opt;
-    o.s1 = ctx->s1;
-    o.s2 = ctx->s2;
-    o.lb = ctx->lb;
-    o.ub = ctx->ub;
-    o.X_out = ctx->X[ctx->cur ^ 1];
-    o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
-    int64_t cnt = ctx->n_rows * ctx->d;
-    if (ctx->phi_dbg_mode != 0 && !debug_phi) { // development: the kernel produced garbage on purpose, keep the particles
-        CU(cudaMemcpyAsync(ctx->X[ctx->cur ^ 1] + ctx->row0 * ctx->d, ctx->X[ctx->cur] + ctx->row0 * ctx->d, (size_t)cnt * sizeof(double),
-                           cudaMemcpyDeviceToDevice, ctx->stream));
-        return SVGDB_OK;
-    }
-    opt_update_tc32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
-    KERNEL_CHECK();
+    ++ctx->stats.phi_launches;
+    ctx->streamed = stream_rows;
     return SVGDB_OK;
 }
 
@@ -1269,6 +1300,8 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     ctx->stream = ctx->own_stream;
     for (auto &ev : ctx->ev) CU(cudaEventCreate(&ev));
     CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : ctx->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_med, cudaEventDisableTiming));
@@ -1349,6 +1382,8 @@ void svgdb_destroy(svgdb_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_med) cudaEventDestroy(ctx->ev_med);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1554,6 +1589,40 @@ int svgdb_step(svgdb_ctx *ctx, int64_t iters)
     CU(cudaSetDevice(ctx->device));
     for (int64_t it = 0; it < iters; ++it) TRY(one_step(ctx));
     return SVGDB_OK;
+}
+
+int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int64_t iters)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if ((!rows_in || !rows_out) && ctx->n_rows > 0) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    if (iters < 1) return fail(ctx, SVGDB_ERR_INVALID, "svgdb_step_host needs at least one iteration");
+    TRY(check_ready(ctx));
+    if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
+    CU(cudaSetDevice(ctx->device));
+    TRY(svgdb_set_particles_rows(ctx, rows_in));
+    for (int64_t it = 0; it + 1 < iters; ++it) TRY(one_step(ctx));
+    // The last iteration hands its rows to the host as they are finished -- from pinned memory only: a copy into pageable
+    // memory blocks the launching thread, which would hold back the launches of the remaining row chunks.
+    cudaPointerAttributes attr{};
+    const bool pinned = rows_out && cudaPointerGetAttributes(&attr, rows_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    ctx->stream_out = pinned ? rows_out : nullptr;
+    ctx->streamed = false;
+    const int rc = one_step(ctx);
+    ctx->stream_out = nullptr;
+    if (rc != SVGDB_OK) {
+        cudaStreamSynchronize(ctx->copy_stream); // nothing may still be writing into the caller's buffer
+        return rc;
+    }
+    if (ctx->streamed) {
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+#ifdef SVGDB_WITH_TC32
+        TRY(check_tc_err(ctx));
+#endif
+        return SVGDB_OK;
+    }
+    return svgdb_get_particles_rows(ctx, rows_out);
 }
 
 int svgdb_compute_phi(svgdb_ctx *ctx, double *phi, double *scale_out)

@@ -254,7 +254,12 @@ class SVGD:
         self._push_kernel()
         o = optimizer
         self._check(self._lib.svgdb_set_optimizer(self._ctx, o.kind, o.learning_rate_, o.decay_rate_1_, o.decay_rate_2_, o.stabilizer_))
-        self._host = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
+        # pinned staging buffer (particle-major): the device-to-host copy of a step overlaps its pair kernel only from pinned memory
+        self._hp = C.c_void_p()
+        count = self.num_particles_ * self.dimension_
+        if self._lib.svgdb_host_alloc(C.byref(self._hp), count * 8) != _capi.OK:
+            raise MemoryError("pinned host allocation of %d bytes failed" % (count * 8))
+        self._host = np.ctypeslib.as_array((C.c_double * count).from_address(self._hp.value)).reshape(self.num_particles_, self.dimension_)
         self._dirty_host = True
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -310,9 +315,11 @@ class SVGD:
         self._push_model()
 
     def Step(self, iters=1):  # SVGD.hpp:373-400 (protected there; public here)
-        self._upload()
-        self._check(self._lib.svgdb_step(self._ctx, int(iters)))
-        self._download()
+        if int(iters) < 1:
+            return
+        self._host[...] = np.asarray(self.coord_matrix_, dtype=np.float64).T
+        self._check(self._lib.svgdb_step_host(self._ctx, _ptr(self._host), _ptr(self._host), int(iters)))
+        self.coord_matrix_[...] = self._host.T
 
     def Run(self):  # SVGD.hpp:338-366
         self.Step(self.num_iterations_)
@@ -356,6 +363,10 @@ class SVGD:
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self._lib.svgdb_destroy(self._ctx)
             self._ctx = C.c_void_p()
+        if getattr(self, "_hp", None) is not None and self._hp:
+            self._host = None
+            self._lib.svgdb_host_free(self._hp)
+            self._hp = C.c_void_p()
 
     def __del__(self):
         try:

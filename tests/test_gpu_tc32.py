@@ -160,3 +160,39 @@ def test_tc32_hessian_scale(sv, oracle):
         assert e_A < 1e-12
         assert e_phi < PHI_TOL
         assert rms < 1e-3
+
+
+def test_tc32_step_host_streams_rows(sv, oracle):
+    """svgdb_step_host (upload + steps + download, the last pair kernel in row chunks whose rows leave for the host as they are
+    finished) against svgdb_set_particles + svgdb_step + svgdb_get_particles on the same input: same particles up to the
+    order of the float partial sums, from pinned and from pageable host memory, with a ragged last chunk."""
+    import ctypes as C
+
+    n, d, iters = 9001, 64, 3
+    results = []
+    for mode in ("plain", "pinned", "pageable"):
+        svgd, x0, mu, cov = _setup(sv, n, d, seed=21)
+        lib, ctx = svgd._lib, svgd._ctx
+        dp = C.POINTER(C.c_double)
+        svgd.Initialize()
+        X = np.array(x0.T, order="C", copy=True)
+        if mode == "plain":
+            assert lib.svgdb_set_particles(ctx, X.ctypes.data_as(dp)) == 0
+            assert lib.svgdb_step(ctx, iters) == 0
+            assert lib.svgdb_get_particles(ctx, X.ctypes.data_as(dp)) == 0
+        elif mode == "pinned":
+            svgd._host[...] = X
+            ptr = svgd._host.ctypes.data_as(dp)
+            assert lib.svgdb_step_host(ctx, ptr, ptr, iters) == 0
+            X = svgd._host.copy()
+        else:
+            out = np.empty_like(X)
+            assert lib.svgdb_step_host(ctx, X.ctypes.data_as(dp), out.ctypes.data_as(dp), iters) == 0
+            X = out
+        results.append(X)
+        svgd.close()
+    ref = results[0]
+    for name, X in zip(("pinned", "pageable"), results[1:]):
+        err = np.sqrt(np.mean((X - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+        print("step_host (%s) vs set/step/get: rms rel diff %.3g" % (name, err))
+        assert np.all(np.isfinite(X)) and err < 1e-6
