@@ -35,11 +35,12 @@ static_assert(HIST_BINS * 8 <= D2_CWARPS * TC_WBUF * 4, "histogram must fit the 
 //   XA2[row] = -2 [hi | lo] (row operand -> TMEM),  XBD[row] = [hi | lo] (column operand, TMA),
 //   UA[row] = [r0 r1 r2 1 1 1 0..],  WB (core-matrix order) = [1 1 1 r0 r1 r2 0..],  r = |x~|^2 as a 3-term bf16 split;
 //   padding rows carry r = +inf: their distances never count.  rt[row] = r (FP64) for the pair kernel's later use.
-__global__ void split_dist2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, int64_t n, int64_t n_rows_a,
+// Rows [row_begin, n_rows_a) of the row-side arrays (and of the column-side ones below n_rows_b).
+__global__ void split_dist2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, int64_t n, int64_t row_begin, int64_t n_rows_a,
                                    int64_t n_rows_b, int d, __nv_bfloat16 *__restrict__ XA2, __nv_bfloat16 *__restrict__ XBD,
                                    __nv_bfloat16 *__restrict__ UA, __nv_bfloat16 *__restrict__ WB, double *__restrict__ rt)
 {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows_a) return;
     double s = 0.0;
@@ -100,6 +101,7 @@ struct Dist2Args {
     const __nv_bfloat16 *WB;  // [n_pad128 / 128][4 KB]
     int64_t n_total;
     int n_jtiles;
+    int jt_begin;                           // column tiles below this one are left out (they belong to an earlier launch of the same pass)
     int pair_offset, pair_stride, n_ipairs; // this rank owns i-pairs offset, offset + stride, ... (n_ipairs of them)
     float lo_f, hi_f;
     unsigned int width_bits; // IEEE bits of a float > fl(hi_f - lo_f): d2 is collected iff 0 <= fl(d2 - lo_f) < width
@@ -112,7 +114,7 @@ struct Dist2Args {
     int dbg; // measurement aid: 1 = counting warps only hand the buffers back, 2 = count without collecting, 3 = 1 + no TMA after priming
 };
 
-// Work list: for this rank's l-th i-pair ip = offset + stride * l, the j-tiles jt in [2 ip, n_jtiles) (tile-level upper
+// Work list: for this rank's l-th i-pair ip = offset + stride * l, the j-tiles jt in [max(2 ip, jt_begin), n_jtiles) (tile-level upper
 // triangle; the two diagonal-adjacent tiles are sorted out by the per-tile weights).  Linearised in that order.
 struct D2Seg { int ip, jb, je; };
 struct D2Cursor { int l; long long base; }; // base = linear position of the first unit of i-pair l
@@ -121,10 +123,11 @@ __device__ __forceinline__ bool d2_segment(const Dist2Args &p, D2Cursor &cur, lo
     if (pos >= end) return false;
     for (;;) { // advance to the i-pair containing pos
         const int ip = p.pair_offset + p.pair_stride * cur.l;
-        const long long len = max(0, p.n_jtiles - 2 * ip);
+        const int j0 = max(2 * ip, p.jt_begin);
+        const long long len = max(0, p.n_jtiles - j0);
         if (pos < cur.base + len) {
             s.ip = ip;
-            s.jb = 2 * ip + (int)(pos - cur.base);
+            s.jb = j0 + (int)(pos - cur.base);
             const long long seg_end = min(end, cur.base + len);
             s.je = s.jb + (int)(seg_end - pos);
             pos = seg_end;
@@ -138,7 +141,7 @@ __device__ __forceinline__ bool d2_segment(const Dist2Args &p, D2Cursor &cur, lo
 __device__ __forceinline__ long long d2_total_units(const Dist2Args &p)
 {
     long long tot = 0;
-    for (int l = 0; l < p.n_ipairs; ++l) tot += max(0, p.n_jtiles - 2 * (p.pair_offset + p.pair_stride * l));
+    for (int l = 0; l < p.n_ipairs; ++l) tot += max(0, p.n_jtiles - max(2 * (p.pair_offset + p.pair_stride * l), p.jt_begin));
     return tot;
 }
 

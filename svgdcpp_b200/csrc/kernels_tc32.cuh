@@ -31,6 +31,13 @@ __global__ void colsum_kernel(const double *__restrict__ X, int64_t n, int d, do
     if (k < d) atomicAdd(&sum[k], acc);
 }
 
+// The operands are centred on colsum / n.  Any common shift gives the same distances and the same phi, so when only the first
+// rows of a new particle set have arrived (svgdb_step_host) their mean stands in for the mean of all of them: sum *= factor.
+__global__ void colsum_scale_kernel(double *__restrict__ sum, int d, double factor)
+{
+    if ((int)threadIdx.x < d) sum[threadIdx.x] *= factor;
+}
+
 // Three-term bf16 split of a scalar (24 significant bits): v ~= t0 + t1 + t2.
 __device__ __forceinline__ void split3_bf16(double v, __nv_bfloat16 &t0, __nv_bfloat16 &t1, __nv_bfloat16 &t2)
 {

@@ -85,6 +85,9 @@ struct svgdb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;                 // svgdb_step_host: finished rows leave for the host while the pair kernel works on the rest
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};
+    int up_chunks = 0;                                  // svgdb_step_host: the particles are arriving in this many row chunks (copy stream) ...
+    int up_ipairs[4] = {0, 0, 0, 0};                    // ... chunk k ends at i-pair up_ipairs[k] (256 rows each); consumed by the first distance pass
     double *stream_out = nullptr;                       // host destination of this rank's updated rows during svgdb_step_host
     bool streamed = false;                              // the last step delivered its rows to stream_out
     cudaStream_t side_stream = nullptr;                 // grad log p runs here, next to the median pass (it only needs X)
@@ -163,6 +166,7 @@ struct svgdb_ctx {
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
+    int host_chunks = 1;  // SVGDB_HOST_CHUNKS=0 (measurement aid): svgdb_step_host moves the particles in one piece each way
 
     // measurement
     svgdb_stats stats{};
@@ -333,6 +337,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_HOST_CHUNKS")) ctx->host_chunks = std::atoi(e);
     return SVGDB_OK;
 }
 #endif
@@ -777,11 +782,20 @@ int launch_dist_operands(svgdb_ctx *ctx)
 {
     using namespace svgdb::tc;
     CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
-    colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->N, ctx->d, ctx->colsum);
-    KERNEL_CHECK();
     const int64_t rows_a = ctx->n_pad128 + 256;
-    split_dist2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->X[ctx->cur], ctx->colsum, ctx->N, rows_a, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
+    // particles still arriving in row chunks (svgdb_step_host): centre on the mean of the first chunk and prepare its rows only,
+    // the other chunks are prepared by the first distance pass as they land (launch_dist_pass_tc32)
+    const int64_t rows_now = ctx->up_chunks > 0 ? (int64_t)ctx->up_ipairs[0] * 256 : ctx->N;
+    const int64_t rows_end = ctx->up_chunks > 0 ? rows_now : rows_a;
+    if (ctx->up_chunks > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
+    colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], rows_now, ctx->d, ctx->colsum);
+    KERNEL_CHECK();
+    if (ctx->up_chunks > 0) {
+        colsum_scale_kernel<<<1, 64, 0, ctx->stream>>>(ctx->colsum, ctx->d, (double)ctx->N / (double)rows_now);
+        KERNEL_CHECK();
+    }
+    split_dist2_kernel<<<(unsigned)((rows_end + 7) / 8), 256, 0, ctx->stream>>>(
+        ctx->X[ctx->cur], ctx->colsum, ctx->N, 0, rows_end, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
         reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
     KERNEL_CHECK();
     return SVGDB_OK;
@@ -805,67 +819,91 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     const float hi_f = key_to_float_ceil(hi);
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
-    // symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks
+    // Symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks.
+    // Particles arriving in row chunks (svgdb_step_host, one rank): the pass is issued in as many launches, launch k covering
+    // the pairs whose later row lies in chunk k, i.e. i-pairs below the chunk's end against the column tiles of the chunk.
     const int n_ipairs_all = (int)((ctx->N + 255) / 256);
-    const int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
-    if (n_ipairs > 0) {
-        Dist2Args b{};
-        b.XA2 = reinterpret_cast<const __nv_bfloat16 *>(ctx->XA2);
-        b.UA = reinterpret_cast<const __nv_bfloat16 *>(ctx->UA2);
-        b.WB = reinterpret_cast<const __nv_bfloat16 *>(ctx->WB2);
-        b.n_total = ctx->N;
-        b.n_jtiles = (int)(ctx->n_pad128 / 128);
-        b.pair_offset = ctx->rank;
-        b.pair_stride = ctx->world;
-        b.n_ipairs = n_ipairs;
-        b.lo_f = lo_f;
-        b.hi_f = hi_f;
-        b.open_low = std::isinf(lo_f) ? 1 : 0;
-        {
-            float wdt = std::isinf(lo_f) || std::isinf(hi_f) ? INFINITY : (float)((double)hi_f - (double)lo_f);
-            if ((double)wdt < (double)hi_f - (double)lo_f) wdt = std::nextafterf(wdt, INFINITY);
-            wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
-            if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
-            uint32_t wb;
-            std::memcpy(&wb, &wdt, 4);
-            b.width_bits = wb;
-            // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
-            float hi_ext = std::isinf(wdt) || std::isinf(lo_f) ? hi_f : (float)((double)lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
-            hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
-            ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
-        }
-        b.lo_key = lo;
-        b.shift = shift;
-        b.below = ctx->below;
-        b.hist = ctx->hist;
-        b.cand = ctx->cand;
-        b.cand_count = ctx->cand_count;
-        b.capacity = ctx->capacity;
-        b.err = ctx->tc_err;
-        b.dbg = ctx->dist_dbg_mode;
-        long long units = 0;
-        for (int l = 0; l < n_ipairs; ++l) units += std::max(0, b.n_jtiles - 2 * (b.pair_offset + b.pair_stride * l));
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
-        if (mode == MODE_HIST) {
-            CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
-            dist2_tc32_kernel<MODE_HIST, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
-        } else {
-            // expected share of pairs inside the bracket (density of the last pass x relative width): with fewer than ~1 hit per
-            // two 32 x 32 warp chunks the gated epilogue (3 instructions per distance + rare collection) is the cheaper one
-            double width_rel = 1.0;
-            if (lo > 0 && hi < KEY_END) {
-                double dlo, dhi;
-                std::memcpy(&dlo, &lo, 8);
-                std::memcpy(&dhi, &hi, 8);
-                if (dhi > 0.0) width_rel = (dhi - dlo) / dhi;
+    const int n_launches = std::max(1, ctx->up_chunks);
+    if (mode == MODE_HIST) CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
+    else CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
+    for (int ch = 0; ch < n_launches; ++ch) {
+        int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
+        int jt_begin = 0, jt_end = (int)(ctx->n_pad128 / 128);
+        if (ctx->up_chunks > 0) {
+            const bool last = ch == ctx->up_chunks - 1;
+            n_ipairs = last ? n_ipairs_all : ctx->up_ipairs[ch];
+            jt_begin = ch == 0 ? 0 : 2 * ctx->up_ipairs[ch - 1];
+            if (!last) jt_end = 2 * ctx->up_ipairs[ch];
+            if (ch > 0) { // this chunk's rows have landed: centre and split them (the last launch also writes the padding rows)
+                using namespace svgdb::tc;
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[ch], 0));
+                const int64_t r0 = (int64_t)ctx->up_ipairs[ch - 1] * 256, r1 = last ? ctx->n_pad128 + 256 : (int64_t)ctx->up_ipairs[ch] * 256;
+                split_dist2_kernel<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
+                    ctx->X[ctx->cur], ctx->colsum, ctx->N, r0, r1, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
+                    reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
+                KERNEL_CHECK();
             }
-            const bool gated = ctx->dist_gated >= 0 ? ctx->dist_gated != 0 : ctx->density * width_rel * 1024.0 < 0.5;
-            CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
-            if (gated) dist2_tc32_kernel<MODE_COLLECT, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
-            else dist2_tc32_kernel<MODE_COLLECT, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
         }
-        KERNEL_CHECK();
+        if (n_ipairs > 0) {
+            Dist2Args b{};
+            b.XA2 = reinterpret_cast<const __nv_bfloat16 *>(ctx->XA2);
+            b.UA = reinterpret_cast<const __nv_bfloat16 *>(ctx->UA2);
+            b.WB = reinterpret_cast<const __nv_bfloat16 *>(ctx->WB2);
+            b.n_total = ctx->N;
+            b.n_jtiles = jt_end;
+            b.jt_begin = jt_begin;
+            b.pair_offset = ctx->rank;
+            b.pair_stride = ctx->world;
+            b.n_ipairs = n_ipairs;
+            b.lo_f = lo_f;
+            b.hi_f = hi_f;
+            b.open_low = std::isinf(lo_f) ? 1 : 0;
+            {
+                float wdt = std::isinf(lo_f) || std::isinf(hi_f) ? INFINITY : (float)((double)hi_f - (double)lo_f);
+                if ((double)wdt < (double)hi_f - (double)lo_f) wdt = std::nextafterf(wdt, INFINITY);
+                wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
+                if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
+                uint32_t wb;
+                std::memcpy(&wb, &wdt, 4);
+                b.width_bits = wb;
+                // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
+                float hi_ext = std::isinf(wdt) || std::isinf(lo_f) ? hi_f : (float)((double)lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
+                hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
+                ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
+            }
+            b.lo_key = lo;
+            b.shift = shift;
+            b.below = ctx->below;
+            b.hist = ctx->hist;
+            b.cand = ctx->cand;
+            b.cand_count = ctx->cand_count;
+            b.capacity = ctx->capacity;
+            b.err = ctx->tc_err;
+            b.dbg = ctx->dist_dbg_mode;
+            long long units = 0;
+            for (int l = 0; l < n_ipairs; ++l) units += std::max(0, b.n_jtiles - std::max(2 * (b.pair_offset + b.pair_stride * l), b.jt_begin));
+            const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
+            if (units <= 0) continue;
+            if (mode == MODE_HIST) {
+                dist2_tc32_kernel<MODE_HIST, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+            } else {
+                // expected share of pairs inside the bracket (density of the last pass x relative width): with fewer than ~1 hit per
+                // two 32 x 32 warp chunks the gated epilogue (3 instructions per distance + rare collection) is the cheaper one
+                double width_rel = 1.0;
+                if (lo > 0 && hi < KEY_END) {
+                    double dlo, dhi;
+                    std::memcpy(&dlo, &lo, 8);
+                    std::memcpy(&dhi, &hi, 8);
+                    if (dhi > 0.0) width_rel = (dhi - dlo) / dhi;
+                }
+                const bool gated = ctx->dist_gated >= 0 ? ctx->dist_gated != 0 : ctx->density * width_rel * 1024.0 < 0.5;
+                if (gated) dist2_tc32_kernel<MODE_COLLECT, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                else dist2_tc32_kernel<MODE_COLLECT, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+            }
+            KERNEL_CHECK();
+        }
     }
+    ctx->up_chunks = 0; // everything has landed and is prepared
     ++ctx->stats.median_passes;
     TRY(kick_grad(ctx));
     TRY(reduce_pass_words(ctx, mode));
@@ -1302,6 +1340,7 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto &e : ctx->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ctx->ev_up) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_med, cudaEventDisableTiming));
@@ -1384,6 +1423,7 @@ void svgdb_destroy(svgdb_ctx *ctx)
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_up) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1599,19 +1639,54 @@ int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int
     TRY(check_ready(ctx));
     if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
     CU(cudaSetDevice(ctx->device));
-    TRY(svgdb_set_particles_rows(ctx, rows_in));
-    for (int64_t it = 0; it + 1 < iters; ++it) TRY(one_step(ctx));
+    cudaPointerAttributes attr{};
+    const bool in_pinned = rows_in && cudaPointerGetAttributes(&attr, rows_in) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int n_ipairs_all = (int)((ctx->N + 255) / 256);
+    bool chunked_upload = false;
+#ifdef SVGDB_WITH_TC32
+    // One rank, tensor-core path, median scale: the first thing a step does is the distance pass over all pairs, and the pairs
+    // among the rows that have already arrived can be counted while the rest is still on the PCIe bus.  The particles go up in
+    // four row chunks on the copy stream; the first distance pass of the step is issued chunk by chunk behind them.
+    chunked_upload = in_pinned && ctx->world == 1 && ctx->precision == SVGDB_PRECISION_TC32 && ctx->scale_method == SVGDB_SCALE_MEDIAN &&
+                     n_ipairs_all >= 32 && ctx->host_chunks != 0;
+#endif
+    if (chunked_upload) {
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream)); // whatever still reads or writes X[cur] on the main stream comes first
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+        int64_t r0 = 0;
+        for (int ch = 0; ch < 4; ++ch) {
+            ctx->up_ipairs[ch] = ch == 3 ? n_ipairs_all : (n_ipairs_all * (ch + 1)) / 4;
+            const int64_t r1 = std::min<int64_t>((int64_t)ctx->up_ipairs[ch] * 256, ctx->N);
+            CU(cudaMemcpyAsync(ctx->X[ctx->cur] + (size_t)r0 * ctx->d, rows_in + (size_t)r0 * ctx->d, (size_t)(r1 - r0) * ctx->d * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_up[ch], ctx->copy_stream));
+            r0 = r1;
+        }
+        ctx->up_chunks = 4;
+    } else {
+        TRY(svgdb_set_particles_rows(ctx, rows_in));
+    }
+    for (int64_t it = 0; it + 1 < iters; ++it) {
+        const int rc = one_step(ctx);
+        if (rc != SVGDB_OK) {
+            ctx->up_chunks = 0;
+            cudaStreamSynchronize(ctx->copy_stream);
+            return rc;
+        }
+    }
     // The last iteration hands its rows to the host as they are finished -- from pinned memory only: a copy into pageable
     // memory blocks the launching thread, which would hold back the launches of the remaining row chunks.
-    cudaPointerAttributes attr{};
-    const bool pinned = rows_out && cudaPointerGetAttributes(&attr, rows_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaPointerAttributes attr_out{};
+    const bool pinned = rows_out && cudaPointerGetAttributes(&attr_out, rows_out) == cudaSuccess && attr_out.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    ctx->stream_out = pinned ? rows_out : nullptr;
+    ctx->stream_out = pinned && ctx->host_chunks != 0 ? rows_out : nullptr;
     ctx->streamed = false;
     const int rc = one_step(ctx);
     ctx->stream_out = nullptr;
+    ctx->up_chunks = 0;
     if (rc != SVGDB_OK) {
-        cudaStreamSynchronize(ctx->copy_stream); // nothing may still be writing into the caller's buffer
+        cudaStreamSynchronize(ctx->copy_stream); // nothing may still be reading or writing the caller's buffers
         return rc;
     }
     if (ctx->streamed) {
