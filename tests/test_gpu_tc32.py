@@ -204,3 +204,30 @@ def test_tc32_step_host_streams_rows(sv, oracle, order):
         assert np.all(np.isfinite(X)) and err < 1e-3
     # the unchunked paths differ only in the order of the float partial sums
     assert np.sqrt(np.mean((results[2] - results[0]) ** 2)) / np.sqrt(np.mean(ref ** 2)) < 1e-6
+
+
+def test_tc32_chunked_distance_pass_counts_every_pair(sv, oracle, monkeypatch):
+    """The first distance pass of svgdb_step_host is issued in four launches behind the arriving row chunks.  A tile left out or
+    counted twice would move the median's rank by thousands of pairs, i.e. the scale by > 4e-5 at this size: the scale of a
+    single step must agree with the oracle to 3e-6, with the candidate buffer large (one collecting pass) and small
+    (histogram narrowing passes first, which are chunked the same way)."""
+    import ctypes as C
+
+    n, d = 9001, 64
+    for capacity in (None, 4096):
+        if capacity is not None:
+            monkeypatch.setenv("SVGDB_CAND_CAPACITY", str(capacity))
+        svgd, x0, mu, cov = _setup(sv, n, d, seed=33)
+        lib, ctx = svgd._lib, svgd._ctx
+        svgd.Initialize()
+        X = np.array(x0.T, order="C", copy=True)
+        svgd._host[...] = X
+        ptr = svgd._host.ctypes.data_as(C.POINTER(C.c_double))
+        for call in range(3):  # the first call has no bracket prediction (histogram pass first), the later ones collect straight away
+            a_ref = oracle.rbf_median_scale(svgd._host)
+            assert lib.svgdb_step_host(ctx, ptr, ptr, 1) == 0, lib.svgdb_last_error(ctx)
+            st = svgd.Stats()
+            print("capacity %s, call %d: a rel err %.3g (%d distance passes so far, %d bracket hits)"
+                  % (capacity, call, abs(st["last_scale"] - a_ref) / a_ref, st["median_passes"], st["median_bracket_hits"]))
+            assert abs(st["last_scale"] - a_ref) <= 3e-6 * a_ref
+        svgd.close()
