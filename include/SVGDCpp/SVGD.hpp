@@ -9,6 +9,8 @@
 #define SVGDCPP_B200_SVGD_HPP
 
 #include <cmath>
+#include <fstream>
+#include <sstream>
 
 #include "Core.hpp"
 #include "Kernel/Kernel.hpp"
@@ -26,7 +28,7 @@ struct SVGDOptions {
     Eigen::VectorXd UpperBound = Eigen::VectorXd::Constant(1, INFINITY);
     std::string IntermediateMatricesOutputPath = "log.txt";
     bool Parallel = false;               /* accepted; the device path is always parallel */
-    bool LogIntermediateMatrices = false; /* K and grad K are never materialised: not supported */
+    bool LogIntermediateMatrices = false; /* inspection path: K and grad K are formed on demand, one step at a time (small n) */
     int Device = 0;                                  /* CUDA device ordinal */
     int PrecisionMode = SVGDB_PRECISION_F64;         /* svgdb_precision */
     SVGDOptions() {}
@@ -47,9 +49,9 @@ public:
          const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const Eigen::VectorXd &bound_lower,
          const Eigen::VectorXd &bound_upper, const bool &parallel = false, const bool &log_intermediate_matrices = false,
          const std::string &intermediate_matrices_output_path = "log.txt", int device = 0, int precision_mode = SVGDB_PRECISION_F64)
-        : num_iterations_(iter), parallel_(parallel)
+        : num_iterations_(iter), parallel_(parallel), log_intermediate_matrices_(log_intermediate_matrices),
+          intermediate_matrices_output_path_(intermediate_matrices_output_path)
     {
-        (void)intermediate_matrices_output_path;
         if (!coord_mat_ptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid coordinate matrix pointer.");
         dimension_ = static_cast<int>(coord_mat_ptr->rows());
         if (dimension_ != static_cast<int>(dim))
@@ -72,8 +74,6 @@ public:
         if (kernel_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Kernel object pointer.");
         if (model_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Model object pointer.");
         if (optimizer_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Optimizer object pointer.");
-        if (log_intermediate_matrices)
-            throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] LogIntermediateMatrices needs the n x n kernel matrices, which the device path never forms.");
 
         int rc = svgdb_create(&ctx_, device, static_cast<int64_t>(coord_matrix_ptr_->cols()), dimension_, precision_mode);
         if (rc != SVGDB_OK) {
@@ -128,7 +128,32 @@ public:
         model_ptr_->Upload(ctx_);
     }
 
-    void Run() { Step(num_iterations_); }
+    void Run()
+    {
+        if (!log_intermediate_matrices_) {
+            Step(num_iterations_);
+            return;
+        }
+        /* Reference Run() with LogIntermediateMatrices (:338-366): after every step, the gradient / kernel / kernel-gradient matrices
+         * that step used and the updated coordinates, in Eigen's default text format.  The device step never forms the n x n
+         * matrices, so they are computed on demand from the pre-step particles (svgdb_compute_kernel_matrices; small n only). */
+        const Eigen::Index n = coord_matrix_ptr_->cols();
+        std::ostringstream log;
+        for (size_t iter = 0; iter < num_iterations_; ++iter) {
+            Eigen::MatrixXd grad(dimension_, n), kernel(n, n), kernel_grad(n * dimension_, n);
+            Check(svgdb_set_particles(ctx_, coord_matrix_ptr_->data()));
+            Check(svgdb_compute_log_model_grad(ctx_, grad.data()));
+            Check(svgdb_compute_kernel_matrices(ctx_, kernel.data(), kernel_grad.data(), nullptr));
+            Step(1);
+            log << "========== Step " << iter + 1 << " =========="
+                << "\nLogModelGrad=\n" << grad << "\n\nKernel=\n" << kernel << "\n\nKernelGrad=\n" << kernel_grad << "\n\nCoordMat=\n"
+                << *coord_matrix_ptr_ << "\n\n";
+        }
+        std::ofstream output_file(intermediate_matrices_output_path_);
+        if (!output_file)
+            throw std::runtime_error(SVGDCPP_LOG_PREFIX + "[Runtime Error] Cannot open " + intermediate_matrices_output_path_ + " for writing.");
+        output_file << log.str();
+    }
 
     /* `iters` SVGD steps on the device; the coordinate matrix is read before and written after. */
     void Step(size_t iters = 1)
@@ -156,6 +181,8 @@ protected:
     int dimension_ = -1;
     size_t num_iterations_;
     const bool parallel_ = false;
+    bool log_intermediate_matrices_ = false;
+    std::string intermediate_matrices_output_path_ = "log.txt";
     bool check_bounds_ = false;
     std::shared_ptr<Kernel> kernel_ptr_;
     std::shared_ptr<Model> model_ptr_;

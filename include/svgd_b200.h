@@ -144,6 +144,12 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out);
  * A = 1/(2 d n) sum_i -Hessian(log p)(x_i) (GaussianRBFKernel.hpp:189-210), which must be positive definite. */
 int svgdb_get_scale_matrix(svgdb_ctx *ctx, double *A_dxd);
 
+/* The matrices SVGDOptions::LogIntermediateMatrices prints (SVGD.hpp:346-365; filled in ComputePhi, :407-454), for the current X and
+ * the scale Kernel::Step would compute from it: K is n x n column-major with K(j, i) = k(x_j, x_i); gradK is (n d) x n column-major
+ * with the block (j d .. j d + d, i) = grad_x k(x, x_i) at x = x_j.  An inspection path: one rank, n^2 (d + 1) doubles <= 2 GiB; the
+ * step itself never forms these matrices.  scale_out (may be NULL) receives the scale (A(0,0) for the Hessian method). */
+int svgdb_compute_kernel_matrices(svgdb_ctx *ctx, double *K_nxn, double *gradK_ndxn, double *scale_out);
+
 /* Model::EvaluateLogModelGrad for every particle (Model/Model.hpp:335-338): G is d x N. */
 int svgdb_compute_log_model_grad(svgdb_ctx *ctx, double *G_dxN);
 

@@ -59,6 +59,8 @@ def lib():
         L.oracle_rbf_hessian_scale.argtypes = [_dp, C.c_long, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
         L.oracle_phi_matrix.argtypes = [_dp, _dp, C.c_long, C.c_int, _dp, _dp]
         L.oracle_phi_matrix.restype = None
+        L.oracle_kernel_matrices.argtypes = [_dp, C.c_long, C.c_int, _dp, _dp, _dp]
+        L.oracle_kernel_matrices.restype = None
         L.oracle_opt_step.argtypes = [C.c_int, C.c_size_t, _dp, C.c_double, C.c_double, C.c_double,
                                       C.c_double, C.POINTER(C.c_uint64), _dp, _dp, _dp]
         L.oracle_opt_step.restype = None
@@ -138,6 +140,17 @@ def phi_matrix(X, G, A):
     out = np.empty_like(X)
     lib().oracle_phi_matrix(_p(X), _p(G), n, d, _p(A), _p(out))
     return out
+
+
+def kernel_matrices(X, A):
+    """kernel_matrix_ (n x n, [i, j] = k(x_j, x_i)) and kernel_grad_matrix_ ([i, j, :] = grad k(x_j, x_i)) of SVGD::ComputePhi."""
+    X = _f64(X)
+    n, d = X.shape
+    A = _f64(np.asarray(A, dtype=np.float64) * np.eye(d) if np.ndim(A) == 0 else A)
+    K = np.empty((n, n))
+    dK = np.empty((n, n, d))
+    lib().oracle_kernel_matrices(_p(X), n, d, _p(A), _p(K), _p(dK))
+    return K, dK
 
 
 def phi(X, G, a):

@@ -302,6 +302,32 @@ void oracle_phi_matrix(const double *X, const double *G, long n, int d, const do
     }
 }
 
+void oracle_kernel_matrices(const double *X, long n, int d, const double *A, double *K, double *dK)
+{
+    /* SVGD.hpp:434-448: kernel_matrix_(j, i) = k(x_j, x_i), kernel_grad_matrix_.block(j d, i, d, 1) = grad k(x_j, x_i), with the
+     * kernel located at x_i (Kernel/GaussianRBFKernel.hpp:75-81): k = exp(-diff^T A diff), grad = -(A + A^T) diff k. */
+    double *df = (double *)malloc(sizeof(double) * d);
+    for (long i = 0; i < n; ++i) {
+        for (long j = 0; j < n; ++j) {
+            double q = 0.0;
+            for (int k = 0; k < d; ++k) df[k] = X[j * d + k] - X[i * d + k];
+            for (int r = 0; r < d; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < d; ++k) s += A[r * d + k] * df[k];
+                q += df[r] * s;
+            }
+            double kv = exp(-q);
+            K[i * n + j] = kv;
+            for (int r = 0; r < d; ++r) {
+                double s = 0.0, st = 0.0;
+                for (int k = 0; k < d; ++k) { s += A[r * d + k] * df[k]; st += A[k * d + r] * df[k]; }
+                dK[(i * n + j) * d + r] = -(s + st) * kv;
+            }
+        }
+    }
+    free(df);
+}
+
 void oracle_opt_step(int kind, size_t count, const double *phi, double lr, double beta1,
                      double beta2, double eps, uint64_t *counter, double *s1, double *s2,
                      double *delta)

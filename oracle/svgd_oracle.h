@@ -70,6 +70,10 @@ int oracle_rbf_hessian_scale(const double *X, long n, int d, int C, const double
  * grad_x k = -(A + A^T)(x - x') k  (Kernel/GaussianRBFKernel.hpp:75-81 taped by CppAD). */
 void oracle_phi_matrix(const double *X, const double *G, long n, int d, const double *A, double *phi);
 
+/* The intermediate matrices of SVGD::ComputePhi (SVGD.hpp:434-448) that SVGDOptions::LogIntermediateMatrices prints (:346-365):
+ * K[i n + j] = kernel_matrix_(j, i), dK[(i n + j) d + c] = kernel_grad_matrix_(j d + c, i); A is the d x d scale matrix. */
+void oracle_kernel_matrices(const double *X, long n, int d, const double *A, double *K, double *dK);
+
 /* Optimizer increments (the driver ADDS the result, SVGD.hpp:393).
  * Optimizer/Adam.hpp:75-96, AdaGrad.hpp:60-65, RMSProp.hpp:69-74.
  * state1 = sum of squares / 2nd moment, state2 = 1st moment (Adam only). */

@@ -177,4 +177,35 @@ inline unsigned row_times_matrix_blocks(int64_t n_rows, int d)
     return (unsigned)((((n_rows + 7) / 8) * cols + 255) / 256);
 }
 
+// Inspection path of SVGDOptions::LogIntermediateMatrices (SVGD.hpp:346-365, 407-454): the n x n kernel matrix and its gradients
+// in the reference's own layouts, for small n.  One thread per pair (j, i):
+//   K[i n + j] = k(x_j, x_i) = exp(-(x_j - x_i)^T A (x_j - x_i))              == kernel_matrix_(j, i), column-major
+//   dK[(i n + j) d + c] = -((A + A^T)(x_j - x_i))_c k(x_j, x_i)               == kernel_grad_matrix_(j d + c, i), column-major
+// (A = a I for the scalar scales).  The hot path never forms either matrix.
+__global__ void kernel_matrices_f64_kernel(const double *__restrict__ X, int64_t n, int d, const double *__restrict__ A, double *__restrict__ K,
+                                           double *__restrict__ dK)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int64_t i = idx / n, j = idx - i * n;
+    const double *xi = X + i * d, *xj = X + j * d;
+    double q = 0.0;
+    for (int r = 0; r < d; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) s += A[(size_t)r * d + k] * (xj[k] - xi[k]);
+        q += (xj[r] - xi[r]) * s;
+    }
+    const double kv = exp(-q);
+    K[idx] = kv;
+    for (int r = 0; r < d; ++r) {
+        double s = 0.0, st = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double df = xj[k] - xi[k];
+            s += A[(size_t)r * d + k] * df;
+            st += A[(size_t)k * d + r] * df;
+        }
+        dK[idx * d + r] = -(s + st) * kv;
+    }
+}
+
 } // namespace svgdb

@@ -1775,6 +1775,43 @@ int svgdb_compute_log_model_grad(svgdb_ctx *ctx, double *G)
     return SVGDB_OK;
 }
 
+int svgdb_compute_kernel_matrices(svgdb_ctx *ctx, double *K, double *gradK, double *scale_out)
+{
+    if (!ctx || !K || !gradK) return fail(ctx, SVGDB_ERR_INVALID, "null output");
+    if (!ctx->kernel_set) return fail(ctx, SVGDB_ERR_UNSET, "Kernel function is unset.");
+    if (ctx->world > 1) return fail(ctx, SVGDB_ERR_INVALID, "the kernel matrices are an inspection aid for one rank");
+    const int64_t n = ctx->N;
+    const int d = ctx->d;
+    const double bytes = (double)n * (double)n * (double)(d + 1) * 8.0;
+    if (bytes > 2147483648.0)
+        return fail(ctx, SVGDB_ERR_DIMENSION, "kernel matrices of " + std::to_string(n) + " particles in " + std::to_string(d) +
+                                                   " dimensions exceed the 2 GiB limit of this inspection path");
+    double a = 0.0;
+    TRY(svgdb_compute_scale(ctx, &a)); // the scale Kernel::Step would compute from the current particles
+    std::vector<double> A((size_t)d * d, 0.0);
+    if (ctx->scale_method == SVGDB_SCALE_HESSIAN) A = ctx->A_host;
+    else
+        for (int r = 0; r < d; ++r) A[(size_t)r * d + r] = a;
+    double *A_dev = nullptr, *K_dev = nullptr, *dK_dev = nullptr;
+    int rc = SVGDB_OK;
+    do {
+        if (cudaMalloc(&A_dev, A.size() * 8) != cudaSuccess || cudaMalloc(&K_dev, (size_t)n * n * 8) != cudaSuccess ||
+            cudaMalloc(&dK_dev, (size_t)n * n * d * 8) != cudaSuccess) {
+            rc = fail(ctx, SVGDB_ERR_NOMEM, "out of device memory for the kernel matrices");
+            break;
+        }
+        if (cudaMemcpyAsync(A_dev, A.data(), A.size() * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = fail(ctx, SVGDB_ERR_CUDA, "copy failed"); break; }
+        kernel_matrices_f64_kernel<<<(unsigned)((n * n + 127) / 128), 128, 0, ctx->stream>>>(ctx->X[ctx->cur], n, d, A_dev, K_dev, dK_dev);
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(ctx, SVGDB_ERR_CUDA, "kernel_matrices_f64_kernel launch failed"); break; }
+        cudaMemcpyAsync(K, K_dev, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(gradK, dK_dev, (size_t)n * n * d * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, SVGDB_ERR_CUDA, "kernel matrices: " + std::string(cudaGetErrorString(cudaGetLastError()))); break; }
+    } while (false);
+    cudaFree(A_dev); cudaFree(K_dev); cudaFree(dK_dev);
+    if (rc == SVGDB_OK && scale_out) *scale_out = a;
+    return rc;
+}
+
 int svgdb_get_opt_state(svgdb_ctx *ctx, double *s1, double *s2, uint64_t *counter)
 {
     if (!ctx) return SVGDB_ERR_INVALID;

@@ -184,6 +184,14 @@ class RMSProp(Optimizer):  # Optimizer/RMSProp.hpp:33-46
 
 
 # ---- driver -------------------------------------------------------------------------------------
+def _eigen_str(M):
+    """Eigen's default operator<< for a matrix: 6 significant digits, columns right-aligned to the widest entry."""
+    M = np.atleast_2d(np.asarray(M, dtype=np.float64))
+    cells = [["%.6g" % v for v in row] for row in M]
+    width = max(len(c) for row in cells for c in row)
+    return "\n".join(" ".join(c.rjust(width) for c in row) for row in cells)
+
+
 class SVGDOptions:  # SVGD.hpp:27-52 (+ device / precision / sharding fields with defaults)
     def __init__(self):
         self.Dimension = 0
@@ -240,8 +248,8 @@ class SVGD:
             raise ValueError("SVGDCpp: [Argument Error] Invalid Model object pointer.")
         if optimizer is None:
             raise ValueError("SVGDCpp: [Argument Error] Invalid Optimizer object pointer.")
-        if log_intermediate_matrices:
-            raise NotImplementedError("LogIntermediateMatrices: K and grad K are never materialised on the device path")
+        self.log_intermediate_matrices_ = bool(log_intermediate_matrices)
+        self.intermediate_matrices_output_path_ = intermediate_matrices_output_path
         self.kernel_, self.model_, self.optimizer_ = kernel, model, optimizer
 
         rc = self._lib.svgdb_create(C.byref(self._ctx), int(device), self.num_particles_, self.dimension_, int(precision))
@@ -322,7 +330,32 @@ class SVGD:
         self.coord_matrix_[...] = self._host.T
 
     def Run(self):  # SVGD.hpp:338-366
-        self.Step(self.num_iterations_)
+        if not self.log_intermediate_matrices_:
+            self.Step(self.num_iterations_)
+            return
+        # LogIntermediateMatrices: one step at a time, the matrices of that step formed on demand (inspection path, small n)
+        chunks = []
+        for it in range(self.num_iterations_):
+            G = self.EvaluateLogModelGrad()
+            K, dK = self.ComputeKernelMatrices()
+            self.Step(1)
+            chunks.append("========== Step %d ==========\nLogModelGrad=\n%s\n\nKernel=\n%s\n\nKernelGrad=\n%s\n\nCoordMat=\n%s\n\n"
+                          % (it + 1, _eigen_str(G), _eigen_str(K), _eigen_str(dK), _eigen_str(self.coord_matrix_)))
+        try:
+            with open(self.intermediate_matrices_output_path_, "w") as f:
+                f.write("".join(chunks))
+        except OSError:
+            raise RuntimeError("SVGDCpp: [Runtime Error] Cannot open %s for writing." % self.intermediate_matrices_output_path_)
+
+    def ComputeKernelMatrices(self):
+        """kernel_matrix_ (n x n, [j, i] = k(x_j, x_i)) and kernel_grad_matrix_ ((n dim) x n, rows j dim .. j dim + dim of column i =
+        grad k(x_j, x_i)) of SVGD::ComputePhi (SVGD.hpp:434-448) for the current particles; small n only."""
+        self._upload()
+        n, d = self.num_particles_, self.dimension_
+        K = np.empty((n, n))          # C order [i, j] == Eigen column-major (j, i)
+        dK = np.empty((n, n * d))     # C order [i, j d + c] == Eigen column-major (j d + c, i)
+        self._check(self._lib.svgdb_compute_kernel_matrices(self._ctx, _ptr(K), _ptr(dK), None))
+        return K.T.copy(), dK.T.copy()
 
     # -- extras used by tests / bench ---------------------------------------------------------------
     def ComputePhi(self):

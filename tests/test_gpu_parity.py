@@ -266,6 +266,68 @@ def test_hessian_scale(sv, oracle):
         assert _rel(x0.T, ref) < FINAL_RTOL
 
 
+@pytest.mark.parametrize("method", ["median", "hessian", "fixed"])
+def test_kernel_matrices_match_oracle(sv, oracle, method):
+    """svgdb_compute_kernel_matrices (the matrices behind SVGDOptions::LogIntermediateMatrices, SVGD.hpp:434-448) against the oracle,
+    and the reference's own assembly of phi from them (SVGD.hpp:453) against ComputePhi."""
+    n, d = 37, 5
+    rng = np.random.default_rng(17)
+    cov = (lambda M: M @ M.T / d + 0.7 * np.eye(d))(rng.standard_normal((d, d)))
+    mu = 0.3 * rng.standard_normal(d)
+    x0 = np.asfortranarray(1.1 * rng.standard_normal((d, n)))
+    X = np.array(x0.T, order="C", copy=True)
+    model = sv.MultivariateNormal(mu, cov)
+    scale = {"median": sv.ScaleMethod.Median, "hessian": sv.ScaleMethod.Hessian, "fixed": sv.ScaleMethod.Median}[method]
+    kernel = sv.GaussianRBFKernel(x0, scale, model)
+    svgd = sv.SVGD(d, 1, x0, kernel, model, sv.AdaGrad(d, n, 0.1))
+    if method == "fixed":
+        svgd.UpdateKernelParameters([0.37 * np.eye(d)])
+    K, dK = svgd.ComputeKernelMatrices()          # Eigen layouts: K[j, i], dK[j d + c, i]
+    A = {"median": lambda: oracle.rbf_median_scale(X) * np.eye(d), "fixed": lambda: 0.37 * np.eye(d),
+         "hessian": lambda: oracle.rbf_hessian_scale(X, mu[None], cov[None])}[method]()
+    K_ref, dK_ref = oracle.kernel_matrices(X, A)
+    assert _rel(K, K_ref.T) < 1e-12
+    assert _rel(dK, dK_ref.reshape(n, n * d).T) < 1e-12
+    G = svgd.EvaluateLogModelGrad()
+    indexer = np.tile(np.eye(d), (1, n))          # kernel_grad_indexer_ (SVGD.hpp:250)
+    phi_assembled = (G @ K + indexer @ dK) / n
+    phi, _ = svgd.ComputePhi()
+    assert _rel(phi_assembled, phi) < 1e-11
+    svgd.close()
+
+
+def test_kernel_matrices_size_limit(sv):
+    """The inspection path refuses sizes whose matrices would not fit its 2 GiB budget."""
+    n, d = 2200, 64  # 2200^2 x 65 doubles = 2.5 GB
+    x0 = np.zeros((d, n), order="F")
+    model = sv.MultivariateNormal(np.zeros(d), np.eye(d))
+    svgd = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1))
+    with pytest.raises(sv.DimensionMismatchException, match="2 GiB"):
+        svgd.ComputeKernelMatrices()
+    svgd.close()
+
+
+def test_python_log_intermediate_matrices(sv, oracle, tmp_path):
+    """LogIntermediateMatrices through the Python mirror writes the reference's text layout."""
+    n, d = 5, 2
+    rng = np.random.default_rng(2)
+    x0 = np.asfortranarray(rng.standard_normal((d, n)))
+    model = sv.MultivariateNormal(np.zeros(d), np.eye(d))
+    path = tmp_path / "log.txt"
+    svgd = sv.SVGD(d, 2, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999),
+                   log_intermediate_matrices=True, intermediate_matrices_output_path=str(path))
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    text = path.read_text()
+    assert text.startswith("========== Step 1 ==========\nLogModelGrad=\n") and "========== Step 2 ==========" in text
+    for name in ("\n\nKernel=\n", "\n\nKernelGrad=\n", "\n\nCoordMat=\n"):
+        assert text.count(name) == 2
+    last = text.rstrip("\n").split("CoordMat=\n")[-1]
+    printed = np.array([[float(t) for t in line.split()] for line in last.splitlines()])
+    assert np.allclose(printed, x0, rtol=1e-5, atol=1e-6)
+
+
 def test_hessian_scale_rejects_indefinite_matrix(sv):
     """Far-apart components make the mean negative Hessian indefinite: the device path reports it instead of running a kernel that
     is not positive definite (the reference would go on with exp(-d^T A d) > 1)."""

@@ -162,3 +162,20 @@ def test_hessian_scale_closed_form_matches_finite_differences(oracle):
     assert np.max(np.abs(oracle.rbf_hessian_scale(X, means[:1], covs[:1]) - np.linalg.inv(covs[0]) / (2 * d))) < 1e-14
     G = oracle.mvn_sum_logp_grad(X, means, covs, lse=True)
     assert np.max(np.abs(oracle.phi_matrix(X, G, 0.37 * np.eye(d)) - oracle.phi(X, G, 0.37))) < 1e-15
+
+
+def test_oracle_kernel_matrices_assemble_phi(oracle):
+    """The oracle's kernel / kernel-gradient matrices (SVGD.hpp:434-448), pushed through the reference's own assembly
+    phi = (G K + indexer dK) / n (SVGD.hpp:453), give the oracle's phi: scalar and matrix scale."""
+    n, d = 23, 4
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((n, d))
+    G = rng.standard_normal((n, d))
+    M = rng.standard_normal((d, d))
+    for A, phi_ref in ((0.6 * np.eye(d), oracle.phi(X, G, 0.6)), (M @ M.T / d + 0.3 * np.eye(d), None)):
+        K, dK = oracle.kernel_matrices(X, A)      # K[i, j] = k(x_j, x_i); dK[i, j, :] = grad k(x_j, x_i)
+        phi = (np.einsum("ij,jc->ic", K, G) + dK.sum(axis=1)) / n
+        if phi_ref is None:
+            phi_ref = oracle.phi_matrix(X, G, A)
+        assert np.max(np.abs(phi - phi_ref)) <= 1e-13 * np.max(np.abs(phi_ref))
+        assert np.allclose(np.diag(K), 1.0) and np.allclose(K, K.T)
