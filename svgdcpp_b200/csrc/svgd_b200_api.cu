@@ -1409,6 +1409,8 @@ void svgdb_destroy(svgdb_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     free_sharded(ctx);
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
