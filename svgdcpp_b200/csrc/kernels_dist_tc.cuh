@@ -145,6 +145,9 @@ __device__ __forceinline__ long long d2_total_units(const Dist2Args &p)
     return tot;
 }
 
+// MODE_HIST, GATED = true selects 32-bit shared counters (native ATOMS.ADD; the 64-bit shared add is a compare-and-swap loop,
+// 4x slower under the contention of a pass whose distances share a few bins): valid while a CTA sees fewer than 2^32 weighted
+// pairs, which the launcher checks.
 // GATED: the bracket is expected to hold so few distances that most 32 x 32 chunks contain none -- count and test with 3
 // instructions per distance and take the collecting path only for chunks where some lane saw a hit.
 template <int MODE, bool GATED>
@@ -169,6 +172,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     uint64_t *seg_done = a_ready + 2;       // [2] every MMA of the segment on tile w complete (commit)
     uint32_t *tmem_holder = (uint32_t *)(seg_done + 2);
     unsigned long long *shist = (unsigned long long *)wbuf; // [HIST_BINS] 64-bit (a CTA sees > 2^32 pairs at N = 1M); MODE_HIST only: aliases the warp staging buffers
+    unsigned int *shist32 = (unsigned int *)wbuf;           // [HIST_BINS] the 32-bit variant
+    constexpr bool HIST32 = MODE == MODE_HIST && GATED;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -178,7 +183,10 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
         fence_barrier_init();
     }
     if (MODE == MODE_HIST)
-        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) shist[b] = 0ull;
+        for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) {
+            if (HIST32) shist32[b] = 0u;
+            else shist[b] = 0ull;
+        }
     if (warp == D2_CWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
@@ -274,10 +282,22 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
             const unsigned int tot = __reduce_add_sync(0xffffffffu, mine);
             if (tot) { // warp-uniform
                 if (MODE == MODE_HIST) {
+                    // consecutive entries of a thread mostly share a bin while the range is still wide: one add per run
+                    unsigned int run_bin = 0xffffffffu, run_cnt = 0u;
+                    auto flush_run = [&]() {
+                        if (run_cnt) {
+                            if (HIST32) atomicAdd(&shist32[run_bin], run_cnt);
+                            else atomicAdd(&shist[run_bin], (unsigned long long)run_cnt);
+                        }
+                    };
                     for (uint32_t e = 0; e < mine; ++e) {
                         const unsigned long long bin = (dist_key(lds_f32(priv_base + 128u * e)) - p.lo_key) >> p.shift;
-                        if (bin < (unsigned long long)HIST_BINS) atomicAdd(&shist[(unsigned int)bin], (unsigned long long)cur_wgt); // the collected range may end just past hi
+                        if (bin < (unsigned long long)HIST_BINS) { // the collected range may end just past hi
+                            if ((unsigned int)bin == run_bin) run_cnt += cur_wgt;
+                            else { flush_run(); run_bin = (unsigned int)bin; run_cnt = cur_wgt; }
+                        }
                     }
+                    flush_run();
                 } else {
                     if (count + tot * cur_wgt > (unsigned int)TC_WBUF) { dist_flush2(mybuf, count, p.cand, p.cand_count, p.capacity); count = 0; }
                     if (tot * cur_wgt > (unsigned int)TC_WBUF) { // more than an empty buffer holds: straight to global
@@ -398,7 +418,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     if (p.dbg == 2) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) cnt4[q & 3] += __float_as_uint(__uint_as_float(r0[q]) - lo) >> 31;
-                    } else if (GATED && !open_low) {
+                    } else if (GATED && MODE == MODE_COLLECT && !open_low) {
                         // t = d2 - lo; count += sign(t); flag |= bits(t) <u bits(width): FADD, LEA.HI, ISETP.OR per distance
                         unsigned int flag;
 #define D2_F4(a, b, c, d)                                                                                                          \
@@ -464,7 +484,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     __syncthreads();
     if (MODE == MODE_HIST)
         for (int b = threadIdx.x; b < HIST_BINS; b += blockDim.x) {
-            unsigned long long cc = shist[b];
+            const unsigned long long cc = HIST32 ? (unsigned long long)shist32[b] : shist[b];
             if (cc) atomicAdd(&p.hist[b], cc);
         }
     if (warp == D2_CWARPS) tmem_dealloc(tmem, 512);

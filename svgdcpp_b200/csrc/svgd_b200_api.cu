@@ -648,12 +648,21 @@ int finish_median(svgdb_ctx *ctx)
     ctx->stats.last_scale = ctx->hs->med.scale;
     {
         const double m_now = 0.5 * (ctx->hs->med.d2_lo + ctx->hs->med.d2_hi);
+        bool jump = false;
         if (ctx->last_pred > 0.0 && m_now > 0.0) {
             ctx->resid[1] = ctx->resid[0];
             ctx->resid[0] = std::fabs(m_now - ctx->last_pred) / m_now;
             // 4x the worse of the two most recent extrapolation errors, never below 2e-5
             ctx->delta = std::min(delta_max, std::max(2e-5, 4.0 * std::max(ctx->resid[0], ctx->resid[1])));
+            // An extrapolation that is off by more than 5 % did not meet a smooth trajectory but a new particle set (the host
+            // replaced the particles): the old medians say nothing about the next one, start the history over.
+            jump = ctx->n_hist >= 2 && ctx->resid[0] > 0.05;
         } else {
+            ctx->delta = std::min(delta_max, 1e-3);
+        }
+        if (jump) {
+            ctx->n_hist = 0;
+            ctx->resid[0] = ctx->resid[1] = 0.0;
             ctx->delta = std::min(delta_max, 1e-3);
         }
         ctx->med_hist[3] = ctx->med_hist[2];
@@ -885,7 +894,10 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
             if (units <= 0) continue;
             if (mode == MODE_HIST) {
-                dist2_tc32_kernel<MODE_HIST, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                // a unit is 256 x 128 pairs of weight <= 2: 32-bit shared counters while a CTA's share stays below 2^32
+                const bool hist32 = (units / grid + 1) * 65536ll < 4294967296ll;
+                if (hist32) dist2_tc32_kernel<MODE_HIST, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                else dist2_tc32_kernel<MODE_HIST, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
             } else {
                 // expected share of pairs inside the bracket (density of the last pass x relative width): with fewer than ~1 hit per
                 // two 32 x 32 warp chunks the gated epilogue (3 instructions per distance + rare collection) is the cheaper one
@@ -1380,6 +1392,7 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         SVGDB_PHI2_ATTR(8)
 #undef SVGDB_PHI2_ATTR
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
+        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
         CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
     }
@@ -1620,6 +1633,11 @@ int svgdb_initialize(svgdb_ctx *ctx)
     CU(cudaMemsetAsync(ctx->s2, 0, local, ctx->stream));
     ctx->counter = 0;
     ctx->initialized = true;
+    // a new run: the medians of the previous one do not predict this one's
+    TRY(finish_median(ctx));
+    ctx->n_hist = 0;
+    ctx->resid[0] = ctx->resid[1] = 0.0;
+    ctx->last_pred = 0.0;
     return SVGDB_OK;
 }
 
