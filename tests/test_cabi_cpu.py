@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -113,3 +114,15 @@ def test_bracket_predictor_order_on_recorded_trajectory():
     transient_q, transient_c = np.median(quad[2:22]), np.median(cub[1:21])            # steps 5..25
     assert transient_c < 0.3 * transient_q, (transient_q, transient_c)
     assert np.median(cub[60:]) < 2e-5
+
+
+def test_eigen_text_format_of_the_python_mirror():
+    """The Python mirror prints matrices the way Eigen's operator<< does (6 significant digits, right-aligned to the widest
+    entry): the published stdout block of the reference's mvn example (examples/README.md:7-12) is the known answer."""
+    from helpers import load_golden
+    from svgdcpp_b200.svgd import _eigen_str
+
+    g = load_golden("mvn_example")
+    init = np.array(g["initial"]).T
+    assert _eigen_str(init) == ("  2.04113    1.6986   2.46988 -0.988663  -1.33335 -0.135618 -0.811293   2.71338   0.81427  -2.15038\n"
+                                "-0.633702   1.79064  -1.81469   1.60938   0.32382  0.773226 0.0804055   2.49717   1.30378  0.641813")
