@@ -58,6 +58,32 @@ public:
     int Dimension() const { return dimension_; }
     bool IsSet() const { return hook_ != nullptr || !model_parameters_.empty(); }
 
+    /* Point evaluations of the reference's Model (Model.hpp:290-338).  They run on the device like everything else: a
+     * one-particle context is created for the call (an inspection aid, not a fast path; the values of all particles of a run come
+     * from svgdb_compute_log_model / svgdb_compute_log_model_grad).  log p goes through log-sum-exp, so it stays finite where the
+     * reference's log(sum exp) underflows.  Models behind a device-gradient hook only have EvaluateLogModelGrad. */
+    double EvaluateLogModel(const Eigen::VectorXd &x) const
+    {
+        double v = 0.0;
+        EvaluateAt(x, &v, nullptr);
+        return v;
+    }
+    double EvaluateModel(const Eigen::VectorXd &x) const { return std::exp(EvaluateLogModel(x)); }
+    Eigen::VectorXd EvaluateLogModelGrad(const Eigen::VectorXd &x) const
+    {
+        Eigen::VectorXd g(dimension_);
+        EvaluateAt(x, nullptr, g.data());
+        return g;
+    }
+    Eigen::VectorXd EvaluateModelGrad(const Eigen::VectorXd &x) const
+    {
+        double v = 0.0;
+        Eigen::VectorXd g(dimension_);
+        EvaluateAt(x, &v, g.data());
+        g *= std::exp(v); /* grad p = p grad log p */
+        return g;
+    }
+
     /* Pushes this model into a device context (called by SVGD). */
     void Upload(svgdb_ctx *ctx) const
     {
@@ -81,6 +107,25 @@ public:
     }
 
 protected:
+    void EvaluateAt(const Eigen::VectorXd &x, double *logp, double *grad) const
+    {
+        if (x.rows() != dimension_) throw DimensionMismatchException("Argument dimension does not match the model dimension.");
+        svgdb_ctx *ctx = nullptr;
+        int rc = svgdb_create(&ctx, 0, 1, dimension_, SVGDB_PRECISION_F64);
+        std::string msg = ctx ? svgdb_last_error(ctx) : "svgdb_create failed";
+        try {
+            svgdcpp_b200::ThrowOnError(rc, msg.c_str());
+            Upload(ctx);
+            svgdcpp_b200::ThrowOnError(svgdb_set_particles(ctx, x.data()), svgdb_last_error(ctx));
+            if (logp) svgdcpp_b200::ThrowOnError(svgdb_compute_log_model(ctx, logp), svgdb_last_error(ctx));
+            if (grad) svgdcpp_b200::ThrowOnError(svgdb_compute_log_model_grad(ctx, grad), svgdb_last_error(ctx));
+        } catch (...) {
+            svgdb_destroy(ctx);
+            throw;
+        }
+        svgdb_destroy(ctx);
+    }
+
     int dimension_ = -1;
     std::vector<Eigen::MatrixXd> model_parameters_;
     svgdb_grad_fn hook_ = nullptr;

@@ -30,6 +30,15 @@ public:
     std::unique_ptr<Model> CloneUniquePointer() const override { return std::make_unique<MultivariateNormal>(*this); }
     std::shared_ptr<Model> CloneSharedPointer() const override { return std::make_shared<MultivariateNormal>(*this); }
 
+    /* Normalised variants (reference :143-175). */
+    double EvaluateModelNormalized(const Eigen::VectorXd &x) const { return norm_const_ * EvaluateModel(x); }
+    double EvaluateLogModelNormalized(const Eigen::VectorXd &x) const { return std::log(norm_const_) + EvaluateLogModel(x); }
+    Eigen::VectorXd EvaluateModelGradNormalized(const Eigen::VectorXd &x) const
+    {
+        Eigen::VectorXd g = EvaluateModelGrad(x);
+        g *= norm_const_;
+        return g;
+    }
     double GetNormalizationConstant() const { return norm_const_; }
 
 protected:

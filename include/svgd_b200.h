@@ -144,6 +144,11 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out);
  * A = 1/(2 d n) sum_i -Hessian(log p)(x_i) (GaussianRBFKernel.hpp:189-210), which must be positive definite. */
 int svgdb_get_scale_matrix(svgdb_ctx *ctx, double *A_dxd);
 
+/* Model::EvaluateLogModel for every particle (Model/Model.hpp:305-308): logp has N entries.  Built-in Gaussian models only (a model
+ * behind the gradient hook has no value function here); evaluated through log-sum-exp, so it stays finite where the reference's
+ * literal log(sum exp) underflows. */
+int svgdb_compute_log_model(svgdb_ctx *ctx, double *logp_N);
+
 /* The matrices SVGDOptions::LogIntermediateMatrices prints (SVGD.hpp:346-365; filled in ComputePhi, :407-454), for the current X and
  * the scale Kernel::Step would compute from it: K is n x n column-major with K(j, i) = k(x_j, x_i); gradK is (n d) x n column-major
  * with the block (j d .. j d + d, i) = grad_x k(x, x_i) at x = x_j.  An inspection path: one rank, n^2 (d + 1) doubles <= 2 GiB; the

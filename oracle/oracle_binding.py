@@ -59,6 +59,8 @@ def lib():
         L.oracle_rbf_hessian_scale.argtypes = [_dp, C.c_long, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
         L.oracle_phi_matrix.argtypes = [_dp, _dp, C.c_long, C.c_int, _dp, _dp]
         L.oracle_phi_matrix.restype = None
+        L.oracle_mvn_sum_logp.argtypes = [_dp, C.c_long, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
+        L.oracle_mvn_sum_logp.restype = C.c_int
         L.oracle_kernel_matrices.argtypes = [_dp, C.c_long, C.c_int, _dp, _dp, _dp]
         L.oracle_kernel_matrices.restype = None
         L.oracle_opt_step.argtypes = [C.c_int, C.c_size_t, _dp, C.c_double, C.c_double, C.c_double,
@@ -120,6 +122,18 @@ def mvn_sum_logp_grad(X, means, covs, lse=False):
     if lib().oracle_mvn_sum_logp_grad(_p(X), n, d, Cn, _p(means), _p(covs), int(lse), _p(G)):
         raise ValueError("singular covariance")
     return G
+
+
+def mvn_sum_logp(X, means, covs, lse=False):
+    """log p(x_i) of the sum of unnormalised Gaussians (Model::EvaluateLogModel)."""
+    X = _f64(X)
+    n, d = X.shape
+    means, covs = _f64(np.atleast_2d(means)), _f64(np.asarray(covs).reshape(-1, d, d))
+    out = np.empty(n)
+    rc = lib().oracle_mvn_sum_logp(_p(X), n, d, means.shape[0], _p(means), _p(covs), int(lse), _p(out))
+    if rc:
+        raise RuntimeError("oracle_mvn_sum_logp failed (singular covariance?)")
+    return out
 
 
 def rbf_hessian_scale(X, means, covs, lse=False):

@@ -197,6 +197,35 @@ int oracle_mvn_sum_logp_grad(const double *X, long n, int d, int C, const double
     return rc;
 }
 
+/* Model::EvaluateLogModel (Model.hpp:305-308) of the sum of unnormalised Gaussians (MultivariateNormal.hpp:56-61, Model.hpp:55-92). */
+int oracle_mvn_sum_logp(const double *X, long n, int d, int C, const double *means, const double *covs, int lse, double *logp)
+{
+    double *prec = (double *)malloc(sizeof(double) * (size_t)C * d * d);
+    double *h = (double *)malloc(sizeof(double) * (size_t)C);
+    if (!prec || !h) { free(prec); free(h); return -1; }
+    for (int c = 0; c < C; ++c)
+        if (oracle_lu_inverse(covs + (size_t)c * d * d, d, prec + (size_t)c * d * d)) { free(prec); free(h); return -1; }
+    for (long i = 0; i < n; ++i) {
+        const double *x = X + i * d;
+        for (int c = 0; c < C; ++c) {
+            const double *P = prec + (size_t)c * d * d, *mu = means + (size_t)c * d;
+            double q = 0.0;
+            for (int r = 0; r < d; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < d; ++k) s += P[r * d + k] * (x[k] - mu[k]);
+                q += (x[r] - mu[r]) * s;
+            }
+            h[c] = -0.5 * q;
+        }
+        double shift = 0.0, tot = 0.0;
+        if (lse) { shift = h[0]; for (int c = 1; c < C; ++c) if (h[c] > shift) shift = h[c]; }
+        for (int c = 0; c < C; ++c) tot += exp(h[c] - shift);
+        logp[i] = shift + log(tot); /* -inf when every exp underflowed and lse == 0, like the reference */
+    }
+    free(prec); free(h);
+    return 0;
+}
+
 /* SVGD.hpp:435-453 */
 void oracle_phi(const double *X, const double *G, long n, int d, double a, double *phi)
 {

@@ -53,6 +53,9 @@ double oracle_rbf_median_scale(const double *X, long n, int d, double *work);
 int oracle_mvn_sum_logp_grad(const double *X, long n, int d, int C, const double *means,
                              const double *covs, int lse, double *G);
 
+/* log p(x_i) of the same model (Model.hpp:305-308); lse as above. */
+int oracle_mvn_sum_logp(const double *X, long n, int d, int C, const double *means, const double *covs, int lse, double *logp);
+
 /* SVGD.hpp:407-454, literal eq. 8 double loop with k = exp(-a |x_j - x_i|^2)
  * (Kernel/GaussianRBFKernel.hpp:75-81) and grad_{x_j} k = -2 a (x_j - x_i) k. */
 void oracle_phi(const double *X, const double *G, long n, int d, double a, double *phi);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "svgdb_get_scale_matrix": (C.c_int, [_ctx, _dp]),
     "svgdb_step_host": (C.c_int, [_ctx, _dp, _dp, C.c_int64]),
     "svgdb_compute_kernel_matrices": (C.c_int, [_ctx, _dp, _dp, _dp]),
+    "svgdb_compute_log_model": (C.c_int, [_ctx, _dp]),
     "svgdb_local_rows": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "svgdb_set_particles_rows": (C.c_int, [_ctx, _dp]),
     "svgdb_get_particles_rows": (C.c_int, [_ctx, _dp]),

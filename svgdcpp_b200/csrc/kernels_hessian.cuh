@@ -208,4 +208,28 @@ __global__ void kernel_matrices_f64_kernel(const double *__restrict__ X, int64_t
     }
 }
 
+// log p(x_i) of a sum of C unnormalised Gaussians for this rank's particles (Model::EvaluateLogModel, Model.hpp:305-308, for the
+// models of Model.hpp:55-92), through log-sum-exp like the gradient kernel.  An inspection entry point: one thread per particle.
+__global__ void mvn_sum_logp_f64_kernel(const double *__restrict__ X, int d, int64_t row0, int64_t n_rows, int C, const double *__restrict__ means,
+                                        const double *__restrict__ prec, double *__restrict__ logp)
+{
+    const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_rows) return;
+    const double *x = X + (row0 + li) * d;
+    double top = -INFINITY, tot = 0.0; // online log-sum-exp over the components
+    for (int c = 0; c < C; ++c) {
+        const double *P = prec + (size_t)c * d * d, *mu = means + (size_t)c * d;
+        double q = 0.0;
+        for (int r = 0; r < d; ++r) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s += P[(size_t)r * d + k] * (x[k] - mu[k]);
+            q += (x[r] - mu[r]) * s;
+        }
+        const double h = -0.5 * q;
+        if (h > top) { tot = tot * exp(top - h) + 1.0; top = h; }
+        else tot += exp(h - top);
+    }
+    logp[li] = top + log(tot);
+}
+
 } // namespace svgdb

@@ -1795,6 +1795,25 @@ int svgdb_compute_log_model_grad(svgdb_ctx *ctx, double *G)
     return SVGDB_OK;
 }
 
+int svgdb_compute_log_model(svgdb_ctx *ctx, double *logp)
+{
+    if (!ctx || !logp) return fail(ctx, SVGDB_ERR_INVALID, "null output");
+    if (ctx->model_kind == MODEL_UNSET) return fail(ctx, SVGDB_ERR_UNSET, "Model function is unset.");
+    if (ctx->model_kind != MODEL_MVN_SUM)
+        return fail(ctx, SVGDB_ERR_UNSET, "a model behind the device-gradient hook has no value function on the device");
+    CU(cudaSetDevice(ctx->device));
+    double *tmp = ctx->V; // N x d doubles: room for N values at any row offset
+    if (ctx->n_rows > 0) {
+        mvn_sum_logp_f64_kernel<<<(unsigned)((ctx->n_rows + 127) / 128), 128, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->d, ctx->row0, ctx->n_rows, ctx->C,
+                                                                                           ctx->means_dev, ctx->prec_dev, tmp + ctx->row0);
+        KERNEL_CHECK();
+    }
+    TRY(allgather_rows(ctx, tmp, 1));
+    CU(cudaMemcpyAsync(logp, tmp, (size_t)ctx->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SVGDB_OK;
+}
+
 int svgdb_compute_kernel_matrices(svgdb_ctx *ctx, double *K, double *gradK, double *scale_out)
 {
     if (!ctx || !K || !gradK) return fail(ctx, SVGDB_ERR_INVALID, "null output");

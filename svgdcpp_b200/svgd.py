@@ -10,7 +10,8 @@ like the reference's own programs (examples/multivariate_normal/mvn_example.cpp)
     svgd = SVGD(dim, iters, x0, kernel, model, opt)    # SVGD.hpp:118
     svgd.Initialize(); svgd.Run()                      # x0 is updated in place (SVGD.hpp:393)
 
-All numerics run in libsvgd_b200.so on the GPU; nothing here computes.  The C++ facade with the
+All numerics run in libsvgd_b200.so on the GPU; nothing here computes (the point evaluations of a
+model exponentiate / scale the device's log p).  The C++ facade with the
 identical API lives in include/SVGDCpp/.
 """
 from __future__ import annotations
@@ -94,6 +95,58 @@ class Model:
     def Step(self):
         pass
 
+    # -- point evaluations (Model.hpp:290-338), on the device through a one-particle context: an inspection aid ------------
+    def _evaluate_at(self, x, want_logp, want_grad):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        if x.shape[0] != self.dimension_:
+            raise DimensionMismatchException("Argument dimension does not match the model dimension.")
+        lib = _capi.load()
+        ctx = C.c_void_p()
+        rc = lib.svgdb_create(C.byref(ctx), 0, 1, self.dimension_, _capi.PRECISION_F64)
+        try:
+            if rc != _capi.OK:
+                _raise_for(rc, ctx)
+            if self._hook is not None:
+                fn, user = self._hook
+                rc = lib.svgdb_set_model_device_hook(ctx, C.cast(fn, C.c_void_p), user)
+            elif self._components:
+                means = np.ascontiguousarray(np.stack([c[0] for c in self._components]))
+                covs = np.ascontiguousarray(np.stack([c[1] for c in self._components]))
+                rc = lib.svgdb_set_model_mvn_sum(ctx, means.shape[0], _ptr(means), _ptr(covs))
+            else:
+                raise UnsetException("Model function is unset.")
+            if rc != _capi.OK:
+                _raise_for(rc, ctx)
+            rc = lib.svgdb_set_particles(ctx, _ptr(x))
+            if rc != _capi.OK:
+                _raise_for(rc, ctx)
+            logp, grad = np.zeros(1), np.zeros(self.dimension_)
+            if want_logp:
+                rc = lib.svgdb_compute_log_model(ctx, _ptr(logp))
+                if rc != _capi.OK:
+                    _raise_for(rc, ctx)
+            if want_grad:
+                rc = lib.svgdb_compute_log_model_grad(ctx, _ptr(grad))
+                if rc != _capi.OK:
+                    _raise_for(rc, ctx)
+            return float(logp[0]), grad
+        finally:
+            if ctx:
+                lib.svgdb_destroy(ctx)
+
+    def EvaluateLogModel(self, x):
+        return self._evaluate_at(x, True, False)[0]
+
+    def EvaluateModel(self, x):
+        return math.exp(self.EvaluateLogModel(x))
+
+    def EvaluateLogModelGrad(self, x):
+        return self._evaluate_at(x, False, True)[1]
+
+    def EvaluateModelGrad(self, x):
+        logp, grad = self._evaluate_at(x, True, True)
+        return math.exp(logp) * grad   # grad p = p grad log p
+
 
 class MultivariateNormal(Model):
     def __init__(self, mean, covariance):
@@ -123,6 +176,15 @@ class MultivariateNormal(Model):
 
     def GetNormalizationConstant(self):
         return self.norm_const_
+
+    def EvaluateModelNormalized(self, x):  # MultivariateNormal.hpp:143-175
+        return self.norm_const_ * self.EvaluateModel(x)
+
+    def EvaluateLogModelNormalized(self, x):
+        return math.log(self.norm_const_) + self.EvaluateLogModel(x)
+
+    def EvaluateModelGradNormalized(self, x):
+        return self.norm_const_ * self.EvaluateModelGrad(x)
 
 
 # ---- kernel -------------------------------------------------------------------------------------

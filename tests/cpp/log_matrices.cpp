@@ -1,6 +1,9 @@
 // SVGDOptions::LogIntermediateMatrices through the facade (reference SVGD.hpp:346-365): a 2-D Gaussian target, 6 particles,
 // RBF kernel with the median scale, Adam, 3 iterations; the log goes to argv[1].  tests/test_facade_gpu.py parses it and
-// checks every printed number against the oracle.
+// checks every printed number against the oracle.  Then the model's point evaluations, printed to stdout.
+#include <iomanip>
+#include <iostream>
+
 #include "Core"
 #include "Kernel"
 #include "Model"
@@ -31,5 +34,12 @@ int main(int argc, char **argv)
     SVGD svgd(options);
     svgd.Initialize();
     svgd.Run();
+
+    // point evaluations of the model (Model.hpp:290-338, MultivariateNormal.hpp:143-175) at a fixed argument
+    Eigen::Vector2d x(0.75, -1.5);
+    MultivariateNormal mvn(mean, covariance);
+    Eigen::VectorXd g = mvn.EvaluateLogModelGrad(x), gp = mvn.EvaluateModelGradNormalized(x);
+    std::cout << std::setprecision(17) << mvn.EvaluateLogModel(x) << " " << mvn.EvaluateModel(x) << " " << g(0) << " " << g(1) << " "
+              << mvn.EvaluateLogModelNormalized(x) << " " << mvn.EvaluateModelNormalized(x) << " " << gp(0) << " " << gp(1) << std::endl;
     return 0;
 }

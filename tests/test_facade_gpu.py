@@ -78,7 +78,7 @@ def test_cpp_log_intermediate_matrices(tmp_path, oracle):
     from helpers import assert_matches_printed
 
     log = tmp_path / "log.txt"
-    _build_and_run("log_matrices", tmp_path, src_dir=os.path.join("tests", "cpp"), args=[str(log)])
+    stdout = _build_and_run("log_matrices", tmp_path, src_dir=os.path.join("tests", "cpp"), args=[str(log)])
     steps = _parse_log(log.read_text())
     n, d, iters = 6, 2, 3
     assert len(steps) == iters
@@ -95,3 +95,11 @@ def test_cpp_log_intermediate_matrices(tmp_path, oracle):
         assert_matches_printed(dK.reshape(n, n * d).T, m["KernelGrad"])
         X = oracle.svgd_run(X0, t + 1, mean, cov, opt_kind=oracle.OPT_ADAM, lr=0.1)
         assert_matches_printed(X.T, m["CoordMat"])
+    # the model's point evaluations printed by the same program (17 digits): unnormalised and normalised Gaussian at x = (0.75, -1.5)
+    vals = np.array([float(t) for t in stdout.strip().splitlines()[-1].split()])
+    x = np.array([[0.75, -1.5]])
+    logp = oracle.mvn_sum_logp(x, mean, cov)[0]
+    g = oracle.mvn_sum_logp_grad(x, mean, cov)[0]
+    norm = 1.0 / (2.0 * np.pi * np.sqrt(np.linalg.det(cov[0])))
+    expect = np.array([logp, np.exp(logp), g[0], g[1], np.log(norm) + logp, norm * np.exp(logp), norm * np.exp(logp) * g[0], norm * np.exp(logp) * g[1]])
+    assert np.max(np.abs(vals - expect) / np.maximum(1e-300, np.abs(expect))) < 1e-13

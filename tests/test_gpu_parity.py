@@ -328,6 +328,45 @@ def test_python_log_intermediate_matrices(sv, oracle, tmp_path):
     assert np.allclose(printed, x0, rtol=1e-5, atol=1e-6)
 
 
+def test_model_point_evaluations(sv, oracle):
+    """Model::Evaluate{Model,LogModel,ModelGrad,LogModelGrad} and MultivariateNormal::*Normalized (Model.hpp:290-338,
+    MultivariateNormal.hpp:143-175) run on the device; the values of all particles of a run come from svgdb_compute_log_model."""
+    import ctypes as C
+
+    d = 3
+    rng = np.random.default_rng(8)
+    mus = rng.standard_normal((2, d))
+    covs = np.stack([(lambda M: M @ M.T / d + 0.6 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(2)])
+    mvn = sv.MultivariateNormal(mus[0], covs[0])
+    mix = mvn + sv.MultivariateNormal(mus[1], covs[1])
+    x = rng.standard_normal(d)
+    for model, m, c in ((mvn, mus[:1], covs[:1]), (mix, mus, covs)):
+        logp = oracle.mvn_sum_logp(x[None], m, c)[0]
+        g = oracle.mvn_sum_logp_grad(x[None], m, c)[0]
+        assert abs(model.EvaluateLogModel(x) - logp) <= 1e-13 * max(1.0, abs(logp))
+        assert abs(model.EvaluateModel(x) - np.exp(logp)) <= 1e-13 * np.exp(logp)
+        assert _rel(model.EvaluateLogModelGrad(x), g) < 1e-13
+        assert _rel(model.EvaluateModelGrad(x), np.exp(logp) * g) < 1e-13
+    # one Gaussian: the closed form, and the normalised density against scipy's definition
+    diff = x - mus[0]
+    q = diff @ np.linalg.solve(covs[0], diff)
+    assert abs(mvn.EvaluateLogModel(x) + 0.5 * q) < 1e-13 * max(1.0, q)
+    pdf = np.exp(-0.5 * q) / np.sqrt((2 * np.pi) ** d * np.linalg.det(covs[0]))
+    assert abs(mvn.EvaluateModelNormalized(x) - pdf) <= 1e-13 * pdf
+    assert abs(mvn.EvaluateLogModelNormalized(x) - np.log(pdf)) <= 1e-12
+    assert _rel(mvn.EvaluateModelGradNormalized(x), -pdf * np.linalg.solve(covs[0], diff)) < 1e-12
+    # every particle of a run in one call, far out where the literal log(sum exp) underflows: finite through log-sum-exp
+    n = 50
+    x0 = np.asfortranarray(rng.standard_normal((d, n)) + 60.0)
+    svgd = sv.SVGD(d, 1, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, mix), mix, sv.AdaGrad(d, n, 0.1))
+    svgd._upload()
+    out = np.empty(n)
+    assert svgd._lib.svgdb_compute_log_model(svgd._ctx, out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    ref = oracle.mvn_sum_logp(np.ascontiguousarray(x0.T), mus, covs, lse=True)
+    assert np.all(np.isfinite(out)) and _rel(out, ref) < 1e-13
+    svgd.close()
+
+
 def test_hessian_scale_rejects_indefinite_matrix(sv):
     """Far-apart components make the mean negative Hessian indefinite: the device path reports it instead of running a kernel that
     is not positive definite (the reference would go on with exp(-d^T A d) > 1)."""

@@ -179,3 +179,17 @@ def test_oracle_kernel_matrices_assemble_phi(oracle):
             phi_ref = oracle.phi_matrix(X, G, A)
         assert np.max(np.abs(phi - phi_ref)) <= 1e-13 * np.max(np.abs(phi_ref))
         assert np.allclose(np.diag(K), 1.0) and np.allclose(K, K.T)
+
+
+def test_oracle_logp_is_consistent_with_its_gradient(oracle):
+    """Central differences of the oracle's log p reproduce the oracle's grad log p (sum of two Gaussians)."""
+    d = 3
+    rng = np.random.default_rng(12)
+    mus = rng.standard_normal((2, d))
+    covs = np.stack([(lambda M: M @ M.T / d + 0.6 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(2)])
+    x = rng.standard_normal(d)
+    g = oracle.mvn_sum_logp_grad(x[None], mus, covs)[0]
+    h = 1e-6
+    fd = np.array([(oracle.mvn_sum_logp((x + h * e)[None], mus, covs)[0] - oracle.mvn_sum_logp((x - h * e)[None], mus, covs)[0]) / (2 * h)
+                   for e in np.eye(d)])
+    assert np.max(np.abs(fd - g)) < 1e-8 * max(1.0, np.max(np.abs(g)))
