@@ -126,3 +126,15 @@ def test_eigen_text_format_of_the_python_mirror():
     init = np.array(g["initial"]).T
     assert _eigen_str(init) == ("  2.04113    1.6986   2.46988 -0.988663  -1.33335 -0.135618 -0.811293   2.71338   0.81427  -2.15038\n"
                                 "-0.633702   1.79064  -1.81469   1.60938   0.32382  0.773226 0.0804055   2.49717   1.30378  0.641813")
+
+
+@pytest.mark.parametrize("src", ["examples/mvn_example.cpp", "examples/gmm_example.cpp", "tests/cpp/log_matrices.cpp"])
+def test_cpp_facade_compiles(src):
+    """The header-only C++ facade (include/SVGDCpp) and the programs written against it compile cleanly with the host compiler;
+    running them needs a GPU (tests/test_facade_gpu.py)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    res = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), os.path.join(root, src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "warning" not in res.stderr, res.stderr
