@@ -105,6 +105,61 @@ def test_row_sharded_protocol_matches_single_process_oracle(oracle, tmp_path, n,
     assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))
 
 
+def _hessian_worker(rank, world, port, n, d, iters, out):
+    """ScaleMethod::Hessian across ranks (hessian_scale_dev / prepare_and_phi_hessian): per-rank partial sums of -Hessian(log p)
+    over the local rows, one all-reduce, A = R^T R, the scalar-bandwidth interaction with a = 1 on y = R x, g^ = R^-T g for the
+    local rows against all columns, phi = R^T phi^."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    mus = 0.4 * rng.standard_normal((2, d))
+    covs = np.stack([(lambda M: M @ M.T / d + 0.7 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(2)])
+    X = 1.2 * rng.standard_normal((n, d))
+    rpr, row0, n_rows = shard_plan(n, world, rank)
+    s = np.zeros((n_rows, d))                                   # AdaGrad state of the local rows
+    for it in range(iters):
+        Xl = X[row0:row0 + n_rows]
+        part = oracle.rbf_hessian_scale(Xl, mus, covs) * (2.0 * d * n_rows) if n_rows else np.zeros((d, d))
+        H = torch.from_numpy(part.copy())
+        dist.all_reduce(H)                                      # sum over ranks of sum_i -Hessian(log p)(x_i)
+        A = H.numpy() / (2.0 * d * n)
+        R = np.linalg.cholesky(A).T                             # A = R^T R, R upper triangular
+        Y = X @ R.T                                             # every rank holds all particles
+        Gh = oracle.mvn_sum_logp_grad(Xl, mus, covs) @ np.linalg.inv(R) if n_rows else np.zeros((0, d))
+        Vl = np.zeros((rpr, d)); Vl[:n_rows] = Gh - 2.0 * Y[row0:row0 + n_rows]
+        Vt = [torch.zeros(rpr, d, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(Vt, torch.from_numpy(Vl))
+        V = torch.cat(Vt).numpy()[:n]
+        Yl = Y[row0:row0 + n_rows]
+        K = np.exp(-((Yl[:, None, :] - Y[None, :, :]) ** 2).sum(-1))
+        phi = ((K @ V + 2.0 * Yl * K.sum(1, keepdims=True)) / n) @ R
+        s = s + phi ** 2
+        Xn = np.zeros((rpr, d)); Xn[:n_rows] = Xl + 0.1 * phi / (1e-8 + np.sqrt(s))
+        Xt = [torch.zeros(rpr, d, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(Xt, torch.from_numpy(Xn))
+        X = torch.cat(Xt).numpy()[:n].copy()
+    if rank == 0:
+        np.save(out, X)
+    dist.destroy_process_group()
+
+
+def test_hessian_scale_protocol_matches_single_process_oracle(oracle, tmp_path):
+    n, d, iters, world = 131, 4, 3, 2
+    out = str(tmp_path / "xh.npy")
+    mp.spawn(_hessian_worker, args=(world, 29671, n, d, iters, out), nprocs=world, join=True)
+    rng = np.random.default_rng(11)
+    mus = 0.4 * rng.standard_normal((2, d))
+    covs = np.stack([(lambda M: M @ M.T / d + 0.7 * np.eye(d))(rng.standard_normal((d, d))) for _ in range(2)])
+    X0 = 1.2 * rng.standard_normal((n, d))
+    ref = oracle.svgd_run(X0, iters, mus, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, scale_method=oracle.SCALE_HESSIAN)
+    got = np.load(out)
+    assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))
+
+
 def test_shard_plan_covers_every_row_once():
     for n in (1, 7, 128, 129, 65536, 1000003):
         for world in (1, 2, 3, 4, 8):
