@@ -126,3 +126,12 @@ def test_eigen_text_format_of_the_python_mirror():
     init = np.array(g["initial"]).T
     assert _eigen_str(init) == ("  2.04113    1.6986   2.46988 -0.988663  -1.33335 -0.135618 -0.811293   2.71338   0.81427  -2.15038\n"
                                 "-0.633702   1.79064  -1.81469   1.60938   0.32382  0.773226 0.0804055   2.49717   1.30378  0.641813")
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/svgd_b200.h is a C ABI: it must compile as C99 with pedantic warnings as errors (no C++ or torch types leak in)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "svgd_b200.h"\nint main(void) { return svgdb_version() == 0; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
