@@ -1,5 +1,6 @@
-// The reference's examples/gaussian_mixture_model/gmm_example.cpp scenario on the B200 facade:
-// sum of two 2-D Gaussians (Model::operator+), 20 particles, median RBF kernel, Adam, 1000 iterations.
+// Twenty particles and a two-mode target built as the sum of two Gaussians (Model::operator+), median-heuristic RBF kernel,
+// Adam for 1000 iterations -- the scenario of the reference's Gaussian-mixture notebook (cell 4 of gmm_example.ipynb), on the
+// B200 facade.  tests/test_facade_gpu.py compares the printed particles with the notebook's captured output.
 #include <iostream>
 
 #include "Core"
@@ -7,31 +8,55 @@
 #include "Model"
 #include "Optimizer"
 
+namespace {
+
+constexpr size_t kDim = 2, kParticles = 20, kIterations = 1000;
+
+struct Component {
+    double mean[2];
+    double cov[4]; // row-major, before the common factor 5
+};
+
+const Component kModes[2] = {
+    {{3.6871, -2.801}, {0.5001, 0.2426, 0.2426, 0.8420}},
+    {{-2.9802, 4.3387}, {0.6779, -0.1652, -0.1652, 0.2260}},
+};
+
+MultivariateNormal MakeMode(const Component &c)
+{
+    Eigen::Matrix2d cov;
+    cov << c.cov[0], c.cov[1], c.cov[2], c.cov[3];
+    cov *= 5;
+    return MultivariateNormal(Eigen::Vector2d(c.mean[0], c.mean[1]), cov);
+}
+
+void Report(const char *title, const Eigen::MatrixXd &particles)
+{
+    std::cout << title << std::endl << particles << std::endl;
+}
+
+} // namespace
+
 int main()
 {
-    Eigen::Vector2d mean1(3.6871, -2.801), mean2(-2.9802, 4.3387);
-    Eigen::Matrix2d cov1, cov2;
-    cov1 << 0.5001, 0.2426, 0.2426, 0.8420;
-    cov2 << 0.6779, -0.1652, -0.1652, 0.2260;
-    cov1 *= 5;
-    cov2 *= 5;
+    // unweighted, unnormalised sum of the two modes: what the reference calls its Gaussian mixture
+    std::shared_ptr<Model> target = std::make_shared<Model>(MakeMode(kModes[0]) + MakeMode(kModes[1]));
 
-    MultivariateNormal mvn1(mean1, cov1);
-    MultivariateNormal mvn2(mean2, cov2);
-    Model gmm = mvn1 + mvn2;
-    std::shared_ptr<Model> gmm_ptr = std::make_shared<Model>(gmm);
+    auto particles = std::make_shared<Eigen::MatrixXd>(8 * Eigen::MatrixXd::Random(kDim, kParticles));
+    Report("Initial particle coordinates", *particles);
 
-    size_t dim = 2, num_particles = 20, num_iterations = 1000;
-    auto x0 = std::make_shared<Eigen::MatrixXd>(8 * Eigen::MatrixXd::Random(dim, num_particles));
-    std::cout << "Initial particle coordinates" << std::endl << *x0 << std::endl;
+    SVGDOptions options;
+    options.Dimension = kDim;
+    options.NumIterations = kIterations;
+    options.CoordinateMatrixPtr = particles;
+    options.ModelPtr = target;
+    options.KernelPtr = std::make_shared<GaussianRBFKernel>(particles, GaussianRBFKernel::ScaleMethod::Median, target);
+    options.OptimizerPtr = std::make_shared<Adam>(kDim, kParticles, 0.1, 0.9, 0.999);
 
-    std::shared_ptr<Kernel> rbf_ptr = std::make_shared<GaussianRBFKernel>(x0, GaussianRBFKernel::ScaleMethod::Median, gmm_ptr);
-    std::shared_ptr<Optimizer> opt_ptr = std::make_shared<Adam>(dim, num_particles, 1.0e-1, 0.9, 0.999);
+    SVGD driver(options);
+    driver.Initialize();
+    driver.Run();
 
-    SVGD svgd(dim, num_iterations, x0, rbf_ptr, gmm_ptr, opt_ptr);
-    svgd.Initialize();
-    svgd.Run();
-
-    std::cout << "Final particle coordinates" << std::endl << *x0 << std::endl;
+    Report("Final particle coordinates", *particles);
     return 0;
 }

@@ -1,7 +1,6 @@
-// The reference's examples/multivariate_normal/mvn_example.cpp scenario on the B200 facade:
-// 2-D MVN target, 10 particles, median-heuristic RBF kernel, AdaGrad(0.1), 1000 iterations.
-// Prints the same two blocks as the reference program; tests compare them with the published output
-// (reference examples/README.md:7-12).
+// Ten particles, a correlated 2-D Gaussian target, the median-heuristic RBF kernel and AdaGrad for 1000 iterations -- the
+// scenario whose output the reference publishes (reference examples/README.md:7-12), here driven through SVGDOptions on the
+// B200 facade.  tests/test_facade_gpu.py compares the two printed blocks with that published output character by character.
 #include <iostream>
 
 #include "Core"
@@ -9,25 +8,41 @@
 #include "Model"
 #include "Optimizer"
 
+namespace {
+
+constexpr size_t kDim = 2, kParticles = 10, kIterations = 1000;
+
+void Report(const char *title, const Eigen::MatrixXd &particles)
+{
+    std::cout << title << std::endl << particles << std::endl;
+}
+
+} // namespace
+
 int main()
 {
-    Eigen::Vector2d mean(-0.6871, 0.8010);
-    Eigen::Matrix2d covariance;
-    covariance << 0.2260, 0.1652, 0.1652, 0.6779;
-    covariance *= 5;
-    std::shared_ptr<Model> mvn_ptr = std::make_shared<MultivariateNormal>(mean, covariance);
+    // target density: N((-0.6871, 0.8010), 5 S)
+    Eigen::Matrix2d sigma;
+    sigma << 0.2260, 0.1652, 0.1652, 0.6779;
+    sigma *= 5;
+    std::shared_ptr<Model> target = std::make_shared<MultivariateNormal>(Eigen::Vector2d(-0.6871, 0.8010), sigma);
 
-    size_t dim = 2, num_particles = 10, num_iterations = 1000;
-    auto x0 = std::make_shared<Eigen::MatrixXd>(3 * Eigen::MatrixXd::Random(dim, num_particles));
-    std::cout << "Initial particle coordinates" << std::endl << *x0 << std::endl;
+    // particles: 3 * uniform(-1, 1), drawn like Eigen::MatrixXd::Random (unseeded)
+    auto particles = std::make_shared<Eigen::MatrixXd>(3 * Eigen::MatrixXd::Random(kDim, kParticles));
+    Report("Initial particle coordinates", *particles);
 
-    std::shared_ptr<Kernel> rbf_ptr = std::make_shared<GaussianRBFKernel>(x0, GaussianRBFKernel::ScaleMethod::Median, mvn_ptr);
-    std::shared_ptr<Optimizer> opt_ptr = std::make_shared<AdaGrad>(dim, num_particles, 1.0e-1);
+    SVGDOptions options;
+    options.Dimension = kDim;
+    options.NumIterations = kIterations;
+    options.CoordinateMatrixPtr = particles;
+    options.ModelPtr = target;
+    options.KernelPtr = std::make_shared<GaussianRBFKernel>(particles, GaussianRBFKernel::ScaleMethod::Median, target);
+    options.OptimizerPtr = std::make_shared<AdaGrad>(kDim, kParticles, 0.1);
 
-    SVGD svgd(dim, num_iterations, x0, rbf_ptr, mvn_ptr, opt_ptr);
-    svgd.Initialize();
-    svgd.Run();
+    SVGD driver(options);
+    driver.Initialize();
+    driver.Run(); // the particle matrix is updated in place
 
-    std::cout << "Final particle coordinates" << std::endl << *x0 << std::endl;
+    Report("Final particle coordinates", *particles);
     return 0;
 }
