@@ -72,7 +72,7 @@ def test_product_package_never_imports_the_oracle():
 
 @pytest.mark.parametrize("example", ["examples/mvn_example", "examples/gmm_example", "tests/cpp/log_matrices"])
 def test_facade_examples_compile(built_lib, example, tmp_path):
-    """The reference's example programs, re-targeted at include/SVGDCpp, and the test program of the logging / point-evaluation
+    """The programs for the reference's two example scenarios, written against include/SVGDCpp, and the test program of the logging / point-evaluation
     API build with the reference's own warning flags (-Wall -Wextra -Wpedantic, reference CMakeLists.txt:4)."""
     exe = tmp_path / os.path.basename(example)
     cmd = [GXX, "-std=c++17", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),

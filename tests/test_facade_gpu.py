@@ -1,4 +1,4 @@
-"""The C++ facade end to end on the GPU: the re-targeted example programs must print the reference's
+"""The C++ facade end to end on the GPU: the programs for the reference's example scenarios must print the reference's
 published output (examples/README.md:7-12 and the notebooks' captured stdout)."""
 import os
 import subprocess
