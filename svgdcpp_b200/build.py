@@ -37,7 +37,7 @@ def _host_cxx() -> list[str]:
 
 
 def sources() -> list[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".hpp")))
 
 
 def is_stale() -> bool:

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "host_math.hpp"
 #include "kernels_f64.cuh"
 #include "kernels_hessian.cuh"
 #include "select.cuh"
@@ -29,6 +30,7 @@
 #endif
 
 using namespace svgdb;
+using namespace svgdb::host;
 
 namespace {
 
@@ -249,13 +251,6 @@ bool invert_matrix(const double *A, int d, std::vector<double> &inv)
             inv[(size_t)r * d + c] = inv[(size_t)c * d + r] = s;
         }
     return true;
-}
-
-inline uint64_t key_of(double v)
-{
-    uint64_t k;
-    std::memcpy(&k, &v, 8);
-    return k;
 }
 
 int free_sharded(svgdb_ctx *ctx)
@@ -810,17 +805,6 @@ int launch_dist_operands(svgdb_ctx *ctx)
     return SVGDB_OK;
 }
 
-// smallest float >= the double whose bits are `key` (+inf for keys past +inf)
-float key_to_float_ceil(uint64_t key)
-{
-    if (key >= 0x7FF0000000000000ull) return INFINITY;
-    double x;
-    std::memcpy(&x, &key, 8);
-    float f = (float)x;
-    if ((double)f < x) f = std::nextafterf(f, INFINITY);
-    return f;
-}
-
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
     using namespace svgdb::tc;
@@ -950,11 +934,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
     const bool stream_rows = ctx->stream_out != nullptr && !debug_phi && ctx->phi_dbg_mode == 0 && n_ipairs_all >= 32;
     const int n_chunks = stream_rows ? 4 : 1;
     int chunk_ipairs[4] = {n_ipairs_all, 0, 0, 0};
-    if (stream_rows) {
-        chunk_ipairs[0] = chunk_ipairs[1] = (3 * n_ipairs_all) / 8;
-        chunk_ipairs[2] = n_ipairs_all / 8;
-        chunk_ipairs[3] = n_ipairs_all - chunk_ipairs[0] - chunk_ipairs[1] - chunk_ipairs[2];
-    }
+    if (stream_rows) download_chunks(n_ipairs_all, chunk_ipairs);
     int ipair0 = 0;
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int64_t off = (int64_t)ipair0 * 256;
@@ -1062,32 +1042,6 @@ void prof_mark(svgdb_ctx *ctx, int i)
 }
 
 // ---- ScaleMethod::Hessian (kernels_hessian.cuh) -----------------------------------------------------------------------
-// Cholesky A = R^T R with R upper triangular; returns false if A is not positive definite.  Rinv = R^-1.
-bool cholesky_upper(const std::vector<double> &A, int d, std::vector<double> &R, std::vector<double> &Rinv)
-{
-    R.assign((size_t)d * d, 0.0);
-    for (int j = 0; j < d; ++j) {
-        double s = A[(size_t)j * d + j];
-        for (int k = 0; k < j; ++k) s -= R[(size_t)k * d + j] * R[(size_t)k * d + j];
-        if (!(s > 0.0) || !std::isfinite(s)) return false;
-        const double rjj = std::sqrt(s);
-        R[(size_t)j * d + j] = rjj;
-        for (int c = j + 1; c < d; ++c) {
-            double t = A[(size_t)j * d + c];
-            for (int k = 0; k < j; ++k) t -= R[(size_t)k * d + j] * R[(size_t)k * d + c];
-            R[(size_t)j * d + c] = t / rjj;
-        }
-    }
-    Rinv.assign((size_t)d * d, 0.0); // back substitution, column by column: R Rinv = I
-    for (int c = 0; c < d; ++c)
-        for (int r = c; r >= 0; --r) {
-            double t = (r == c) ? 1.0 : 0.0;
-            for (int k = r + 1; k <= c; ++k) t -= R[(size_t)r * d + k] * Rinv[(size_t)k * d + c];
-            Rinv[(size_t)r * d + c] = t / R[(size_t)r * d + r];
-        }
-    return true;
-}
-
 // Sum over all particles of the particle-dependent part of -Hessian(log p) and of the softmax weights (kernels_hessian.cuh).
 int hessian_partial_sums(svgdb_ctx *ctx, std::vector<double> &H, std::vector<double> &W)
 {
@@ -1675,8 +1629,8 @@ int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int
         CU(cudaEventRecord(ctx->ev_fork, ctx->stream)); // whatever still reads or writes X[cur] on the main stream comes first
         CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
         int64_t r0 = 0;
+        upload_chunk_ends(n_ipairs_all, ctx->up_ipairs);
         for (int ch = 0; ch < 4; ++ch) {
-            ctx->up_ipairs[ch] = ch == 3 ? n_ipairs_all : (n_ipairs_all * (ch + 1)) / 4;
             const int64_t r1 = std::min<int64_t>((int64_t)ctx->up_ipairs[ch] * 256, ctx->N);
             CU(cudaMemcpyAsync(ctx->X[ctx->cur] + (size_t)r0 * ctx->d, rows_in + (size_t)r0 * ctx->d, (size_t)(r1 - r0) * ctx->d * sizeof(double),
                                cudaMemcpyHostToDevice, ctx->copy_stream));

@@ -1,0 +1,83 @@
+// CPU unit test of svgdcpp_b200/csrc/host_math.hpp (the library's pure host arithmetic): run by tests/test_cabi_cpu.py.
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <random>
+
+#include "host_math.hpp"
+
+using namespace svgdb::host;
+
+static int failures = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+    } while (0)
+
+int main()
+{
+    std::mt19937_64 rng(5);
+    std::normal_distribution<double> normal(0.0, 1.0);
+
+    // keys: order preserving on non-negative doubles; key_to_float_ceil = smallest float >= the double
+    {
+        double prev = 0.0;
+        for (int i = 0; i < 2000; ++i) {
+            const double v = prev + std::ldexp(std::fabs(normal(rng)), (i % 80) - 40);
+            CHECK(key_of(v) >= key_of(prev));
+            const float f = key_to_float_ceil(key_of(v));
+            CHECK((double)f >= v);
+            CHECK(f == 0.0f || (double)std::nextafterf(f, -std::numeric_limits<float>::infinity()) < v);
+            prev = v;
+        }
+        CHECK(key_of(0.0) == 0ull);
+        CHECK(std::isinf(key_to_float_ceil(key_of(std::numeric_limits<double>::infinity()))));
+        CHECK(std::isinf(key_to_float_ceil(key_of(1e300)))); // beyond the float range
+        CHECK(key_to_float_ceil(key_of(1.0)) == 1.0f);
+    }
+
+    // Cholesky: A = R^T R with R upper triangular, R Rinv = I; indefinite and non-finite matrices are refused
+    for (int d : {1, 2, 7, 64}) {
+        std::vector<double> M((size_t)d * d), A((size_t)d * d, 0.0), R, Rinv;
+        for (auto &m : M) m = normal(rng);
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c) {
+                double s = r == c ? 0.5 : 0.0;
+                for (int k = 0; k < d; ++k) s += M[(size_t)r * d + k] * M[(size_t)c * d + k] / d;
+                A[(size_t)r * d + c] = s;
+            }
+        CHECK(cholesky_upper(A, d, R, Rinv));
+        double err_a = 0.0, err_i = 0.0, below = 0.0;
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c) {
+                double s = 0.0, t = 0.0;
+                for (int k = 0; k < d; ++k) { s += R[(size_t)k * d + r] * R[(size_t)k * d + c]; t += R[(size_t)r * d + k] * Rinv[(size_t)k * d + c]; }
+                err_a = std::fmax(err_a, std::fabs(s - A[(size_t)r * d + c]));
+                err_i = std::fmax(err_i, std::fabs(t - (r == c ? 1.0 : 0.0)));
+                if (r > c) below = std::fmax(below, std::fabs(R[(size_t)r * d + c]) + std::fabs(Rinv[(size_t)r * d + c]));
+            }
+        CHECK(err_a < 1e-13 * d);
+        CHECK(err_i < 1e-12 * d);
+        CHECK(below == 0.0);
+        std::vector<double> B = A;
+        B[(size_t)(d - 1) * d + (d - 1)] = -1.0; // not positive definite
+        CHECK(!cholesky_upper(B, d, R, Rinv));
+        B = A;
+        B[0] = std::numeric_limits<double>::quiet_NaN();
+        CHECK(!cholesky_upper(B, d, R, Rinv));
+    }
+
+    // row chunks of svgdb_step_host: every i-pair exactly once, in order, nothing negative
+    for (int n = 32; n < 5000; n += (n < 300 ? 1 : 37)) {
+        int down[4], up[4];
+        download_chunks(n, down);
+        upload_chunk_ends(n, up);
+        CHECK(down[0] >= 0 && down[1] >= 0 && down[2] >= 0 && down[3] >= 0);
+        CHECK(down[0] + down[1] + down[2] + down[3] == n);
+        CHECK(down[2] + down[3] <= n / 4 + 8); // the exposed tail stays small
+        CHECK(up[0] > 0 && up[0] <= up[1] && up[1] <= up[2] && up[2] <= up[3] && up[3] == n);
+    }
+
+    if (failures == 0) std::printf("host_math_test: all checks passed\n");
+    return failures == 0 ? 0 : 1;
+}

@@ -135,3 +135,15 @@ def test_header_is_plain_c(tmp_path):
     res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_host_math_unit_tests(tmp_path):
+    """The library's pure host arithmetic (svgdcpp_b200/csrc/host_math.hpp: median keys, the Cholesky factor of the Hessian scale,
+    the row chunks of svgdb_step_host) is included verbatim by svgd_b200_api.cu; its unit test builds and runs on the CPU."""
+    exe = tmp_path / "host_math_test"
+    res = subprocess.run([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-I", os.path.join(ROOT, "svgdcpp_b200", "csrc"),
+                          os.path.join(ROOT, "tests", "cpp", "host_math_test.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "all checks passed" in run.stdout, run.stdout
+    assert '#include "host_math.hpp"' in open(os.path.join(ROOT, "svgdcpp_b200", "csrc", "svgd_b200_api.cu")).read()
