@@ -15,7 +15,7 @@ public:
     enum class ScaleMethod {
         Median = 0,
         Hessian = 1,
-        Constant = 2 /* the reference's "TODO: constant scale"; value given by UpdateParameters({A}) */
+        Constant = 2 /* the reference's "TODO: constant scale"; value a given by UpdateParameters({a I}) */
     };
 
     GaussianRBFKernel() {}
@@ -26,14 +26,20 @@ public:
         if (scale_method_ == ScaleMethod::Hessian && !model_ptr) throw UnsetException("Hessian-based scale requires a model.");
     }
 
-    /* UpdateParameters({A}) fixes the scale to A(0,0) (A = a I), like SVGD::UpdateKernelParameters. */
+    /* With ScaleMethod::Median / Hessian the scale is recomputed from the particles at every Step and overwrites the parameters
+     * (reference GaussianRBFKernel.hpp:141-156), so UpdateParameters only takes effect for ScaleMethod::Constant, where
+     * params[0] must be a I (the device kernel's scale is a scalar). */
     void UpdateParameters(const std::vector<Eigen::MatrixXd> &params) override
     {
         Kernel::UpdateParameters(params);
-        if (!params.empty() && params[0].size() > 0) {
-            fixed_scale_ = params[0](0, 0);
-            scale_method_ = ScaleMethod::Constant;
-        }
+        if (scale_method_ != ScaleMethod::Constant || params.empty() || params[0].size() == 0) return;
+        const Eigen::MatrixXd &A = params[0];
+        if (A.rows() != dimension_ || A.cols() != dimension_) throw DimensionMismatchException("Kernel parameter matrix must be dimension x dimension.");
+        for (int r = 0; r < dimension_; ++r)
+            for (int c = 0; c < dimension_; ++c)
+                if (A(r, c) != (r == c ? A(0, 0) : 0.0))
+                    throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] the device RBF kernel takes a scalar scale: A must be a * I.");
+        fixed_scale_ = A(0, 0);
     }
 
     std::unique_ptr<Kernel> CloneUniquePointer() const override { return std::make_unique<GaussianRBFKernel>(*this); }

@@ -43,8 +43,9 @@ typedef enum {
 } svgdb_status;
 
 /* Arithmetic of the pair interaction.  F64: IEEE double end to end (DMMA tensor cores),
- * oracle-grade.  TC32: tcgen05 tensor cores on split-bf16 operands with fp32 accumulation in
- * TMEM and an fp32 exp; error bound stated in DESIGN.md "Precision modes". */
+ * oracle-grade.  TC32: tcgen05 kind::f16 tensor cores on split-fp16 operands (pair kernel; split-bf16
+ * in the median's distance pass), fp32 accumulation in TMEM, fp32 ex2, kernel values rounded to
+ * fp16, FP64 optimizer state; error bound stated in DESIGN.md "Precision modes". */
 typedef enum { SVGDB_PRECISION_F64 = 0, SVGDB_PRECISION_TC32 = 1 } svgdb_precision;
 
 /* GaussianRBFKernel::ScaleMethod (Kernel/GaussianRBFKernel.hpp:25-30) plus a constant scale
@@ -89,7 +90,9 @@ int svgdb_set_stream(svgdb_ctx *ctx, void *cuda_stream);
 int svgdb_nccl_unique_id(void *out_id, size_t bytes);
 int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique_id, size_t bytes);
 
-/* ---- particles (the shared coordinate matrix, SVGD.hpp:176,393) ---------------------------- */
+/* ---- particles (the shared coordinate matrix, SVGD.hpp:176,393) ----------------------------
+ * The set_* calls return after the host buffer has been read (pinned or pageable): the caller may
+ * reuse or free it at once. */
 int svgdb_set_particles(svgdb_ctx *ctx, const double *X_dxN);
 int svgdb_get_particles(svgdb_ctx *ctx, double *X_dxN);
 /* Row-sharded I/O for multi-rank runs (after svgdb_comm_init): this rank owns particles [row0, row0 + n_rows).

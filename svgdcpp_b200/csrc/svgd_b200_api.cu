@@ -580,41 +580,53 @@ int median_scale(svgdb_ctx *ctx)
 
     // 2) radix narrowing on the key bits until the bracket fits the candidate buffer
     if (!collected) {
-        while (in_range > ctx->capacity && hi - lo > 1) {
-            uint64_t span = hi - lo - 1;
-            int bits = 0;
-            while (bits < 64 && (span >> bits) != 0ull) ++bits;
-            int shift = std::max(0, bits - 12);
-            TRY(launch_dist_pass(ctx, MODE_HIST, lo, hi, shift));
-            TRY(read_pass_results(ctx, MODE_HIST, nullptr));
-            uint64_t cum = ctx->hs->below;
-            int b = 0;
-            for (; b < HIST_BINS; ++b) {
-                if (k_hi < cum + ctx->hs->hist[b]) break;
-                cum += ctx->hs->hist[b];
+        // The collecting pass may see more than the histogram promised: the tensor-core pass collects a superset [lo, hi') of the
+        // bracket, and the widening below moves lo downwards.  If that overflows the candidate buffer while the bracket is still
+        // wider than one key, narrow again instead of trusting the overflowing list (a few rounds at most, then an error).
+        for (int round = 0;; ++round) {
+            while (in_range > ctx->capacity && hi - lo > 1) {
+                uint64_t span = hi - lo - 1;
+                int bits = 0;
+                while (bits < 64 && (span >> bits) != 0ull) ++bits;
+                int shift = std::max(0, bits - 12);
+                TRY(launch_dist_pass(ctx, MODE_HIST, lo, hi, shift));
+                TRY(read_pass_results(ctx, MODE_HIST, nullptr));
+                uint64_t cum = ctx->hs->below;
+                int b = 0;
+                for (; b < HIST_BINS; ++b) {
+                    if (k_hi < cum + ctx->hs->hist[b]) break;
+                    cum += ctx->hs->hist[b];
+                }
+                if (b == HIST_BINS) return fail(ctx, SVGDB_ERR_NUMERIC, "median select: rank not found (non-finite particles?)");
+                uint64_t nlo = lo + ((uint64_t)b << shift);
+                uint64_t nhi = std::min<uint64_t>(hi, nlo + (1ull << shift));
+                lo = nlo; hi = nhi; below_known = cum; in_range = ctx->hs->hist[b];
             }
-            if (b == HIST_BINS) return fail(ctx, SVGDB_ERR_NUMERIC, "median select: rank not found (non-finite particles?)");
-            uint64_t nlo = lo + ((uint64_t)b << shift);
-            uint64_t nhi = std::min<uint64_t>(hi, nlo + (1ull << shift));
-            lo = nlo; hi = nhi; below_known = cum; in_range = ctx->hs->hist[b];
-        }
-        for (int attempt = 0;; ++attempt) {
-            TRY(launch_dist_pass(ctx, MODE_COLLECT, lo, hi, 0));
-            TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
-            below_known = ctx->hs->below;
-            if (!(below_known <= k_hi && k_hi < below_known + mid))
-                return fail(ctx, SVGDB_ERR_NUMERIC, "median select: bracket lost the rank (non-finite particles?)");
-            // tensor-core pass, even count, lower middle element just below the bracket: widen downwards and recollect
-            const bool pred_outside = even && ctx->precision == SVGDB_PRECISION_TC32 && below_known == k_hi && lo > 0 && mid <= ctx->capacity;
-            if (!pred_outside || attempt >= 40) break;
-            const uint64_t step = std::max<uint64_t>(hi - lo, 1ull) << std::min(attempt, 20);
-            lo = lo > step ? lo - step : 0;
+            bool pred_outside = false;
+            for (int attempt = 0;; ++attempt) {
+                TRY(launch_dist_pass(ctx, MODE_COLLECT, lo, hi, 0));
+                TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
+                below_known = ctx->hs->below;
+                if (!(below_known <= k_hi && k_hi < below_known + mid))
+                    return fail(ctx, SVGDB_ERR_NUMERIC, "median select: bracket lost the rank (non-finite particles?)");
+                // tensor-core pass, even count, lower middle element just below the bracket: widen downwards and recollect
+                pred_outside = even && ctx->precision == SVGDB_PRECISION_TC32 && below_known == k_hi && lo > 0 && mid <= ctx->capacity;
+                if (!pred_outside || attempt >= 40) break;
+                const uint64_t step = std::max<uint64_t>(hi - lo, 1ull) << std::min(attempt, 20);
+                lo = lo > step ? lo - step : 0;
+            }
+            if (pred_outside)
+                return fail(ctx, SVGDB_ERR_NUMERIC, "median select: the lower middle distance was not found below the bracket (non-finite particles?)");
+            if (mid <= ctx->capacity || hi - lo == 1) break;
+            if (round >= 6)
+                return fail(ctx, SVGDB_ERR_NUMERIC, "median select: the candidate buffer cannot hold the narrowed bracket (SVGDB_CAND_CAPACITY too small for this particle set)");
+            in_range = mid; // > capacity: forces at least one more histogram pass over [lo, hi)
         }
     }
 
     const uint64_t kk = k_hi - below_known;
     if (mid > ctx->capacity) {
-        // only reachable when hi - lo == 1: more than `capacity` identical distances
+        // here hi - lo == 1 (guarded above; the predicted-bracket path requires mid <= capacity): more than `capacity` identical distances
         median_finalize_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, kk, even ? 1 : 0, ctx->max_below, 1, lo, log_n,
                                                           ctx->medres, ctx->a_dev);
         KERNEL_CHECK();
@@ -815,6 +827,21 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     // Symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks.
     // Particles arriving in row chunks (svgdb_step_host, one rank): the pass is issued in as many launches, launch k covering
     // the pairs whose later row lies in chunk k, i.e. i-pairs below the chunk's end against the column tiles of the chunk.
+    // Bracket width as the kernel tests it, and the exclusive key bound of what the pass may collect.  Pure host arithmetic on
+    // (lo, hi): computed on EVERY rank, also on ranks that own no i-pair (they take part in the select's collectives and must
+    // derive the same digit plan from the same hi).
+    uint32_t width_bits = 0;
+    {
+        float wdt = std::isinf(lo_f) || std::isinf(hi_f) ? INFINITY : (float)((double)hi_f - (double)lo_f);
+        if ((double)wdt < (double)hi_f - (double)lo_f) wdt = std::nextafterf(wdt, INFINITY);
+        wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
+        if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
+        std::memcpy(&width_bits, &wdt, 4);
+        // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
+        float hi_ext = std::isinf(wdt) || std::isinf(lo_f) ? hi_f : (float)((double)lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
+        hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
+        ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
+    }
     const int n_ipairs_all = (int)((ctx->N + 255) / 256);
     const int n_launches = std::max(1, ctx->up_chunks);
     if (mode == MODE_HIST) CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
@@ -851,19 +878,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             b.lo_f = lo_f;
             b.hi_f = hi_f;
             b.open_low = std::isinf(lo_f) ? 1 : 0;
-            {
-                float wdt = std::isinf(lo_f) || std::isinf(hi_f) ? INFINITY : (float)((double)hi_f - (double)lo_f);
-                if ((double)wdt < (double)hi_f - (double)lo_f) wdt = std::nextafterf(wdt, INFINITY);
-                wdt = std::nextafterf(std::nextafterf(wdt, INFINITY), INFINITY); // strictly above the rounded difference of any pair
-                if (!(wdt > 0.0f)) wdt = std::numeric_limits<float>::min();
-                uint32_t wb;
-                std::memcpy(&wb, &wdt, 4);
-                b.width_bits = wb;
-                // every collected distance satisfies fl(d2 - lo) < wdt, hence d2 < lo + wdt (1 + 2^-24): an exclusive upper key bound
-                float hi_ext = std::isinf(wdt) || std::isinf(lo_f) ? hi_f : (float)((double)lo_f + (double)wdt * (1.0 + 1.0 / 8388608.0));
-                hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
-                ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
-            }
+            b.width_bits = width_bits;
             b.lo_key = lo;
             b.shift = shift;
             b.below = ctx->below;
@@ -1240,8 +1255,14 @@ int one_step(svgdb_ctx *ctx)
         ctx->opt.bias1 = 1.0 - std::pow(ctx->opt.beta1, (double)ctx->counter);
         ctx->opt.bias2 = 1.0 - std::pow(ctx->opt.beta2, (double)ctx->counter);
     }
-    TRY(prepare_and_phi(ctx, false));
-    TRY(allgather_rows(ctx, ctx->X[ctx->cur ^ 1], ctx->d));
+    {
+        int rc = prepare_and_phi(ctx, false);
+        if (rc == SVGDB_OK) rc = allgather_rows(ctx, ctx->X[ctx->cur ^ 1], ctx->d);
+        if (rc != SVGDB_OK) { // the step was not enqueued: it does not count (Adam's bias correction depends on the counter)
+            --ctx->counter;
+            return rc;
+        }
+    }
     ctx->cur ^= 1;
     ++ctx->stats.iterations;
     if (ctx->profiling) {
@@ -1440,6 +1461,8 @@ int svgdb_set_particles(svgdb_ctx *ctx, const double *X)
 {
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
     CU(cudaMemcpyAsync(ctx->X[ctx->cur], X, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // the caller may reuse or free X as soon as this returns, also when X is pinned memory (svgdb_host_alloc)
+    CU(cudaStreamSynchronize(ctx->stream));
     // the median bracket prediction is only a hint (verified by exact counts), so it survives re-uploads
     return SVGDB_OK;
 }
@@ -1463,13 +1486,27 @@ int svgdb_local_rows(svgdb_ctx *ctx, int64_t *row0, int64_t *n_rows)
     return SVGDB_OK;
 }
 
-int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local)
+} // extern "C"
+
+namespace {
+// enqueue only: svgdb_step_host returns after a synchronize of its own, so the caller's buffer is read before it gets control back
+int set_particles_rows_async(svgdb_ctx *ctx, const double *rows_local)
 {
-    if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
     if (ctx->n_rows > 0)
         CU(cudaMemcpyAsync(ctx->X[ctx->cur] + (size_t)ctx->row0 * ctx->d, rows_local, (size_t)ctx->n_rows * ctx->d * sizeof(double),
                            cudaMemcpyHostToDevice, ctx->stream));
     return allgather_rows(ctx, ctx->X[ctx->cur], ctx->d); // every rank needs all particles: NVLink instead of N x PCIe
+}
+} // namespace
+
+extern "C" {
+
+int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local)
+{
+    if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    TRY(set_particles_rows_async(ctx, rows_local));
+    CU(cudaStreamSynchronize(ctx->stream)); // rows_local may be reused or freed on return
+    return SVGDB_OK;
 }
 
 int svgdb_get_particles_rows(svgdb_ctx *ctx, double *rows_local)
@@ -1639,7 +1676,7 @@ int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int
         }
         ctx->up_chunks = 4;
     } else {
-        TRY(svgdb_set_particles_rows(ctx, rows_in));
+        TRY(set_particles_rows_async(ctx, rows_in));
     }
     for (int64_t it = 0; it + 1 < iters; ++it) {
         const int rc = one_step(ctx);

@@ -205,6 +205,22 @@ class GaussianRBFKernel:
         self.scale_method_ = ScaleMethod(method)
         self.fixed_scale_ = float(fixed_scale)
         self.target_model_ = model
+        self.kernel_parameters_ = []
+
+    def UpdateParameters(self, params):
+        """Kernel::UpdateParameters.  With ScaleMethod.Median / Hessian the reference recomputes the scale from the particles at every
+        Step and overwrites whatever was set (GaussianRBFKernel.hpp:141-156), so the parameters only take effect for the constant
+        scale (ScaleMethod.Fixed), where params[0] must be a I."""
+        A = np.atleast_2d(np.asarray(params[0], dtype=np.float64))
+        d = self.dimension_
+        if A.shape != (d, d):
+            raise DimensionMismatchException("Kernel parameter matrix must be %d x %d." % (d, d))
+        self.kernel_parameters_ = [A.copy()]
+        if self.scale_method_ == ScaleMethod.Fixed:
+            a = float(A[0, 0])
+            if not np.array_equal(A, a * np.eye(d)):
+                raise ValueError("SVGDCpp: [Argument Error] the device RBF kernel takes a scalar scale: A must be a * I.")
+            self.fixed_scale_ = a
 
 
 # ---- optimizers ---------------------------------------------------------------------------------
@@ -374,10 +390,8 @@ class SVGD:
         self.model_.Initialize()
         self._check(self._lib.svgdb_initialize(self._ctx))
 
-    def UpdateKernelParameters(self, params):  # SVGD.hpp:304-321: params[0] = A = a I
-        A = np.asarray(params[0], dtype=np.float64)
-        self.kernel_.scale_method_ = ScaleMethod.Fixed
-        self.kernel_.fixed_scale_ = float(A[0, 0]) if A.ndim == 2 else float(A)
+    def UpdateKernelParameters(self, params):  # SVGD.hpp:304-321: params[0] = A (= a I for the constant scale)
+        self.kernel_.UpdateParameters(params)
         self._push_kernel()
 
     def UpdateModelParameters(self, params):  # SVGD.hpp:328-332

@@ -36,7 +36,7 @@ def main():
     prec = _capi.PRECISION_TC32 if args.precision == "tc32" else _capi.PRECISION_F64
     dp = C.POINTER(C.c_double)
     failures = 0
-    for n, d, iters in [(301, 5, 6), (1000, 64, 5), (2500, 33, 4)]:
+    for n, d, iters in [(301, 5, 6), (1000, 64, 5), (2500, 33, 4), (9001, 64, 3)]:
         rng = np.random.default_rng(n)
         A = rng.standard_normal((d, d))
         cov = np.ascontiguousarray(A @ A.T / d + 0.5 * np.eye(d))
@@ -70,6 +70,14 @@ def main():
         s1 = np.empty_like(X0)
         cnt = C.c_uint64(0)
         check(lib.svgdb_get_opt_state(ctx, s1.ctypes.data_as(dp), None, C.byref(cnt)))
+        # two more iterations through the host-buffer call, every rank moving only its own rows (svgdb_step_host under sharding)
+        r0, nr = C.c_int64(0), C.c_int64(0)
+        check(lib.svgdb_local_rows(ctx, C.byref(r0), C.byref(nr)))
+        mine = np.ascontiguousarray(X[r0.value:r0.value + nr.value])
+        check(lib.svgdb_step_host(ctx, mine.ctypes.data_as(dp), mine.ctypes.data_as(dp), 2))
+        X2 = np.empty_like(X0)
+        check(lib.svgdb_get_particles(ctx, X2.ctypes.data_as(dp)))
+        own_rows_ok = bool(np.array_equal(mine, X2[r0.value:r0.value + nr.value]))
         lib.svgdb_destroy(ctx)
         if rank == 0:
             import oracle_binding as oracle
@@ -82,9 +90,15 @@ def main():
             e_phi = np.max(np.abs(phi - phi_ref)) / np.max(np.abs(phi_ref))
             e_x = np.sqrt(np.mean((X - X_ref) ** 2)) / np.sqrt(np.mean(X_ref ** 2))
             tol = (1e-12, 1e-11, 1e-9) if prec == _capi.PRECISION_F64 else (1e-5, 2e-4, 1e-3)
-            ok = e_a < tol[0] and e_phi < tol[1] and e_x < tol[2] and cnt.value == iters and np.all(np.isfinite(s1))
-            print("world=%d %s n=%d d=%d: a err %.2e, phi err %.2e, trajectory rms err %.2e -> %s" % (world, args.precision, n, d, e_a, e_phi, e_x, "OK" if ok else "FAIL"), flush=True)
+            X2_ref = oracle.svgd_run(X0, iters + 2, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1)
+            e_x2 = np.sqrt(np.mean((X2 - X2_ref) ** 2)) / np.sqrt(np.mean(X2_ref ** 2))
+            ok = e_a < tol[0] and e_phi < tol[1] and e_x < tol[2] and e_x2 < tol[2] and cnt.value == iters and np.all(np.isfinite(s1))
+            print("world=%d %s n=%d d=%d: a err %.2e, phi err %.2e, trajectory rms err %.2e, after 2 more steps through svgdb_step_host %.2e -> %s"
+                  % (world, args.precision, n, d, e_a, e_phi, e_x, e_x2, "OK" if ok else "FAIL"), flush=True)
             failures += 0 if ok else 1
+        if not own_rows_ok:
+            print("rank %d: svgdb_step_host returned rows that differ from the device's copy" % rank, flush=True)
+            failures += 1
     if prec == _capi.PRECISION_F64:  # ScaleMethod::Hessian: per-rank Hessian partial sums, one all-reduce
         n, d, iters = 700, 12, 4
         rng = np.random.default_rng(7)
@@ -133,7 +147,7 @@ def main():
             print("world=%d f64 Hessian scale n=%d d=%d: A err %.2e, phi err %.2e, trajectory rms err %.2e -> %s" % (world, n, d, e_a, e_phi, e_x, "OK" if ok else "FAIL"), flush=True)
             failures += 0 if ok else 1
     f = torch.tensor([failures], device="cuda")
-    dist.broadcast(f, 0)
+    dist.all_reduce(f)
     dist.destroy_process_group()
     sys.exit(int(f.item()))
 

@@ -277,8 +277,8 @@ def test_kernel_matrices_match_oracle(sv, oracle, method):
     x0 = np.asfortranarray(1.1 * rng.standard_normal((d, n)))
     X = np.array(x0.T, order="C", copy=True)
     model = sv.MultivariateNormal(mu, cov)
-    scale = {"median": sv.ScaleMethod.Median, "hessian": sv.ScaleMethod.Hessian, "fixed": sv.ScaleMethod.Median}[method]
-    kernel = sv.GaussianRBFKernel(x0, scale, model)
+    scale = {"median": sv.ScaleMethod.Median, "hessian": sv.ScaleMethod.Hessian, "fixed": sv.ScaleMethod.Fixed}[method]
+    kernel = sv.GaussianRBFKernel(x0, scale, model, fixed_scale=1.0)
     svgd = sv.SVGD(d, 1, x0, kernel, model, sv.AdaGrad(d, n, 0.1))
     if method == "fixed":
         svgd.UpdateKernelParameters([0.37 * np.eye(d)])

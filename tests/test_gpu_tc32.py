@@ -231,3 +231,120 @@ def test_tc32_chunked_distance_pass_counts_every_pair(sv, oracle, monkeypatch):
                   % (capacity, call, abs(st["last_scale"] - a_ref) / a_ref, st["median_passes"], st["median_bracket_hits"]))
             assert abs(st["last_scale"] - a_ref) <= 3e-6 * a_ref
         svgd.close()
+
+
+def _mixture(sv, means, covs):
+    model = None
+    for k in range(len(means)):
+        m = sv.MultivariateNormal(means[k], covs[k])
+        model = m if model is None else model + m
+    return model
+
+
+def test_tc32_baseline_configs_c1_c2(sv, oracle):
+    """BASELINE.json configs[0] / configs[1] as worded there on the tensor-core path: C1 = the MVN example's target,
+    N = 100, Adam, 1000 iterations; C2 = three Gaussians, N = 1000, AdaGrad, median scale, 1000 iterations (the reference's
+    gmm_example.cpp:9-49 with a third component).  Finals within the stated 1e-3 of the oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import load_golden
+    from svgdcpp_b200 import synth
+
+    g1, g2 = load_golden("mvn_example"), load_golden("gmm_example")
+    n, d, iters = 100, 2, 1000
+    mu, cov = np.asarray(g1["means"][0], dtype=np.float64), np.asarray(g1["covs"][0], dtype=np.float64)
+    x0 = np.asfortranarray(3.0 * synth.uniform_pm1(1001, (n, d)).T)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = sv.MultivariateNormal(mu, cov)
+    svgd = sv.SVGD(d, iters, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999), precision=TC32)
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, iters, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1)
+    rms = np.sqrt(np.mean((x0.T - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+    mx = np.max(np.abs(x0.T - ref)) / np.max(np.abs(ref))
+    print("TC32 C1 (N=100, Adam, 1000 it): finals rms rel err %.3g, max rel err %.3g" % (rms, mx))
+    assert rms < 1e-3
+    n, iters = 1000, 1000
+    means = np.array(list(g2["means"]) + [[-3.0, -3.5]], dtype=np.float64)
+    covs = np.array(list(g2["covs"]) + [g1["covs"][0]], dtype=np.float64)
+    x0 = np.asfortranarray(8.0 * synth.uniform_pm1(1002, (n, d)).T)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = _mixture(sv, means, covs)
+    svgd = sv.SVGD(d, iters, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1), precision=TC32)
+    phi, a = svgd.ComputePhi()
+    a_ref = oracle.rbf_median_scale(X0)
+    phi_ref = oracle.phi(X0, oracle.mvn_sum_logp_grad(X0, means, covs, lse=True), a_ref)
+    e_phi = np.max(np.abs(phi.T - phi_ref)) / np.max(np.abs(phi_ref))
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, iters, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+    rms = np.sqrt(np.mean((x0.T - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+    mx = np.max(np.abs(x0.T - ref)) / np.max(np.abs(ref))
+    print("TC32 C2 (three Gaussians, N=1000, AdaGrad, 1000 it): phi max-rel err %.3g, finals rms rel err %.3g, max rel err %.3g" % (e_phi, rms, mx))
+    assert abs(a - a_ref) <= 1e-5 * a_ref
+    assert e_phi < PHI_TOL
+    assert rms < 1e-3
+
+
+@pytest.mark.parametrize("n,d,C", [(2048, 64, 4), (1536, 48, 16)])
+def test_tc32_mixture_slice(sv, oracle, n, d, C):
+    """The config-4 recipe (well-separated components, particles drawn around them: SURVEY.md 8d) at a dimension the d <= 64
+    tensor-core kernels serve: kernel scale, mixture gradient (log-sum-exp), phi and 20 AdaGrad steps against the oracle."""
+    from svgdcpp_b200 import synth
+
+    x0, means, covs = synth.gmm_problem(n, d, C)
+    X0 = np.array(x0.T, order="C", copy=True)
+    model = _mixture(sv, means, covs)
+    svgd = sv.SVGD(d, 20, x0, sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1), precision=TC32)
+    phi, a = svgd.ComputePhi()
+    a_ref = oracle.rbf_median_scale(X0)
+    G_ref = oracle.mvn_sum_logp_grad(X0, means, covs, lse=True)
+    G = svgd.EvaluateLogModelGrad()
+    phi_ref = oracle.phi(X0, G_ref, a_ref)
+    e_phi = np.max(np.abs(phi.T - phi_ref)) / np.max(np.abs(phi_ref))
+    e_g = np.max(np.abs(G.T - G_ref)) / np.max(np.abs(G_ref))
+    svgd.Initialize()
+    svgd.Run()
+    svgd.close()
+    ref = oracle.svgd_run(X0, 20, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+    rms = np.sqrt(np.mean((x0.T - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+    print("TC32 mixture slice n=%d d=%d C=%d: a rel err %.3g, grad rel err %.3g, phi max-rel err %.3g, 20-step rms rel err %.3g"
+          % (n, d, C, abs(a - a_ref) / a_ref, e_g, e_phi, rms))
+    assert abs(a - a_ref) <= 1e-5 * a_ref
+    assert e_g < 1e-10
+    assert e_phi < PHI_TOL
+    assert rms < 1e-3
+
+
+def test_tc32_full_size_100_steps_vs_f64(sv):
+    """100 iterations of parity at config 3 (N = 65,536, d = 64, Adam, median scale every step).  The CPU oracle cannot
+    run this size; the FP64 device path (itself pinned to the oracle at small sizes, 1e-9) is the reference trajectory."""
+    from svgdcpp_b200 import synth
+
+    n, d, iters = 65536, 64, 100
+    x0, means, covs = synth.mvn_problem(n, d)
+    model = sv.MultivariateNormal(means[0], covs[0])
+    finals, scales = [], []
+    for prec in (0, TC32):
+        x = x0.copy(order="F")
+        svgd = sv.SVGD(d, iters, x, sv.GaussianRBFKernel(x, sv.ScaleMethod.Median, model), model, sv.Adam(d, n, 0.1, 0.9, 0.999), precision=prec)
+        svgd.Initialize()
+        svgd.Run()
+        st = svgd.Stats()
+        scales.append(st["last_scale"])
+        print("precision %d: %d iterations, %d distance passes, %d bracket hits, last scale %.9g" % (prec, st["iterations"], st["median_passes"], st["median_bracket_hits"], st["last_scale"]))
+        svgd.close()
+        finals.append(np.array(x.T, order="C", copy=True))
+    ref, got = finals
+    diff = got - ref
+    rms = np.sqrt(np.mean(diff ** 2)) / np.sqrt(np.mean(ref ** 2))
+    mx = np.max(np.abs(diff)) / np.max(np.abs(ref))
+    moved = np.sqrt(np.mean((ref - x0.T) ** 2)) / np.sqrt(np.mean(ref ** 2))
+    print("N=65536 d=64, 100 Adam steps, TC32 vs the FP64 device path: finals rms rel err %.3g, max rel err %.3g (particles moved %.3g), scale rel diff %.3g"
+          % (rms, mx, moved, abs(scales[1] - scales[0]) / scales[0]))
+    assert np.all(np.isfinite(got))
+    assert moved > 0.05
+    assert rms < 1e-3 and mx < 1e-2
+    assert abs(scales[1] - scales[0]) <= 1e-4 * scales[0]
