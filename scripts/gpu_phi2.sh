@@ -12,12 +12,12 @@ fi
 for cfg in "$@"; do
   set -- $cfg
   F="$OUT/bench_p$1_d$2"
-  SVGDB_PHI_POLY=$1 SVGDB_PHI_DBG=$2 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$F.json" 2> "$F.err"
+  SVGDB_PHI_POLY=$1 SVGDB_PHI_DBG=$2 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-f64-leg --no-parity > "$F.json" 2> "$F.err"
   echo "poly $1 dbg $2: exit $?"; python - "$F.json" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read())
-    print("  ms/step %.3f  phi %.3f ms  frac %.3f  finite %s" % (d["ms_per_step"], d["roofline"]["phase_ms_per_step"]["phi"], d["roofline"]["frac"], d["config"]["finite"]))
+    print("  ms/step %.3f  phi %.3f ms  frac %.3f  finite %s" % (d["ms_per_step"], d["roofline"]["phase_ms_per_step"]["phi"], d["roofline"]["frac_sustained"], d["config"]["finite"]))
 except Exception as e:
     print("  no bench line:", e)
 PY

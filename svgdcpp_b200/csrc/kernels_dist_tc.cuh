@@ -33,7 +33,8 @@ static_assert(HIST_BINS * 8 <= D2_CWARPS * TC_WBUF * 4, "histogram must fit the 
 
 // Operand rows for the distance pass, one warp per particle (scale 1):
 //   XA2[row] = -2 [hi | lo] (row operand -> TMEM),  XBD[row] = [hi | lo] (column operand, TMA),
-//   UA[row] = [r0 r1 r2 1 1 1 0..],  WB (core-matrix order) = [1 1 1 r0 r1 r2 0..],  r = |x~|^2 as a 3-term bf16 split;
+//   UA[row] = [r0 r1 r2 1 1 1 0..],  WB (core-matrix order) = [1 1 1 r0 r1 r2 1 1 1 0..],  r = |x~|^2 as a 3-term bf16 split
+//   (columns 6..8 of the row chunk are filled by a FOLD pass with the split of -lo, see dist2_tc32_kernel);
 //   padding rows carry r = +inf: their distances never count.  rt[row] = r (FP64) for the pair kernel's later use.
 // Rows [row_begin, n_rows_a) of the row-side arrays (and of the column-side ones below n_rows_b).
 __global__ void split_dist2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, int64_t n, int64_t row_begin, int64_t n_rows_a,
@@ -68,7 +69,7 @@ __global__ void split_dist2_kernel(const double *__restrict__ X, const double *_
         UA[row * 16 + lane] = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : lane < 6 ? one : zero;
         if (row < n_rows_b)
             *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<uint8_t *>(WB) + (row >> 7) * P2_W_BYTES + p2_ex_offset((uint32_t)(row & 127), (uint32_t)lane)) =
-                lane < 3 ? one : lane == 3 ? r0 : lane == 4 ? r1 : lane == 5 ? r2 : zero;
+                lane < 3 ? one : lane == 3 ? r0 : lane == 4 ? r1 : lane == 5 ? r2 : lane < 9 ? one : zero; // 6..8: multiply the folded -lo of the row chunk
     }
 }
 
@@ -104,6 +105,9 @@ struct Dist2Args {
     int jt_begin;                           // column tiles below this one are left out (they belong to an earlier launch of the same pass)
     int pair_offset, pair_stride, n_ipairs; // this rank owns i-pairs offset, offset + stride, ... (n_ipairs of them)
     float lo_f, hi_f;
+    // FOLD instantiations: -lo_f rides in the norm K chunk as a three-term bf16 split (exact: 24 bits), so the accumulator IS
+    // t = d2 - lo_f and the epilogue needs no subtraction; fold_l01 = bf16 pair (L0, L1), fold_l2 = (L2, 0)
+    unsigned int fold_l01, fold_l2;
     unsigned int width_bits; // IEEE bits of a float > fl(hi_f - lo_f): d2 is collected iff 0 <= fl(d2 - lo_f) < width
     int open_low;            // lo_f = -inf (nothing lies below): collect d2 < hi_f by a plain compare
     unsigned long long lo_key;
@@ -122,7 +126,10 @@ __device__ __forceinline__ bool d2_segment(const Dist2Args &p, D2Cursor &cur, lo
 {
     if (pos >= end) return false;
     for (;;) { // advance to the i-pair containing pos
-        const int ip = p.pair_offset + p.pair_stride * cur.l;
+        // the rank's i-pairs are visited in folded order 0, n-1, 1, n-2, ...: a long row of the triangle is followed by a short one,
+        // so every CTA's contiguous range holds about the same number of segments (each segment start costs a pipeline refill)
+        const int lf = (cur.l & 1) ? p.n_ipairs - 1 - (cur.l >> 1) : (cur.l >> 1);
+        const int ip = p.pair_offset + p.pair_stride * lf;
         const int j0 = max(2 * ip, p.jt_begin);
         const long long len = max(0, p.n_jtiles - j0);
         if (pos < cur.base + len) {
@@ -150,7 +157,12 @@ __device__ __forceinline__ long long d2_total_units(const Dist2Args &p)
 // pairs, which the launcher checks.
 // GATED: the bracket is expected to hold so few distances that most 32 x 32 chunks contain none -- count and test with 3
 // instructions per distance and take the collecting path only for chunks where some lane saw a hit.
-template <int MODE, bool GATED>
+// FOLD (collecting passes over a predicted bracket): the accumulator is t = d2 - lo (see Dist2Args); counting is the sign bit of t,
+// the bracket test is bits(t) <u bits(width).  GATED + FOLD: 1.5 instructions per distance (LEA.HI per value, one three-input
+// FMNMX3 over |t| per two values; a chunk whose smallest |t| is below the width takes the exact collecting path).  The values of
+// a pass are the roundings of ITS OWN accumulation, so passes that must agree with each other on every single distance
+// (histogram narrowing followed by a collecting pass) all run unfolded.
+template <int MODE, bool GATED, bool FOLD>
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Dist2Args p)
 {
@@ -174,6 +186,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     unsigned long long *shist = (unsigned long long *)wbuf; // [HIST_BINS] 64-bit (a CTA sees > 2^32 pairs at N = 1M); MODE_HIST only: aliases the warp staging buffers
     unsigned int *shist32 = (unsigned int *)wbuf;           // [HIST_BINS] the 32-bit variant
     constexpr bool HIST32 = MODE == MODE_HIST && GATED;
+    static_assert(!(FOLD && MODE == MODE_HIST), "histogram passes run unfolded");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -301,7 +314,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                 } else {
                     if (count + tot * cur_wgt > (unsigned int)TC_WBUF) { dist_flush2(mybuf, count, p.cand, p.cand_count, p.capacity); count = 0; }
                     if (tot * cur_wgt > (unsigned int)TC_WBUF) { // more than an empty buffer holds: straight to global
-                        for (uint32_t e = 0; e < mine; ++e) dist_append_global2(lds_f32(priv_base + 128u * e), cur_wgt, p.cand, p.cand_count, p.capacity);
+                        for (uint32_t e = 0; e < mine; ++e)
+                            dist_append_global2(lds_f32(priv_base + 128u * e) + (FOLD ? p.lo_f : 0.0f), cur_wgt, p.cand, p.cand_count, p.capacity);
                     } else {
                         uint32_t incl = mine; // inclusive scan over lanes
 #pragma unroll
@@ -311,7 +325,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                         }
                         uint32_t dst = wbuf_base + 4u * (count + (incl - mine) * cur_wgt);
                         for (uint32_t e = 0; e < mine; ++e) {
-                            const float v = lds_f32(priv_base + 128u * e);
+                            const float v = lds_f32(priv_base + 128u * e) + (FOLD ? p.lo_f : 0.0f); // staged as t = d2 - lo when folded
                             sts_f32(dst, v); dst += 4u;
                             if (cur_wgt == 2u) { sts_f32(dst, v); dst += 4u; }
                         }
@@ -355,7 +369,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     }
                     const uint4 *usrc = reinterpret_cast<const uint4 *>(p.UA + i * 16);
                     const uint32_t aex = smem_u32(sAex + w * P2_AEX_BYTES) + p2_ex_offset((uint32_t)row, 0);
-                    const uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
+                    uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
+                    if (FOLD) { ua0.w = p.fold_l01; ua1.x = p.fold_l2; } // columns 6, 7, 8 = -lo (the column chunk carries ones there)
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex), "r"(ua0.x), "r"(ua0.y), "r"(ua0.z), "r"(ua0.w) : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex + 128u), "r"(ua1.x), "r"(ua1.y), "r"(ua1.z), "r"(ua1.w) : "memory");
                     fence_proxy_async();
@@ -391,10 +406,11 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     if (lane == 0) mbar_arrive(s_free + 3 * w + buf); // this warp's part of the accumulator is in registers
                     if (p.dbg == 1 || p.dbg == 3) continue;
                     if (wgt != cur_wgt) { compact(); cur_wgt = wgt; }
-                    if (has_diag) { // |x_i - x_i|^2 = 0 exactly (diagonal tiles only)
+                    if (has_diag) { // |x_i - x_i|^2 = 0 exactly (diagonal tiles only); folded: t = 0 - lo
+                        const uint32_t dz = FOLD ? __float_as_uint(-p.lo_f) : 0u;
 #pragma unroll
                         for (int q = 0; q < 32; ++q)
-                            if (dcol == q) r0[q] = 0u;
+                            if (dcol == q) r0[q] = dz;
                     }
                     // Five instructions per distance, no branch: t = d2 - lo; count += sign bit of t (d2 < lo exactly: a negative
                     // difference never rounds to +0); in = bits(t) < bits(width) as UNSIGNED integers (0 <= t < width; negative
@@ -417,7 +433,45 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     };
                     if (p.dbg == 2) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) cnt4[q & 3] += __float_as_uint(__uint_as_float(r0[q]) - lo) >> 31;
+                        for (int q = 0; q < 32; ++q) cnt4[q & 3] += FOLD ? r0[q] >> 31 : __float_as_uint(__uint_as_float(r0[q]) - lo) >> 31;
+                    } else if (FOLD && MODE == MODE_COLLECT) {
+                        // the accumulator is t = d2 - lo: count += sign bit (LEA.HI); in the bracket iff bits(t) <u bits(width)
+                        if (GATED) {
+                            // ... which needs |t| < width: one FMNMX3 over |t| per two distances decides whether the chunk holds a candidate
+                            float m0 = INFINITY, m1 = INFINITY;
+#pragma unroll
+                            for (int q = 0; q < 32; q += 4) {
+                                cnt4[0] += r0[q] >> 31;
+                                cnt4[1] += r0[q + 1] >> 31;
+                                cnt4[2] += r0[q + 2] >> 31;
+                                cnt4[3] += r0[q + 3] >> 31;
+                                m0 = fminf(fminf(m0, fabsf(__uint_as_float(r0[q]))), fabsf(__uint_as_float(r0[q + 1])));
+                                m1 = fminf(fminf(m1, fabsf(__uint_as_float(r0[q + 2]))), fabsf(__uint_as_float(r0[q + 3])));
+                            }
+                            if (__any_sync(0xffffffffu, fminf(m0, m1) < __uint_as_float(wbits))) { // rare: collect with the exact test
+#pragma unroll
+                                for (int q = 0; q < 32; ++q)
+                                    asm volatile("{\n\t.reg .pred pi;\n\t"
+                                                 "setp.lt.u32 pi, %1, %2;\n\t"
+                                                 "@pi st.shared.b32 [%0], %1;\n\t"
+                                                 "@pi add.u32 %0, %0, 128;\n\t}"
+                                                 : "+r"(paddr)
+                                                 : "r"(r0[q]), "r"(wbits)
+                                                 : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) {
+                                cnt4[q & 3] += r0[q] >> 31;
+                                asm volatile("{\n\t.reg .pred pi;\n\t"
+                                             "setp.lt.u32 pi, %1, %2;\n\t"
+                                             "@pi st.shared.b32 [%0], %1;\n\t"
+                                             "@pi add.u32 %0, %0, 128;\n\t}"
+                                             : "+r"(paddr)
+                                             : "r"(r0[q]), "r"(wbits)
+                                             : "memory");
+                            }
+                        }
                     } else if (GATED && MODE == MODE_COLLECT && !open_low) {
                         // t = d2 - lo; count += sign(t); flag |= bits(t) <u bits(width): FADD, LEA.HI, ISETP.OR per distance
                         unsigned int flag;

@@ -165,6 +165,8 @@ struct svgdb_ctx {
     CUtensorMap mapBD{};
     int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
     int dist_gated = -1;   // SVGDB_DIST_GATED=0/1 forces the flat / gated counting epilogue (default: chosen per pass)
+    bool dist_fold_next = false; // the next collecting pass runs over a predicted bracket (set by median_scale): it may fold -lo into the operands
+    int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
@@ -328,6 +330,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     CU(cudaMalloc(&ctx->XBD, np * 128 * 2));
     TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
+    if (const char *e = std::getenv("SVGDB_DIST_FOLD")) ctx->dist_fold = std::atoi(e);
     TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
@@ -560,6 +563,7 @@ int median_scale(svgdb_ctx *ctx)
         if (!(predicted > 0.0) || !std::isfinite(predicted)) predicted = m[0];
         const double dl = std::min(delta_max, std::max(ctx->delta, 2e-5));
         uint64_t klo = key_of(std::max(predicted * (1.0 - dl), 0.0)), khi = key_of(predicted * (1.0 + dl)) + 1;
+        ctx->dist_fold_next = true;
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
         TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
         uint64_t b = ctx->hs->below;
@@ -842,6 +846,27 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
         hi_ext = std::nextafterf(std::nextafterf(hi_ext, INFINITY), INFINITY);
         ctx->collect_hi_ext = std::isinf(hi_ext) ? hi : std::max<uint64_t>(hi, key_of((double)hi_ext) + 1);
     }
+    // A collecting pass over a predicted bracket defines its own values: -lo is folded into the norm K chunk (exact three-term bf16
+    // split of the float) and the accumulator is d2 - lo.  Passes that must agree with one another distance by distance (narrowing
+    // histograms and the collecting pass that follows them) run unfolded.
+    const bool fold = mode == MODE_COLLECT && ctx->dist_fold_next && ctx->dist_fold != 0 && std::isfinite(lo_f) && std::isfinite(hi_f);
+    ctx->dist_fold_next = false;
+    uint32_t fold_l01 = 0, fold_l2 = 0;
+    if (fold) {
+        float rem = -lo_f;
+        uint16_t t[3];
+        for (int k = 0; k < 3; ++k) { // bf16 by truncation: the remainder of a 24-bit float is exact after three 8-bit terms
+            uint32_t bits;
+            std::memcpy(&bits, &rem, 4);
+            bits &= 0xFFFF0000u;
+            float term;
+            std::memcpy(&term, &bits, 4);
+            t[k] = (uint16_t)(bits >> 16);
+            rem -= term;
+        }
+        fold_l01 = (uint32_t)t[0] | ((uint32_t)t[1] << 16);
+        fold_l2 = (uint32_t)t[2];
+    }
     const int n_ipairs_all = (int)((ctx->N + 255) / 256);
     const int n_launches = std::max(1, ctx->up_chunks);
     if (mode == MODE_HIST) CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
@@ -879,6 +904,8 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             b.hi_f = hi_f;
             b.open_low = std::isinf(lo_f) ? 1 : 0;
             b.width_bits = width_bits;
+            b.fold_l01 = fold_l01;
+            b.fold_l2 = fold_l2;
             b.lo_key = lo;
             b.shift = shift;
             b.below = ctx->below;
@@ -895,11 +922,11 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             if (mode == MODE_HIST) {
                 // a unit is 256 x 128 pairs of weight <= 2: 32-bit shared counters while a CTA's share stays below 2^32
                 const bool hist32 = (units / grid + 1) * 65536ll < 4294967296ll;
-                if (hist32) dist2_tc32_kernel<MODE_HIST, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
-                else dist2_tc32_kernel<MODE_HIST, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                if (hist32) dist2_tc32_kernel<MODE_HIST, true, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                else dist2_tc32_kernel<MODE_HIST, false, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
             } else {
                 // expected share of pairs inside the bracket (density of the last pass x relative width): with fewer than ~1 hit per
-                // two 32 x 32 warp chunks the gated epilogue (3 instructions per distance + rare collection) is the cheaper one
+                // two 32 x 32 warp chunks the gated epilogue (1.5 instructions per distance + rare collection) is the cheaper one
                 double width_rel = 1.0;
                 if (lo > 0 && hi < KEY_END) {
                     double dlo, dhi;
@@ -908,8 +935,13 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
                     if (dhi > 0.0) width_rel = (dhi - dlo) / dhi;
                 }
                 const bool gated = ctx->dist_gated >= 0 ? ctx->dist_gated != 0 : ctx->density * width_rel * 1024.0 < 0.5;
-                if (gated) dist2_tc32_kernel<MODE_COLLECT, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
-                else dist2_tc32_kernel<MODE_COLLECT, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                if (fold) {
+                    if (gated) dist2_tc32_kernel<MODE_COLLECT, true, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                    else dist2_tc32_kernel<MODE_COLLECT, false, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                } else {
+                    if (gated) dist2_tc32_kernel<MODE_COLLECT, true, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                    else dist2_tc32_kernel<MODE_COLLECT, false, false><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
+                }
             }
             KERNEL_CHECK();
         }
@@ -1366,10 +1398,15 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         SVGDB_PHI2_ATTR(6)
         SVGDB_PHI2_ATTR(8)
 #undef SVGDB_PHI2_ATTR
-        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
-        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_HIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
-        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
-        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
+#define SVGDB_D2_ATTR(M, G, F) \
+    CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<M, G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
+        SVGDB_D2_ATTR(MODE_HIST, false, false)
+        SVGDB_D2_ATTR(MODE_HIST, true, false)
+        SVGDB_D2_ATTR(MODE_COLLECT, false, false)
+        SVGDB_D2_ATTR(MODE_COLLECT, true, false)
+        SVGDB_D2_ATTR(MODE_COLLECT, false, true)
+        SVGDB_D2_ATTR(MODE_COLLECT, true, true)
+#undef SVGDB_D2_ATTR
     }
 #endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
@@ -1949,9 +1986,13 @@ int svgdb_time_kernel(svgdb_ctx *ctx, int which, int reps, int variant, double r
         const uint64_t klo = key_of(std::max(m * (1.0 - rel_halfwidth), 0.0)), khi = key_of(m * (1.0 + rel_halfwidth)) + 1;
         rc = launch_dist_operands(ctx);
         ctx->dist_dbg_mode = variant;
+        ctx->dist_fold_next = true;
         if (rc == SVGDB_OK) rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0); // warm-up
         cudaEventRecord(e0, ctx->stream);
-        for (int r = 0; rc == SVGDB_OK && r < reps; ++r) rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0);
+        for (int r = 0; rc == SVGDB_OK && r < reps; ++r) {
+            ctx->dist_fold_next = true;
+            rc = launch_dist_pass_tc32(ctx, MODE_COLLECT, klo, khi, 0);
+        }
         cudaEventRecord(e1, ctx->stream);
         ctx->dist_dbg_mode = 0;
     } else if (which == 1) { // pair-interaction kernel (with its operand preparation and the optimizer epilogue kernel), no state change
