@@ -31,6 +31,7 @@ struct SVGDOptions {
     bool LogIntermediateMatrices = false; /* inspection path: K and grad K are formed on demand, one step at a time (small n) */
     int Device = 0;                                  /* CUDA device ordinal */
     int PrecisionMode = SVGDB_PRECISION_F64;         /* svgdb_precision */
+    int Tc32Variant = SVGDB_TC32_AUTO;               /* svgdb_tc32_variant: arithmetic of the tensor-core pair kernel (TC32 mode only) */
     SVGDOptions() {}
 };
 
@@ -38,7 +39,10 @@ class SVGD {
 public:
     SVGD(const SVGDOptions &o)
         : SVGD(o.Dimension, o.NumIterations, o.CoordinateMatrixPtr, o.KernelPtr, o.ModelPtr, o.OptimizerPtr, o.LowerBound, o.UpperBound,
-               o.Parallel, o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath, o.Device, o.PrecisionMode) {}
+               o.Parallel, o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath, o.Device, o.PrecisionMode)
+    {
+        Check(svgdb_set_tc32_variant(ctx_, o.Tc32Variant));
+    }
 
     SVGD(const size_t &dim, const size_t &iter, const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const std::shared_ptr<Kernel> &kernel_ptr,
          const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const bool &parallel = false)

@@ -48,6 +48,13 @@ typedef enum {
  * fp16, FP64 optimizer state; error bound stated in DESIGN.md "Precision modes". */
 typedef enum { SVGDB_PRECISION_F64 = 0, SVGDB_PRECISION_TC32 = 1 } svgdb_precision;
 
+/* Arithmetic variant of the tensor-core pair kernel under SVGDB_PRECISION_TC32 (no reference counterpart; ignored in F64 mode).
+ * FAST: column particle and kernel values carry one fp16 term each (phi within 2e-4 of max|phi|; the error terms are zero-mean
+ * and average over a row's neighbours).  PRECISE: both particles and the kernel values carry two fp16 terms (1.5x the MMAs; phi
+ * within 1e-5 of max|phi|).  AUTO (default): FAST for one Gaussian target with at least 16,384 particles, PRECISE otherwise
+ * (mixtures, gradient hooks, small particle sets). */
+typedef enum { SVGDB_TC32_AUTO = 0, SVGDB_TC32_FAST = 1, SVGDB_TC32_PRECISE = 2 } svgdb_tc32_variant;
+
 /* GaussianRBFKernel::ScaleMethod (Kernel/GaussianRBFKernel.hpp:25-30) plus a constant scale
  * (the reference's "TODO: constant scale", used by tests/test_svgd.cpp:97-106 via a bare Kernel). */
 typedef enum { SVGDB_SCALE_MEDIAN = 0, SVGDB_SCALE_HESSIAN = 1, SVGDB_SCALE_FIXED = 2 } svgdb_scale_method;
@@ -114,6 +121,9 @@ int svgdb_set_model_device_hook(svgdb_ctx *ctx, svgdb_grad_fn fn, void *user);
 /* ---- kernel: GaussianRBFKernel(x0, ScaleMethod, model) (Kernel/GaussianRBFKernel.hpp:47-88);
  * the scale is recomputed from the current X every Step (:141-156). */
 int svgdb_set_kernel_rbf(svgdb_ctx *ctx, int scale_method, double fixed_a);
+
+/* Selects the arithmetic variant of the tensor-core pair kernel (svgdb_tc32_variant above). */
+int svgdb_set_tc32_variant(svgdb_ctx *ctx, int variant);
 
 /* ---- optimizer: Adam(dim,n,lr,b1,b2,eps) / AdaGrad(dim,n,lr,eps) / RMSProp(dim,n,lr,b,eps)
  * (Optimizer/Adam.hpp:33-49, AdaGrad.hpp:31-37, RMSProp.hpp:33-46); beta1 is RMSProp's decay. */

@@ -11,6 +11,7 @@ OK, ERR_INVALID, ERR_DIMENSION, ERR_UNSET, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_NU
 PRECISION_F64, PRECISION_TC32 = 0, 1
 SCALE_MEDIAN, SCALE_HESSIAN, SCALE_FIXED = 0, 1, 2
 OPT_ADAGRAD, OPT_ADAM, OPT_RMSPROP = 0, 1, 2
+TC32_AUTO, TC32_FAST, TC32_PRECISE = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _ctx = C.c_void_p
@@ -66,6 +67,7 @@ SIGNATURES = {
     "svgdb_local_rows": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "svgdb_set_particles_rows": (C.c_int, [_ctx, _dp]),
     "svgdb_get_particles_rows": (C.c_int, [_ctx, _dp]),
+    "svgdb_set_tc32_variant": (C.c_int, [_ctx, C.c_int]),
     "svgdb_time_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float)]),
 }
 

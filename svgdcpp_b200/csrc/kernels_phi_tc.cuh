@@ -32,15 +32,22 @@
 namespace svgdb {
 namespace tc {
 
-constexpr int P2_STAGES = 4;
-constexpr uint32_t P2_XB_BYTES = 16384;               // 128 particles x 64 fp16 (128 B rows, SWIZZLE_128B)
 constexpr uint32_t P2_VBOX = 8192;                    // 64 coordinates x 64 particles fp16
 constexpr uint32_t P2_V_BYTES = 4 * P2_VBOX;          // hi j[0,64) | hi j[64,128) | lo j[0,64) | lo j[64,128)
 constexpr uint32_t P2_W_BYTES = 4096;                 // 128 particles x 16 fp16 exponent-offset columns (no-swizzle core-matrix order)
-constexpr uint32_t P2_STAGE = 53248;                  // 52 KB per stage (1024-aligned)
-constexpr uint32_t P2_TX = P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES;
 constexpr uint32_t P2_AEX_BYTES = 4096;               // per i-tile: 128 rows x 16 fp16 exponent-offset columns
-constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 2 * P2_AEX_BYTES + 256 + 1024;
+// Two arithmetic variants of the pair kernel (DESIGN.md "Precision modes"):
+//   fast    : S = (hi_i + lo_i) . hi_j,  E = fp16(2^15 k),  Phi += E . (v_hi + v_lo)                  16 + 1 MMAs per 128 x 64 unit
+//   PRECISE : S = hi_i.hi_j + lo_i.hi_j + hi_i.lo_j (both particles 22 bits),  E = E_hi + E_lo (two fp16 terms),
+//             Phi += E_hi.v_hi + E_hi.v_lo + E_lo.v_hi                                                  24 + 1 MMAs per unit
+template <bool PRECISE>
+struct P2Cfg {
+    static constexpr int STAGES = PRECISE ? 3 : 4;
+    static constexpr uint32_t XB_BYTES = PRECISE ? 32768u : 16384u; // 128 particles x 64 fp16 hi (+ 64 fp16 lo): 128 B rows, SWIZZLE_128B boxes
+    static constexpr uint32_t STAGE = XB_BYTES + P2_V_BYTES + P2_W_BYTES; // 52 KB / 68 KB (1024-aligned)
+    static constexpr uint32_t TX = STAGE;
+    static constexpr uint32_t SMEM = STAGES * STAGE + 2 * P2_AEX_BYTES + 256 + 1024;
+};
 // K-major operand of 16 fp16 columns WITHOUT swizzle: 8 x 16 B core matrices; row r, column k lives at
 // (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2   (LBO = 128 B between the two K halves, SBO = 256 B per 8 rows)
 __host__ __device__ constexpr uint32_t p2_ex_offset(uint32_t r, uint32_t k) { return (r >> 3) * 256u + (k >> 3) * 128u + (r & 7u) * 16u + (k & 7u) * 2u; }
@@ -67,9 +74,10 @@ __device__ __forceinline__ void split3_f16(double v, __half &t0, __half &t1, __h
 //     UA[row] = [u0 u1 u2 1 1 1 0..]      WB[row] = [1 1 1 w0 w1 w2 0..]      (three-term fp16 splits)
 // so that the accumulator of the first contraction IS the exponent.  WB is stored per 128-particle tile in the
 // core-matrix order the MMA reads (p2_ex_offset), UA as plain rows.
+// precise != 0: the column operand keeps both terms, XB2[row] = [hi | lo] (128 columns per row), and w = -|hi + lo|^2/2.
 __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
                                   int64_t n, int64_t n_rows_a, int64_t n_rows_b, int d, __half *__restrict__ XA2,
-                                  __half *__restrict__ XB2, __half *__restrict__ UA, __half *__restrict__ WB)
+                                  __half *__restrict__ XB2, __half *__restrict__ UA, __half *__restrict__ WB, int precise)
 {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
@@ -90,7 +98,14 @@ __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__
         s_hi += hid * hid;
         XA2[row * P2_A_LD + k] = hi;
         XA2[row * P2_A_LD + 64 + k] = lo;
-        if (row < n_rows_b) XB2[row * 64 + k] = hi;
+        if (row < n_rows_b) {
+            if (precise) {
+                XB2[row * 128 + k] = hi;
+                XB2[row * 128 + 64 + k] = lo;
+            } else {
+                XB2[row * 64 + k] = hi;
+            }
+        }
     }
     for (int o = 16; o; o >>= 1) {
         s_full += __shfl_xor_sync(0xffffffffu, s_full, o);
@@ -99,7 +114,7 @@ __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__
     if (lane < 16) {
         __half u0, u1, u2, w0, w1, w2;
         split3_f16((row < n) ? 15.0 - 0.5 * s_full : 0.0, u0, u1, u2);
-        split3_f16((row < n) ? -0.5 * s_hi : -60000.0, w0, w1, w2);
+        split3_f16((row < n) ? -0.5 * (precise ? s_full : s_hi) : -60000.0, w0, w1, w2);
         const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
         const __half ua = lane == 0 ? u0 : lane == 1 ? u1 : lane == 2 ? u2 : lane < 6 ? one : zero;
         const __half wb = lane < 3 ? one : lane == 3 ? w0 : lane == 4 ? w1 : lane == 5 ? w2 : zero;
@@ -171,6 +186,17 @@ __device__ __forceinline__ void acc_f16x2(float &acc_lo, float &acc_hi, uint32_t
         : "+f"(acc_lo), "+f"(acc_hi)
         : "r"(p));
 }
+// fp16x2( e_lo - float(p.lo), e_hi - float(p.hi) ): the second fp16 term of a value whose first term is already packed in p
+// (FHFMA: fp16 x fp16 + fp32, one instruction per element)
+__device__ __forceinline__ uint32_t residual_f16x2(uint32_t p, float e_lo, float e_hi)
+{
+    float r0, r1;
+    asm("{\n\t.reg .f16 a, b, m;\n\tmov.b32 {a, b}, %2;\n\tmov.b16 m, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, a, m, %3;\n\tfma.rn.f32.f16 %1, b, m, %4;\n\t}"
+        : "=f"(r0), "=f"(r1)
+        : "r"(p), "f"(e_lo), "f"(e_hi));
+    return pack_f16x2(r0, r1);
+}
 // 2^x for x <= 15 on the FMA / ALU pipes: round-to-nearest split x = n + f (magic-number add), degree-4
 // polynomial for 2^f on [-1/2, 1/2], exponent add.  x is clamped at
 // -126 (results that small round to +0 in fp16 anyway; -inf from padding columns lands there too).
@@ -227,10 +253,13 @@ __device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, lo
 constexpr int P2_EWARPS = 16;
 constexpr int P2_THREADS = (P2_EWARPS + 3) * 32;
 
-template <int POLY>
+template <int POLY, bool PRECISE>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p)
 {
+    using Cfg = P2Cfg<PRECISE>;
+    constexpr int P2_STAGES = Cfg::STAGES;
+    constexpr uint32_t P2_XB_BYTES = Cfg::XB_BYTES, P2_STAGE = Cfg::STAGE, P2_TX = Cfg::TX;
     // this CTA's contiguous range of (i-pair, j-tile) work units
     const long long units = (long long)p.n_ipairs * p.n_jtiles;
     const long long u_beg = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
@@ -275,6 +304,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     const int j0 = jt * TC_TILE;
                     mbar_arrive_expect_tx(full + slot, P2_TX);
                     tma_load_2d(st, &mapB, 0, j0, full + slot);
+                    if (PRECISE) tma_load_2d(st + 16384, &mapB, 64, j0, full + slot); // lo_j
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
@@ -307,6 +337,13 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dS, aT + 40, bl + 2, idesc);
                 umma_f16_ts2<true>(dS, aT + 48, bl + 4, idesc);
                 umma_f16_ts2<true>(dS, aT + 56, bl + 6, idesc);
+                if (PRECISE) { // hi_i . lo_j
+                    const uint32_t bo = bl + (16384 >> 4);
+                    umma_f16_ts2<true>(dS, aT, bo, idesc);
+                    umma_f16_ts2<true>(dS, aT + 8, bo + 2, idesc);
+                    umma_f16_ts2<true>(dS, aT + 16, bo + 4, idesc);
+                    umma_f16_ts2<true>(dS, aT + 24, bo + 6, idesc);
+                }
                 // + u_i + w_j: the 16-column exponent-offset chunks (no-swizzle operands, both from shared memory)
                 umma_f16_ss_desc(dS, aex_lo0 + w * (P2_AEX_BYTES >> 4), DESC_HI_K_NOSW,
                                  wb_lo0 + slot * (P2_STAGE >> 4) + k * (2048 >> 4), DESC_HI_K_NOSW, idesc);
@@ -332,6 +369,12 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
                 umma_f16_ts2<true>(dP, e + 32, vl + 4, idesc);
                 umma_f16_ts2<true>(dP, e + 40, vl + 6, idesc);
+                if (PRECISE) { // E_lo . v_hi  (E_lo sits in the second 16 columns of each 32-column half)
+                    umma_f16_ts2<true>(dP, e + 16, vh, idesc);
+                    umma_f16_ts2<true>(dP, e + 24, vh + 2, idesc);
+                    umma_f16_ts2<true>(dP, e + 48, vh + 4, idesc);
+                    umma_f16_ts2<true>(dP, e + 56, vh + 6, idesc);
+                }
                 if (k == 1) umma_commit(empty + slot);
                 if (k == 1 && last) umma_commit(phi_full + w);
             }
@@ -420,6 +463,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 tmem_ld_wait();
                 if (tracer) TC_TRACE(1 + w, gt, 2 + 3 * k);
                 uint32_t pk[16];
+                uint32_t pl[PRECISE ? 16 : 1]; // E_lo = fp16(E - E_hi)
                 auto exp_chunk = [&](auto diag_tag) {
                     constexpr bool DIAG = decltype(diag_tag)::value;
 #pragma unroll
@@ -437,19 +481,31 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                         }
                         pk[2 * q4] = pack_f16x2(e0, e1);
                         pk[2 * q4 + 1] = pack_f16x2(e2, e3);
-                        acc_f16x2(rs0, rs1, pk[2 * q4]);
-                        acc_f16x2(rs2, rs3, pk[2 * q4 + 1]);
+                        if constexpr (PRECISE) {
+                            // the row sum adds E itself (E_hi + E_lo represents it to 2^-22; the diagonal 2^15 is exact in both)
+                            rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
+                            pl[2 * q4] = residual_f16x2(pk[2 * q4], e0, e1);
+                            pl[2 * q4 + 1] = residual_f16x2(pk[2 * q4 + 1], e2, e3);
+                        } else {
+                            acc_f16x2(rs0, rs1, pk[2 * q4]);
+                            acc_f16x2(rs2, rs3, pk[2 * q4 + 1]);
+                        }
                     }
                 };
                 if (p.dbg != 0) {
 #pragma unroll
                     for (int z = 0; z < 16; ++z) pk[z] = r0[z] ^ r0[z + 16];
+                    if constexpr (PRECISE) {
+#pragma unroll
+                        for (int z = 0; z < 16; ++z) pl[z] = r0[z] & r0[z + 16];
+                    }
                 } else if (has_diag) {
                     exp_chunk(std::true_type{});
                 } else {
                     exp_chunk(std::false_type{});
                 }
                 tmem_st16(tS, pk);
+                if constexpr (PRECISE) tmem_st16(tS + 16, pl);
                 const bool more = q + 1 < nunits;
                 const int kn = (int)((q + 1) & 1u);
                 const uint32_t gn = g + ((q + 1) >> 1);

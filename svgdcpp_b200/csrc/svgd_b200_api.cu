@@ -169,6 +169,7 @@ struct svgdb_ctx {
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
+    int tc32_variant = SVGDB_TC32_AUTO; // svgdb_set_tc32_variant / SVGDB_TC32_VARIANT: arithmetic of the tensor-core pair kernel
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
     int host_chunks = 1;  // SVGDB_HOST_CHUNKS=0 (measurement aid): svgdb_step_host moves the particles in one piece each way
 
@@ -334,6 +335,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
     TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_HOST_CHUNKS")) ctx->host_chunks = std::atoi(e);
     return SVGDB_OK;
@@ -953,6 +955,17 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     return SVGDB_OK;
 }
 
+// Which arithmetic the tensor-core pair kernel runs (kernels_phi_tc.cuh, DESIGN.md "Precision modes").  The fast variant's error
+// terms (fp16 rounding of the column particle and of the kernel values) are zero-mean and average over a row's effective neighbours:
+// it is the default only where that holds by construction -- one Gaussian target and at least 16,384 particles; mixtures, user
+// models behind the gradient hook and small particle sets get the precise variant (1.5x the MMAs).
+bool tc32_precise(const svgdb_ctx *ctx)
+{
+    if (ctx->tc32_variant == SVGDB_TC32_FAST) return false;
+    if (ctx->tc32_variant == SVGDB_TC32_PRECISE) return true;
+    return !(ctx->model_kind == MODEL_MVN_SUM && ctx->C == 1 && ctx->N >= 16384);
+}
+
 // The particle-side operands of the pair kernel (they need X and the bandwidth, not V) and the zeroed accumulator.
 int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
 {
@@ -961,8 +974,11 @@ int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
     CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, stream));
     // the bandwidth is folded into the operands, so the accumulator of the first contraction is the exponent
     const int64_t rows_a = ctx->n_pad128 + 256;
+    // precise variant: the column operand keeps both fp16 terms; it goes into the distance pass's column buffer (free by now)
+    const bool precise = tc32_precise(ctx);
     split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a, ctx->n_pad128,
-                                                                         ctx->d, ctx->XA2, ctx->XB2, ctx->UA2, ctx->WB2);
+                                                                         ctx->d, ctx->XA2, precise ? reinterpret_cast<__half *>(ctx->XBD) : ctx->XB2,
+                                                                         ctx->UA2, ctx->WB2, precise ? 1 : 0);
     KERNEL_CHECK();
     return SVGDB_OK;
 }
@@ -1004,15 +1020,16 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         const long long units = (long long)a.n_ipairs * a.n_jtiles;
         const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units); // persistent: one CTA per SM
         if (ch == 0) prof_mark(ctx, 5);
-#define SVGDB_PHI2_CASE(P) \
-    case P: phi2_tc32_kernel<P><<<grid, P2_THREADS, P2_SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a); break;
+        const bool precise = tc32_precise(ctx);
+#define SVGDB_PHI2_CASE(P)                                                                                                            \
+    case P:                                                                                                                           \
+        if (precise) phi2_tc32_kernel<P, true><<<grid, P2_THREADS, P2Cfg<true>::SMEM, ctx->stream>>>(ctx->mapBD, ctx->mapV2, a);      \
+        else phi2_tc32_kernel<P, false><<<grid, P2_THREADS, P2Cfg<false>::SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a);            \
+        break;
         switch (ctx->phi_poly) {
             SVGDB_PHI2_CASE(0)
-            SVGDB_PHI2_CASE(2)
             SVGDB_PHI2_CASE(4)
-            SVGDB_PHI2_CASE(6)
-            SVGDB_PHI2_CASE(8)
-        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 2, 4, 6 or 8");
+        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 or 4");
         }
 #undef SVGDB_PHI2_CASE
         KERNEL_CHECK();
@@ -1390,13 +1407,11 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     if (precision_mode == SVGDB_PRECISION_TC32) {
         if (d > svgdb::tc::TC_D)
             return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
-#define SVGDB_PHI2_ATTR(P) \
-    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2_SMEM));
+#define SVGDB_PHI2_ATTR(P)                                                                                                                        \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));
         SVGDB_PHI2_ATTR(0)
-        SVGDB_PHI2_ATTR(2)
         SVGDB_PHI2_ATTR(4)
-        SVGDB_PHI2_ATTR(6)
-        SVGDB_PHI2_ATTR(8)
 #undef SVGDB_PHI2_ATTR
 #define SVGDB_D2_ATTR(M, G, F) \
     CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<M, G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
@@ -1609,6 +1624,15 @@ int svgdb_set_kernel_rbf(svgdb_ctx *ctx, int scale_method, double fixed_a)
     ctx->scale_method = scale_method;
     ctx->fixed_a = fixed_a;
     ctx->kernel_set = true;
+    return SVGDB_OK;
+}
+
+int svgdb_set_tc32_variant(svgdb_ctx *ctx, int variant)
+{
+    if (!ctx) return SVGDB_ERR_INVALID;
+    if (variant != SVGDB_TC32_AUTO && variant != SVGDB_TC32_FAST && variant != SVGDB_TC32_PRECISE)
+        return fail(ctx, SVGDB_ERR_INVALID, "unknown TC32 variant");
+    ctx->tc32_variant = variant;
     return SVGDB_OK;
 }
 

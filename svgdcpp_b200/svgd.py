@@ -285,6 +285,7 @@ class SVGDOptions:  # SVGD.hpp:27-52 (+ device / precision / sharding fields wit
         self.LogIntermediateMatrices = False
         self.Device = 0
         self.Precision = _capi.PRECISION_F64
+        self.Tc32Variant = _capi.TC32_AUTO
 
 
 class SVGD:
@@ -293,14 +294,14 @@ class SVGD:
 
     def __init__(self, dim, iter=None, coord_mat=None, kernel=None, model=None, optimizer=None,
                  bound_lower=None, bound_upper=None, parallel=False, log_intermediate_matrices=False,
-                 intermediate_matrices_output_path="log.txt", device=0, precision=_capi.PRECISION_F64):
+                 intermediate_matrices_output_path="log.txt", device=0, precision=_capi.PRECISION_F64, tc32_variant=_capi.TC32_AUTO):
         if isinstance(dim, SVGDOptions):
             o = dim
             dim, iter, coord_mat, kernel, model, optimizer = (o.Dimension, o.NumIterations, o.CoordinateMatrixPtr,
                                                               o.KernelPtr, o.ModelPtr, o.OptimizerPtr)
             bound_lower, bound_upper, parallel = o.LowerBound, o.UpperBound, o.Parallel
             log_intermediate_matrices, intermediate_matrices_output_path = o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath
-            device, precision = o.Device, o.Precision
+            device, precision, tc32_variant = o.Device, o.Precision, o.Tc32Variant
         self._lib = _capi.load()
         self._ctx = C.c_void_p()
         if coord_mat is None:
@@ -332,6 +333,7 @@ class SVGD:
 
         rc = self._lib.svgdb_create(C.byref(self._ctx), int(device), self.num_particles_, self.dimension_, int(precision))
         self._check(rc)
+        self._check(self._lib.svgdb_set_tc32_variant(self._ctx, int(tc32_variant)))
         if self.check_bounds_:
             lbf = np.ascontiguousarray(np.broadcast_to(lb, (self.dimension_,)) if lb.size == 1 else lb)
             ubf = np.ascontiguousarray(np.broadcast_to(ub, (self.dimension_,)) if ub.size == 1 else ub)
