@@ -1,0 +1,444 @@
+// kernels_phi_wide.cuh — the tensor-core pair-interaction kernel of SVGDB_PRECISION_TC32 for 64 < d <= 256 (sm_100a).
+//
+// Same arithmetic as kernels_phi_tc.cuh (both variants, see P2Cfg there): y = sqrt(2c)(x - mean) split in fp16 terms, the first
+// contraction produces the exponent log2(2^15 k) directly (offsets in a 16-column K chunk), one ex2 per pair, kernel values as
+// fp16 term(s), second contraction against [v_hi ; v_lo].  Reference: SVGD.hpp:407-454, Kernel/GaussianRBFKernel.hpp:75-81.
+//
+// What changes is the TMEM budget (512 columns per SM).  With DP = d padded to a multiple of 64, the row operand [hi | lo] of a
+// 128-particle i-tile takes DP columns and the accumulator Phi another DP, so:
+//   * ONE i-tile per CTA (the d <= 64 kernel holds two);
+//   * DP = 128, 192: A (DP) + Phi (DP) + two S/E unit buffers (2 x 64) fit: one pass over j;
+//   * DP = 256: Phi is produced in G = 2 column groups of GW = 128 (A 256 + Phi 128 + S/E 128 = 512), each a pass over j that
+//     recomputes S and E (DESIGN.md "TC32 beyond d = 64").
+// A unit is 128 x 64 pairs; a pipeline stage holds one unit's column operands: X^_j (64 particles x DP fp16, KC = DP / 64 boxes of
+// 64 x 64, SWIZZLE_128B; twice that for the PRECISE variant), the V^T tile of the group ([v_hi ; v_lo], 2 GW rows x 64 particles)
+// and the 2 KB exponent-offset chunk.  Warps: 8 exp warps (row quadrant x 32-column half), one TMA producer, one MMA issuer.
+// Per unit the MMA warp issues  S(u+1) before PV(u)  so the tensor pipe has the next unit's first contraction to work on while the
+// exp warps turn S(u) into E(u); at these dimensions the tensor pipe (>= 1000 cycles per unit) dominates the exponentials (512).
+#pragma once
+#include "kernels_phi_tc.cuh"
+
+namespace svgdb {
+namespace tc {
+
+template <int DP, bool PRECISE>
+struct PWCfg {
+    static_assert(DP == 128 || DP == 192 || DP == 256, "padded dimension");
+    static constexpr int KC = DP / 64;                 // 64-column K chunks of the first contraction
+    static constexpr int GW = DP == 256 ? 128 : DP;    // Phi columns per pass
+    static constexpr int G = DP / GW;                  // passes over j
+    static constexpr uint32_t XB_BYTES = 8192u * KC * (PRECISE ? 2u : 1u);
+    static constexpr uint32_t V_BYTES = 2u * GW * 128u; // [v_hi ; v_lo] rows of the group, 128 B (64 particles) each
+    static constexpr uint32_t W_BYTES = 2048;           // 64 particles x 16 fp16 exponent-offset columns
+    static constexpr uint32_t STAGE = XB_BYTES + V_BYTES + W_BYTES;
+    static constexpr uint32_t FIXED = P2_AEX_BYTES + 512 + 1024;
+    static constexpr int STAGES_FIT = (int)((227u * 1024u - FIXED) / STAGE);
+    static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+    static constexpr uint32_t SMEM = STAGES * STAGE + FIXED;
+    static constexpr uint32_t COL_PHI = 128, COL_A = 128 + GW;
+    static constexpr int PHI_LD = DP + 16;              // phi_buf row: [0, DP) sum_j E v, [DP] sum_j E
+    static_assert(STAGES >= 2, "two pipeline stages must fit");
+    static_assert(COL_A + DP <= 512, "TMEM budget");
+    static_assert(STAGE % 1024 == 0, "stages keep the 1024-byte alignment of the swizzled boxes");
+};
+
+constexpr int PW_EWARPS = 8;
+constexpr int PW_THREADS = (PW_EWARPS + 2) * 32;
+
+// ---- operand preparation (one warp per particle; any DP) ---------------------------------------------------------------
+// XA[row] = [hi(DP) | lo(DP)] (row operand), XB[row] = [hi(DP)] or [hi(DP) | lo(DP)] (column operand, PRECISE), UA / WB as in
+// split_phi2_kernel (the WB chunk of a 128-particle tile in core-matrix order: a 64-particle unit is one 2 KB half of it).
+__global__ void split_phiw_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
+                                  int64_t n, int64_t n_rows_a, int64_t n_rows_b, int d, int dp, __half *__restrict__ XA,
+                                  __half *__restrict__ XB, __half *__restrict__ UA, __half *__restrict__ WB, int precise)
+{
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_a) return;
+    const double c = (*a_ptr) * 1.4426950408889634; // a log2(e)
+    const double scale = sqrt(2.0 * c);
+    const int ldb = precise ? 2 * dp : dp;
+    double s_full = 0.0, s_hi = 0.0;
+    for (int k = lane; k < dp; k += 32) {
+        double y = 0.0;
+        if (row < n && k < d) y = scale * (X[row * d + k] - colsum[k] / (double)n);
+        const __half hi = __double2half(y);
+        const double hid = (double)__half2float(hi);
+        const __half lo = __double2half(y - hid);
+        const double full = hid + (double)__half2float(lo);
+        s_full += full * full;
+        s_hi += hid * hid;
+        XA[row * (2 * dp) + k] = hi;
+        XA[row * (2 * dp) + dp + k] = lo;
+        if (row < n_rows_b) {
+            XB[row * ldb + k] = hi;
+            if (precise) XB[row * ldb + dp + k] = lo;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        s_full += __shfl_xor_sync(0xffffffffu, s_full, o);
+        s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
+    }
+    if (lane < 16) {
+        __half u0, u1, u2, w0, w1, w2;
+        split3_f16((row < n) ? 15.0 - 0.5 * s_full : 0.0, u0, u1, u2);
+        split3_f16((row < n) ? -0.5 * (precise ? s_full : s_hi) : -60000.0, w0, w1, w2);
+        const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+        const __half ua = lane == 0 ? u0 : lane == 1 ? u1 : lane == 2 ? u2 : lane < 6 ? one : zero;
+        const __half wb = lane < 3 ? one : lane == 3 ? w0 : lane == 4 ? w1 : lane == 5 ? w2 : zero;
+        UA[row * 16 + lane] = ua;
+        if (row < n_rows_b)
+            *reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(WB) + (row >> 7) * P2_W_BYTES + p2_ex_offset((uint32_t)(row & 127), (uint32_t)lane)) = wb;
+    }
+}
+
+// v~ for any d: the d <= 64 kernel (make_v32_kernel) is dimension-agnostic and reused.
+// V^T (fp16, [2 dp][ldn]): rows [0, dp) v_hi, [dp, 2 dp) v_lo.  One block = 64 particles x 64 coordinates, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+make_vtw_kernel(const float *__restrict__ V32, int64_t n, int64_t ldn, int d, int dp, __half *__restrict__ VT)
+{
+    __shared__ __half tile[128][64 + 2];
+    const int64_t j0 = (int64_t)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64;
+    for (int t = threadIdx.x; t < 64 * 64; t += blockDim.x) {
+        const int jl = t >> 6, c = t & 63;
+        const int64_t j = j0 + jl;
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (j < n && c0 + c < d) {
+            const float v = V32[j * d + c0 + c];
+            hi = __float2half_rn(v);
+            lo = __float2half_rn(v - __half2float(hi));
+        }
+        tile[c][jl] = hi;
+        tile[64 + c][jl] = lo;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 128 * 64; t += blockDim.x) {
+        const int rr = t >> 6, jl = t & 63;
+        const int64_t out_row = rr < 64 ? (int64_t)c0 + rr : (int64_t)dp + c0 + (rr - 64);
+        if (j0 + jl < ldn) VT[out_row * ldn + j0 + jl] = tile[rr][jl];
+    }
+}
+
+struct PhiWArgs {
+    float *phi_buf;        // [n_pad128 + 128][PHI_LD], zeroed; added atomically at segment ends
+    const __half *XA;      // [n_pad128 + 128][2 DP]
+    const __half *UA;      // [n_pad128 + 128][16]
+    const __half *WB;      // [n_pad128 / 128][4 KB]
+    int64_t row0, n_rows;  // this launch's rows
+    int n_junits;          // 64-particle column units (n_pad128 / 64)
+    int n_itiles;          // 128-row i-tiles of this launch
+    int dbg;
+    int *err;
+};
+
+// segment of a CTA: (i-tile, column group) with column units [jb, je)
+struct PWSeg { int it, g, jb, je; };
+template <int G>
+__device__ __forceinline__ bool pw_segment(const PhiWArgs &p, long long &pos, long long end, PWSeg &s)
+{
+    if (pos >= end) return false;
+    const long long L = pos / p.n_junits; // linear (i-tile, group) index
+    s.it = (int)(L / G);
+    s.g = (int)(L - (long long)s.it * G);
+    s.jb = (int)(pos - L * p.n_junits);
+    const long long seg_end = min(end, (L + 1) * p.n_junits);
+    s.je = s.jb + (int)(seg_end - pos);
+    pos = seg_end;
+    return true;
+}
+
+template <int DP, bool PRECISE>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ PhiWArgs p)
+{
+    using Cfg = PWCfg<DP, PRECISE>;
+    constexpr int KC = Cfg::KC, GW = Cfg::GW, G = Cfg::G, STAGES = Cfg::STAGES;
+    constexpr uint32_t STAGE = Cfg::STAGE, XB_BYTES = Cfg::XB_BYTES, V_BYTES = Cfg::V_BYTES;
+    constexpr uint32_t COL_PHI = Cfg::COL_PHI, COL_A = Cfg::COL_A;
+
+    const long long units = (long long)p.n_itiles * G * p.n_junits;
+    const long long u_beg = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
+    if (u_beg >= u_end) return;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sAex = smem + STAGES * STAGE;  // [P2_AEX_BYTES] row exponent-offset chunk of the i-tile
+    uint64_t *bars = (uint64_t *)(sAex + P2_AEX_BYTES);
+    uint64_t *full = bars;                  // [STAGES] TMA bytes landed
+    uint64_t *empty = full + STAGES;        // [STAGES] every MMA reading the stage has completed
+    uint64_t *s_full = empty + STAGES;      // [2] S of the buffer complete
+    uint64_t *e_ready = s_full + 2;         // [2] E of the buffer written (8 warp arrivals)
+    uint64_t *phi_full = e_ready + 2;       // every MMA of the segment complete
+    uint64_t *a_ready = phi_full + 1;       // row operand in TMEM, Phi flushed (8 warp arrivals)
+    uint32_t *tmem_holder = (uint32_t *)(a_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, PW_EWARPS); }
+        mbar_init(phi_full, 1);
+        mbar_init(a_ready, PW_EWARPS);
+        fence_barrier_init();
+    }
+    if (warp == PW_EWARPS) tmem_alloc(tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp == PW_EWARPS) { // ---- TMA producer
+        long long pos = u_beg;
+        PWSeg sg;
+        uint32_t u = 0;
+        bool ok = true;
+        while (ok && pw_segment<G>(p, pos, u_end, sg)) {
+            for (int ju = sg.jb; ok && ju < sg.je; ++ju, ++u) {
+                const uint32_t slot = u % STAGES, use = u / STAGES;
+                if (!mbar_wait(empty + slot, (use & 1) ^ 1, p.err, 110)) { ok = false; break; }
+                if (elect_one()) {
+                    uint8_t *st = smem + slot * STAGE;
+                    const int j0 = ju * 64;
+                    mbar_arrive_expect_tx(full + slot, STAGE);
+#pragma unroll
+                    for (int c = 0; c < KC * (PRECISE ? 2 : 1); ++c) // hi chunks, then lo chunks (columns [DP, 2 DP) of the operand rows)
+                        tma_load_2d(st + c * 8192, &mapB, c * 64, j0, full + slot);
+#pragma unroll
+                    for (int b = 0; b < GW / 64; ++b) {
+                        tma_load_2d(st + XB_BYTES + b * 8192, &mapV, j0, sg.g * GW + b * 64, full + slot);                 // v_hi rows of the group
+                        tma_load_2d(st + XB_BYTES + GW * 128 + b * 8192, &mapV, j0, DP + sg.g * GW + b * 64, full + slot); // v_lo rows
+                    }
+                    bulk_load_1d(st + XB_BYTES + V_BYTES, reinterpret_cast<const uint8_t *>(p.WB) + (size_t)ju * 2048, 2048, full + slot);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == PW_EWARPS + 1) { // ---- MMA issuer
+        const uint32_t idesc_s = make_idesc_f16(TC_TILE, 64), idesc_pv = make_idesc_f16(TC_TILE, GW);
+        const uint32_t st_lo0 = desc_lo_k_sw128(smem_u32(smem));
+        const uint32_t aex_lo = desc_lo_k_sw128(smem_u32(sAex)) | DESC_LO_K_NOSW_LBO;
+        const uint32_t wb_lo0 = desc_lo_k_sw128(smem_u32(smem + XB_BYTES + V_BYTES)) | DESC_LO_K_NOSW_LBO;
+        const uint32_t aT = tmem + COL_A;
+        // S(u) into buffer u & 1
+        auto issue_s = [&](uint32_t u) -> bool {
+            const uint32_t slot = u % STAGES, use = u / STAGES, buf = u & 1u;
+            if (!mbar_wait(full + slot, use & 1, p.err, 121)) return false;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t dS = tmem + buf * 64;
+                const uint32_t bh = st_lo0 + slot * (STAGE >> 4);
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (c == 0 && ks == 0) umma_f16_ts2<false>(dS, aT, bh, idesc_s);
+                        else umma_f16_ts2<true>(dS, aT + c * 32 + ks * 8, bh + c * (8192 >> 4) + ks * 2, idesc_s);            // hi_i . hi_j
+                    }
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16_ts2<true>(dS, aT + DP / 2 + c * 32 + ks * 8, bh + c * (8192 >> 4) + ks * 2, idesc_s);        // lo_i . hi_j
+                if (PRECISE) {
+#pragma unroll
+                    for (int c = 0; c < KC; ++c)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16_ts2<true>(dS, aT + c * 32 + ks * 8, bh + (KC + c) * (8192 >> 4) + ks * 2, idesc_s);       // hi_i . lo_j
+                }
+                umma_f16_ss_desc(dS, aex_lo, DESC_HI_K_NOSW, wb_lo0 + slot * (STAGE >> 4), DESC_HI_K_NOSW, idesc_s);          // + u_i + w_j
+                umma_commit(s_full + buf);
+            }
+            __syncwarp();
+            return true;
+        };
+        // Phi += E(u) . [v_hi ; v_lo] of the group
+        auto issue_pv = [&](uint32_t u, bool first, bool last) -> bool {
+            const uint32_t slot = u % STAGES, buf = u & 1u;
+            if (!mbar_wait(e_ready + buf, (u >> 1) & 1, p.err, 122)) return false;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t dP = tmem + COL_PHI, e = tmem + buf * 64;
+                const uint32_t vh = st_lo0 + slot * (STAGE >> 4) + (XB_BYTES >> 4), vl = vh + ((GW * 128) >> 4);
+                const uint32_t ecol[4] = {0u, 8u, 32u, 40u}; // E columns of the four 16-particle K steps
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks == 0) umma_f16_ts2r(dP, e, vh, idesc_pv, first ? 0u : 1u);
+                    else umma_f16_ts2<true>(dP, e + ecol[ks], vh + ks * 2, idesc_pv);                                          // E_hi . v_hi
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16_ts2<true>(dP, e + ecol[ks], vl + ks * 2, idesc_pv);                    // E_hi . v_lo
+                if (PRECISE) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts2<true>(dP, e + 16 + ecol[ks], vh + ks * 2, idesc_pv);           // E_lo . v_hi
+                }
+                umma_commit(empty + slot);
+                if (last) umma_commit(phi_full);
+            }
+            __syncwarp();
+            return true;
+        };
+        long long pos = u_beg;
+        PWSeg sg;
+        uint32_t u0 = 0; // units issued before this segment
+        bool ok = true;
+        for (uint32_t seg = 0; ok && pw_segment<G>(p, pos, u_end, sg); ++seg) {
+            const uint32_t nu = (uint32_t)(sg.je - sg.jb);
+            if (!mbar_wait(a_ready, seg & 1, p.err, 120)) { ok = false; break; }
+            ok = issue_s(u0);
+            for (uint32_t t = 0; ok && t < nu; ++t) {
+                if (t + 1 < nu) ok = issue_s(u0 + t + 1);
+                ok = ok && issue_pv(u0 + t, t == 0, t + 1 == nu);
+            }
+            u0 += nu;
+        }
+    } else { // ---- exp warps: thread = particle row of the i-tile, 32-column half h of every unit
+        const int h = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        long long pos = u_beg;
+        PWSeg sg;
+        uint32_t u0 = 0;
+        bool ok = true;
+        for (uint32_t seg = 0; ok && pw_segment<G>(p, pos, u_end, sg); ++seg) {
+            const uint32_t nu = (uint32_t)(sg.je - sg.jb);
+            const int64_t iw0 = p.row0 + (int64_t)sg.it * TC_TILE;
+            const int64_t i = iw0 + row;
+            { // row operand of particle i -> TMEM: hi half by the h = 0 warp, lo half by the h = 1 warp (previous segment complete: phi_full)
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.XA + i * (2 * DP) + DP * h);
+                const uint32_t tA = tmem + COL_A + (DP / 2) * h + lane_base;
+#pragma unroll 1
+                for (int k = 0; k < DP / 32; ++k) { // 16 TMEM columns (32 fp16) per step
+                    uint32_t v[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 x = __ldg(src + 4 * k + q);
+                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                    }
+                    tmem_st16(tA + 16 * k, v);
+                }
+                if (h == 0) { // exponent-offset chunk [u0 u1 u2 1 1 1 0..] -> shared memory, core-matrix order (SS operand)
+                    const uint4 *usrc = reinterpret_cast<const uint4 *>(p.UA + i * 16);
+                    const uint32_t aex = smem_u32(sAex) + p2_ex_offset((uint32_t)row, 0);
+                    const uint4 ua0 = __ldg(usrc), ua1 = __ldg(usrc + 1);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex), "r"(ua0.x), "r"(ua0.y), "r"(ua0.z), "r"(ua0.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(aex + 128u), "r"(ua1.x), "r"(ua1.y), "r"(ua1.z), "r"(ua1.w) : "memory");
+                    fence_proxy_async();
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            for (uint32_t t = 0; ok && t < nu; ++t) {
+                const uint32_t u = u0 + t, buf = u & 1u;
+                const uint32_t tS = tmem + buf * 64 + 32 * h + lane_base;
+                const int64_t j0 = (int64_t)(sg.jb + (int)t) * 64 + 32 * h;
+                const int dq = (int)(i - j0); // column of k(x_i, x_i) among this warp's 32, if inside [0,32)
+                const int64_t r_lo = iw0 + (warp & 3) * 32;
+                const bool has_diag = (j0 < r_lo + 32) && (j0 + 32 > r_lo); // warp-uniform
+                if (!mbar_wait(s_full + buf, (u >> 1) & 1, p.err, 140)) { ok = false; break; }
+                tc_fence_after();
+                uint32_t r0[32];
+                tmem_ld32(tS, r0);
+                tmem_ld_wait();
+                uint32_t pk[16];
+                uint32_t pl[PRECISE ? 16 : 1];
+                auto exp_chunk = [&](auto diag_tag) {
+                    constexpr bool DIAG = decltype(diag_tag)::value;
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        float e0 = ex2_approx(__uint_as_float(r0[4 * q4])), e1 = ex2_approx(__uint_as_float(r0[4 * q4 + 1]));
+                        float e2 = ex2_approx(__uint_as_float(r0[4 * q4 + 2])), e3 = ex2_approx(__uint_as_float(r0[4 * q4 + 3]));
+                        if (DIAG) { // k(x_i, x_i) = exp(0) exactly, like the reference (2^15 after the fp16 scaling)
+                            if (dq == 4 * q4) e0 = 32768.0f;
+                            if (dq == 4 * q4 + 1) e1 = 32768.0f;
+                            if (dq == 4 * q4 + 2) e2 = 32768.0f;
+                            if (dq == 4 * q4 + 3) e3 = 32768.0f;
+                        }
+                        pk[2 * q4] = pack_f16x2(e0, e1);
+                        pk[2 * q4 + 1] = pack_f16x2(e2, e3);
+                        if constexpr (PRECISE) {
+                            rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
+                            pl[2 * q4] = residual_f16x2(pk[2 * q4], e0, e1);
+                            pl[2 * q4 + 1] = residual_f16x2(pk[2 * q4 + 1], e2, e3);
+                        } else {
+                            acc_f16x2(rs0, rs1, pk[2 * q4]);
+                            acc_f16x2(rs2, rs3, pk[2 * q4 + 1]);
+                        }
+                    }
+                };
+                if (has_diag) exp_chunk(std::true_type{});
+                else exp_chunk(std::false_type{});
+                tmem_st16(tS, pk);
+                if constexpr (PRECISE) tmem_st16(tS + 16, pl);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e_ready + buf);
+            }
+            u0 += nu;
+            if (!ok || !mbar_wait(phi_full, seg & 1, p.err, 150)) { ok = false; break; }
+            tc_fence_after();
+            { // ---- flush this warp's half of the group's Phi columns and (first group only) its partial row sum
+                const bool valid = i < p.row0 + p.n_rows;
+                const uint32_t tP = tmem + COL_PHI + (GW / 2) * h + lane_base;
+                float *dst = p.phi_buf + i * Cfg::PHI_LD + sg.g * GW + (GW / 2) * h;
+#pragma unroll 1
+                for (int c0 = 0; c0 < GW / 2; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tP + c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int z = 0; z < 16; ++z) atomicAdd(dst + c0 + z, __uint_as_float(v[z]) * TC_E_UNSCALE);
+                    }
+                }
+                if (valid && sg.g == 0) atomicAdd(p.phi_buf + i * Cfg::PHI_LD + DP, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
+                tc_fence_before(); // the a_ready arrival of the next segment orders these loads before its first MMA
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == PW_EWARPS) tmem_dealloc(tmem, 512);
+}
+
+// phi = (Phi + 2 a x~ rowsum)/n in FP64 from the partial sums, then the optimizer increment and clamp (FP64 state); any row stride.
+struct OptWArgs {
+    const double *X;
+    const double *colsum;
+    const float *phi_buf;
+    const double *a_ptr;
+    int64_t n_total, row0, n_rows, state_row0;
+    int d, ld, ones_col;
+    OptParams opt;
+    double *s1, *s2;
+    const double *lb, *ub;
+    double *X_out, *phi_out;
+};
+__global__ void opt_update_wide_kernel(OptWArgs p)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n_rows * p.d) return;
+    int64_t li = idx / p.d;
+    int c = (int)(idx - li * p.d);
+    int64_t i = p.row0 + li;
+    const int64_t sidx = (i - p.state_row0) * p.d + c;
+    const double a = *p.a_ptr;
+    double x = p.X[i * p.d + c];
+    double xc = x - p.colsum[c] / (double)p.n_total;
+    double acc = (double)p.phi_buf[i * p.ld + c];
+    double rowsum = (double)p.phi_buf[i * p.ld + p.ones_col];
+    double phi = (1.0 / (double)p.n_total) * (acc + 2.0 * a * xc * rowsum);
+    if (p.phi_out != nullptr) {
+        p.phi_out[sidx] = phi;
+    } else {
+        double xn = x + opt_increment(p.opt, phi, p.s1, p.s2, sidx);
+        p.X_out[i * p.d + c] = clamp_coord(xn, p.lb, p.ub, c);
+    }
+}
+
+} // namespace tc
+} // namespace svgdb

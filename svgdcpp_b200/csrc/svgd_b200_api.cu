@@ -27,6 +27,8 @@
 #include "kernels_tc32.cuh"
 #include "kernels_phi_tc.cuh"
 #include "kernels_dist_tc.cuh"
+#include "kernels_phi_wide.cuh"
+#include "kernels_dist_wide.cuh"
 #endif
 
 using namespace svgdb;
@@ -152,6 +154,9 @@ struct svgdb_ctx {
 
     // tensor-core path (SVGDB_PRECISION_TC32)
     int64_t n_pad128 = 0;
+    int dp = 64;       // particle dimension padded to a multiple of 64 (d <= 64: the two-tile kernels; 64 < d <= 256: the wide kernels)
+    bool wide = false; // d > 64
+    CUtensorMap mapBW{}, mapBWP{}, mapVW{}; // wide kernels: column operand hi (XB2, [np][dp]) / [hi | lo] (XBD, [np][2 dp]), V^T ([2 dp][np]); boxes of 64 x 64
     float *phi_buf = nullptr;
     double *rt = nullptr, *colsum = nullptr;
     int *tc_err = nullptr;
@@ -307,33 +312,42 @@ int alloc_tc32(svgdb_ctx *ctx)
 {
     using namespace svgdb::tc;
     ctx->n_pad128 = (ctx->N + 127) / 128 * 128;
-    const size_t np = (size_t)ctx->n_pad128;
+    ctx->wide = ctx->d > TC_D;
+    ctx->dp = ctx->wide ? (ctx->d + 63) / 64 * 64 : 64;
+    const size_t np = (size_t)ctx->n_pad128, dp = (size_t)ctx->dp;
+    const size_t phi_ld = ctx->wide ? dp + 16 : (size_t)TC_PHI_LD;
     CU(cudaMalloc(&ctx->rt, np * 8));
-    CU(cudaMalloc(&ctx->colsum, 64 * 8));
+    CU(cudaMalloc(&ctx->colsum, 256 * 8));
     CU(cudaMalloc(&ctx->tc_err, 4));
     if (std::getenv("SVGDB_TC_TRACE")) {
         CU(cudaMalloc(&ctx->tc_trace, 3 * 64 * 8 * 8));
         CU(cudaMemsetAsync(ctx->tc_trace, 0, 3 * 64 * 8 * 8, ctx->stream));
     }
     // rows of a tile may reach past the last rank-local row: keep a tile of slack
-    CU(cudaMalloc(&ctx->phi_buf, (np + 256) * TC_PHI_LD * 4));
+    CU(cudaMalloc(&ctx->phi_buf, (np + 256) * phi_ld * 4));
     CU(cudaMemsetAsync(ctx->tc_err, 0, 4, ctx->stream));
-    // persistent kernel operands (16-bit elements: the bf16 tensor-map type moves fp16 bit patterns unchanged)
-    CU(cudaMalloc(&ctx->XA2, (np + 256) * P2_A_LD * 2));
-    CU(cudaMalloc(&ctx->XB2, np * 64 * 2));
-    CU(cudaMalloc(&ctx->VT2, (size_t)128 * np * 2));
+    // operands (16-bit elements: the bf16 tensor-map type moves fp16 bit patterns unchanged)
+    CU(cudaMalloc(&ctx->XA2, (np + 256) * 2 * dp * 2));             // row operand [hi | lo]
+    CU(cudaMalloc(&ctx->XB2, np * dp * 2));                         // column operand hi (pair kernel, fast variant)
+    CU(cudaMalloc(&ctx->VT2, (size_t)2 * dp * np * 2));             // [v_hi ; v_lo]^T
     CU(cudaMalloc(&ctx->UA2, (np + 256) * 16 * 2));
     CU(cudaMalloc(&ctx->WB2, np / 128 * P2_W_BYTES));
-    CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * P2_A_LD * 2, ctx->stream));
+    CU(cudaMemsetAsync(ctx->XA2, 0, (np + 256) * 2 * dp * 2, ctx->stream));
     CU(cudaMemsetAsync(ctx->UA2, 0, (np + 256) * 16 * 2, ctx->stream));
     CU(cudaMalloc(&ctx->V32, (size_t)ctx->n_pad * ctx->d * sizeof(float)));
     CU(cudaMemsetAsync(ctx->V32, 0, (size_t)ctx->n_pad * ctx->d * sizeof(float), ctx->stream));
-    CU(cudaMalloc(&ctx->XBD, np * 128 * 2));
-    TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
+    CU(cudaMalloc(&ctx->XBD, np * 2 * dp * 2));                     // column operand [hi | lo] (distance pass; pair kernel, precise variant)
+    if (ctx->wide) {
+        TRY(make_bf16_map(ctx, &ctx->mapBW, ctx->XB2, np, dp, 64));
+        TRY(make_bf16_map(ctx, &ctx->mapBWP, ctx->XBD, np, 2 * dp, 64));
+        TRY(make_bf16_map(ctx, &ctx->mapVW, ctx->VT2, 2 * dp, np, 64));
+    } else {
+        TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
+        TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
+        TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
+    }
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
     if (const char *e = std::getenv("SVGDB_DIST_FOLD")) ctx->dist_fold = std::atoi(e);
-    TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
-    TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
@@ -800,10 +814,30 @@ int launch_make_v(svgdb_ctx *ctx)
 
 #ifdef SVGDB_WITH_TC32
 // column sums (for centring) and the centred bf16-split operand rows of the distance pass
+// column sums of `X` (rows [0, rows)) into ctx->colsum on the main stream
+int launch_colsum(svgdb_ctx *ctx, const double *X, int64_t rows)
+{
+    using namespace svgdb::tc;
+    CU(cudaMemsetAsync(ctx->colsum, 0, 256 * 8, ctx->stream));
+    if (ctx->wide) colsum_wide_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(X, rows, ctx->d, ctx->colsum);
+    else colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(X, rows, ctx->d, ctx->colsum);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
 int launch_dist_operands(svgdb_ctx *ctx)
 {
     using namespace svgdb::tc;
-    CU(cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream));
+    if (ctx->wide) { // 64 < d <= 256: kernels_dist_wide.cuh (no chunked upload on this path)
+        TRY(launch_colsum(ctx, ctx->X[ctx->cur], ctx->N));
+        const int64_t rows_a = ctx->n_pad128 + 256;
+        split_distw_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, ctx->stream>>>(
+            ctx->X[ctx->cur], ctx->colsum, ctx->N, rows_a, ctx->n_pad128, ctx->d, ctx->dp, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
+            reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
+        KERNEL_CHECK();
+        return SVGDB_OK;
+    }
+    CU(cudaMemsetAsync(ctx->colsum, 0, 256 * 8, ctx->stream));
     const int64_t rows_a = ctx->n_pad128 + 256;
     // particles still arriving in row chunks (svgdb_step_host): centre on the mean of the first chunk and prepare its rows only,
     // the other chunks are prepared by the first distance pass as they land (launch_dist_pass_tc32)
@@ -869,10 +903,63 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
         fold_l01 = (uint32_t)t[0] | ((uint32_t)t[1] << 16);
         fold_l2 = (uint32_t)t[2];
     }
-    const int n_ipairs_all = (int)((ctx->N + 255) / 256);
-    const int n_launches = std::max(1, ctx->up_chunks);
     if (mode == MODE_HIST) CU(cudaMemsetAsync(ctx->hist, 0, HIST_BINS * sizeof(unsigned long long), ctx->stream));
     else CU(cudaMemsetAsync(ctx->cand_count, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->wide) { // 64 < d <= 256: one i-tile per CTA (kernels_dist_wide.cuh); i-tiles dealt cyclically to the ranks
+        const int n_itiles_all = (int)(ctx->n_pad128 / 128);
+        const int n_itiles = (n_itiles_all - ctx->rank + ctx->world - 1) / ctx->world;
+        if (n_itiles > 0) {
+            DistWArgs b{};
+            b.XA = reinterpret_cast<const __nv_bfloat16 *>(ctx->XA2);
+            b.UA = reinterpret_cast<const __nv_bfloat16 *>(ctx->UA2);
+            b.WB = reinterpret_cast<const __nv_bfloat16 *>(ctx->WB2);
+            b.n_total = ctx->N;
+            b.n_junits = (int)(ctx->n_pad128 / 64);
+            b.tile_offset = ctx->rank;
+            b.tile_stride = ctx->world;
+            b.n_itiles = n_itiles;
+            b.lo_f = lo_f;
+            b.hi_f = hi_f;
+            b.open_low = std::isinf(lo_f) ? 1 : 0;
+            b.width_bits = width_bits;
+            b.fold_l01 = fold_l01;
+            b.fold_l2 = fold_l2;
+            b.lo_key = lo;
+            b.shift = shift;
+            b.below = ctx->below;
+            b.hist = ctx->hist;
+            b.cand = ctx->cand;
+            b.cand_count = ctx->cand_count;
+            b.capacity = ctx->capacity;
+            b.err = ctx->tc_err;
+            long long units = 0;
+            for (int l = 0; l < n_itiles; ++l) units += std::max(0, b.n_junits - 2 * (b.tile_offset + b.tile_stride * l));
+            const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
+            // variants: histogram (unfolded), collecting unfolded (after a histogram, or an open lower end), collecting folded + gated (predicted bracket)
+#define SVGDB_DW_LAUNCH(DPV)                                                                                                                   \
+    case DPV:                                                                                                                                  \
+        if (mode == MODE_HIST) distw_tc32_kernel<DPV, MODE_HIST, false, false><<<grid, DW_THREADS, DWCfg<DPV>::SMEM, ctx->stream>>>(ctx->mapBWP, b); \
+        else if (fold) distw_tc32_kernel<DPV, MODE_COLLECT, true, true><<<grid, DW_THREADS, DWCfg<DPV>::SMEM, ctx->stream>>>(ctx->mapBWP, b);  \
+        else distw_tc32_kernel<DPV, MODE_COLLECT, false, false><<<grid, DW_THREADS, DWCfg<DPV>::SMEM, ctx->stream>>>(ctx->mapBWP, b);          \
+        break;
+            if (units > 0) {
+                switch (ctx->dp) {
+                    SVGDB_DW_LAUNCH(128)
+                    SVGDB_DW_LAUNCH(192)
+                    SVGDB_DW_LAUNCH(256)
+                default: return fail(ctx, SVGDB_ERR_DIMENSION, "internal: no wide distance kernel for this dimension");
+                }
+                KERNEL_CHECK();
+            }
+#undef SVGDB_DW_LAUNCH
+        }
+        ++ctx->stats.median_passes;
+        TRY(kick_grad(ctx));
+        TRY(reduce_pass_words(ctx, mode));
+        return SVGDB_OK;
+    }
+    const int n_ipairs_all = (int)((ctx->N + 255) / 256);
+    const int n_launches = std::max(1, ctx->up_chunks);
     for (int ch = 0; ch < n_launches; ++ch) {
         int n_ipairs = (n_ipairs_all - ctx->rank + ctx->world - 1) / ctx->world; // this rank's share
         int jt_begin = 0, jt_end = (int)(ctx->n_pad128 / 128);
@@ -971,9 +1058,17 @@ int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
-    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * TC_PHI_LD * 4, stream));
+    CU(cudaMemsetAsync(ctx->phi_buf, 0, (size_t)(ctx->n_pad128 + 256) * (ctx->wide ? ctx->dp + 16 : TC_PHI_LD) * 4, stream));
     // the bandwidth is folded into the operands, so the accumulator of the first contraction is the exponent
     const int64_t rows_a = ctx->n_pad128 + 256;
+    if (ctx->wide) {
+        const bool prec = tc32_precise(ctx);
+        split_phiw_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a, ctx->n_pad128, ctx->d,
+                                                                             ctx->dp, ctx->XA2, prec ? reinterpret_cast<__half *>(ctx->XBD) : ctx->XB2,
+                                                                             ctx->UA2, ctx->WB2, prec ? 1 : 0);
+        KERNEL_CHECK();
+        return SVGDB_OK;
+    }
     // precise variant: the column operand keeps both fp16 terms; it goes into the distance pass's column buffer (free by now)
     const bool precise = tc32_precise(ctx);
     split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a, ctx->n_pad128,
@@ -983,11 +1078,76 @@ int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
     return SVGDB_OK;
 }
 
+// 64 < d <= 256: kernels_phi_wide.cuh (one i-tile per CTA, Phi in column groups at d > 192), then the FP64 optimizer kernel
+int launch_phi_wide(svgdb_ctx *ctx, bool debug_phi)
+{
+    using namespace svgdb::tc;
+    const int dp = ctx->dp;
+    make_vtw_kernel<<<dim3((unsigned)(ctx->n_pad128 / 64), (unsigned)(dp / 64)), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, dp, ctx->VT2);
+    KERNEL_CHECK();
+    PhiWArgs a{};
+    a.phi_buf = ctx->phi_buf;
+    a.XA = ctx->XA2;
+    a.UA = ctx->UA2;
+    a.WB = ctx->WB2;
+    a.row0 = ctx->row0;
+    a.n_rows = ctx->n_rows;
+    a.n_junits = (int)(ctx->n_pad128 / 64);
+    a.n_itiles = (int)((ctx->n_rows + 127) / 128);
+    a.dbg = 0;
+    a.err = ctx->tc_err;
+    const bool precise = tc32_precise(ctx);
+    const int groups = dp == 256 ? 2 : 1;
+    const long long units = (long long)a.n_itiles * groups * a.n_junits;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
+    prof_mark(ctx, 5);
+#define SVGDB_PW_LAUNCH(DPV)                                                                                                                        \
+    case DPV:                                                                                                                                       \
+        if (precise) phiw_tc32_kernel<DPV, true><<<grid, PW_THREADS, PWCfg<DPV, true>::SMEM, ctx->stream>>>(ctx->mapBWP, ctx->mapVW, a);            \
+        else phiw_tc32_kernel<DPV, false><<<grid, PW_THREADS, PWCfg<DPV, false>::SMEM, ctx->stream>>>(ctx->mapBW, ctx->mapVW, a);                   \
+        break;
+    switch (dp) {
+        SVGDB_PW_LAUNCH(128)
+        SVGDB_PW_LAUNCH(192)
+        SVGDB_PW_LAUNCH(256)
+    default: return fail(ctx, SVGDB_ERR_DIMENSION, "internal: no wide pair kernel for this dimension");
+    }
+#undef SVGDB_PW_LAUNCH
+    KERNEL_CHECK();
+    prof_mark(ctx, 6);
+    OptWArgs o{};
+    o.X = ctx->X[ctx->cur];
+    o.colsum = ctx->colsum;
+    o.phi_buf = ctx->phi_buf;
+    o.a_ptr = ctx->a_dev;
+    o.n_total = ctx->N;
+    o.row0 = ctx->row0;
+    o.n_rows = ctx->n_rows;
+    o.state_row0 = ctx->row0;
+    o.d = ctx->d;
+    o.ld = dp + 16;
+    o.ones_col = dp;
+    o.opt = ctx->opt;
+    o.s1 = ctx->s1;
+    o.s2 = ctx->s2;
+    o.lb = ctx->lb;
+    o.ub = ctx->ub;
+    o.X_out = ctx->X[ctx->cur ^ 1];
+    o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+    const int64_t cnt = ctx->n_rows * ctx->d;
+    opt_update_wide_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
+    KERNEL_CHECK();
+    ++ctx->stats.phi_launches;
+    ctx->streamed = false;
+    return SVGDB_OK;
+}
+
 int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false)
 {
     using namespace svgdb::tc;
     if (ctx->n_rows <= 0) return SVGDB_OK;
     if (!x_operands_done) TRY(launch_phi_x_operands(ctx, ctx->stream));
+    if (ctx->wide) return launch_phi_wide(ctx, debug_phi);
     make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
     KERNEL_CHECK();
     // Row chunks.  Normally one; when the updated rows are wanted on the host (svgdb_step_host) the rows are processed in four
@@ -1223,9 +1383,8 @@ int prepare_and_phi_hessian(svgdb_ctx *ctx, bool debug_phi)
     int rc = SVGDB_OK;
 #ifdef SVGDB_WITH_TC32
     if (ctx->precision == SVGDB_PRECISION_TC32) { // the tensor-core pair kernel centres its operands: column sums of Y
-        cudaMemsetAsync(ctx->colsum, 0, 64 * 8, ctx->stream);
-        svgdb::tc::colsum_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(ctx->Y_dev, ctx->N, d, ctx->colsum);
-        rc = launch_phi_x_operands(ctx, ctx->stream);
+        rc = launch_colsum(ctx, ctx->Y_dev, ctx->N);
+        if (rc == SVGDB_OK) rc = launch_phi_x_operands(ctx, ctx->stream);
         if (rc == SVGDB_OK) rc = launch_make_v(ctx);
         prof_mark(ctx, 3);
         if (rc == SVGDB_OK) rc = launch_phi_tc32(ctx, true, true);
@@ -1405,8 +1564,21 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     }
 #ifdef SVGDB_WITH_TC32
     if (precision_mode == SVGDB_PRECISION_TC32) {
-        if (d > svgdb::tc::TC_D)
-            return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 64 in this build; use SVGDB_PRECISION_F64");
+        if (d > 256)
+            return fail(ctx, SVGDB_ERR_DIMENSION, "SVGDB_PRECISION_TC32 supports d <= 256 (the row operand and the accumulator of a 128-particle tile must fit the 512 TMEM columns); use SVGDB_PRECISION_F64");
+        if (d > svgdb::tc::TC_D) {
+            using namespace svgdb::tc;
+#define SVGDB_WIDE_ATTR(DPV)                                                                                                                              \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, false>::SMEM));                    \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, true>::SMEM));                      \
+    CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_HIST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));        \
+    CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_COLLECT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));     \
+    CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_COLLECT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));
+            SVGDB_WIDE_ATTR(128)
+            SVGDB_WIDE_ATTR(192)
+            SVGDB_WIDE_ATTR(256)
+#undef SVGDB_WIDE_ATTR
+        }
 #define SVGDB_PHI2_ATTR(P)                                                                                                                        \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));
@@ -1721,7 +1893,7 @@ int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int
     // among the rows that have already arrived can be counted while the rest is still on the PCIe bus.  The particles go up in
     // four row chunks on the copy stream; the first distance pass of the step is issued chunk by chunk behind them.
     chunked_upload = in_pinned && ctx->world == 1 && ctx->precision == SVGDB_PRECISION_TC32 && ctx->scale_method == SVGDB_SCALE_MEDIAN &&
-                     n_ipairs_all >= 32 && ctx->host_chunks != 0;
+                     n_ipairs_all >= 32 && ctx->host_chunks != 0 && !ctx->wide;
 #endif
     if (chunked_upload) {
         CU(cudaEventRecord(ctx->ev_fork, ctx->stream)); // whatever still reads or writes X[cur] on the main stream comes first

@@ -77,10 +77,11 @@ def test_tc32_trajectory(sv, oracle, opt):
 
 
 def test_tc32_rejects_large_dimension(sv):
-    x0 = np.zeros((65, 8), order="F")
-    model = sv.MultivariateNormal(np.zeros(65), np.eye(65))
+    """The tensor-core path serves d <= 256 (row operand + accumulator of a 128-particle tile within the 512 TMEM columns)."""
+    x0 = np.zeros((257, 8), order="F")
+    model = sv.MultivariateNormal(np.zeros(257), np.eye(257))
     with pytest.raises(sv.DimensionMismatchException):
-        sv.SVGD(65, 1, x0, sv.GaussianRBFKernel(x0), model, sv.AdaGrad(65, 8, 0.1), precision=TC32)
+        sv.SVGD(257, 1, x0, sv.GaussianRBFKernel(x0), model, sv.AdaGrad(257, 8, 0.1), precision=TC32)
 
 
 @pytest.mark.parametrize("capacity", [64, 4096])
