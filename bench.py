@@ -212,7 +212,7 @@ def sampled_parity(lib, ctx, check, n, d, means, covs, rank, tol):
     g_ref = -np.einsum("cn,cnd->nd", r, Y)
     g_err = float(np.max(np.abs(G[rows] - g_ref)) / max(1e-300, np.max(np.abs(g_ref))))
     # kernel scale: the median of all n^2 distances, estimated from 2M sampled ordered pairs (incl. the n/n^2 share of zeros)
-    m = 2_000_000
+    m = 2_000_000 if d <= 64 else 250_000   # (bounded host memory: m x d doubles twice)
     ii, jj = rng.integers(0, n, m), rng.integers(0, n, m)
     dist = np.sqrt(np.einsum("ij,ij->i", X[ii] - X[jj], X[ii] - X[jj]))
     a_est = np.log(n) / np.median(dist) ** 2
@@ -351,7 +351,8 @@ def main():
         phi_ms = phi_phase_ms
     prof_iters = max(1, int(sp.iterations))
     phase_ms = {"median": sp.ms_median / prof_iters, "grad": sp.ms_grad / prof_iters, "phi": sp.ms_phi / prof_iters,
-                "comm_and_misc": sp.ms_comm / prof_iters}
+                "comm_and_misc": sp.ms_comm / prof_iters,
+                "grad_kernel_on_side_stream": sp.ms_grad_kernel / prof_iters, "median_passes": sp.median_passes / prof_iters}
 
     # ---- correctness of what was just timed (all ranks; rank 0 reports) ---------------------------
     parity = None

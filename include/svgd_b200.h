@@ -77,6 +77,7 @@ typedef struct {
     double ms_median, ms_grad, ms_phi, ms_comm; /* accumulated CUDA-event time per phase, if profiling */
     uint64_t phi_launches;        /* launches of the pair-interaction kernel inside ms_phi */
     double ms_phi_kernel;         /* ... of which the pair-interaction kernel alone (events around its launch) */
+    double ms_grad_kernel;        /* grad log p alone (it runs on a side stream next to the median phase, so ms_grad only shows what sticks out) */
 } svgdb_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */

@@ -24,7 +24,7 @@ class Stats(C.Structure):
         ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("median_passes", C.c_uint64),
         ("median_bracket_hits", C.c_uint64), ("last_scale", C.c_double),
         ("ms_median", C.c_double), ("ms_grad", C.c_double), ("ms_phi", C.c_double), ("ms_comm", C.c_double),
-        ("phi_launches", C.c_uint64), ("ms_phi_kernel", C.c_double),
+        ("phi_launches", C.c_uint64), ("ms_phi_kernel", C.c_double), ("ms_grad_kernel", C.c_double),
     ]
 
 

@@ -1,6 +1,7 @@
 // host_math.hpp -- the pure host-side arithmetic of the library (no CUDA): shared by svgd_b200_api.cu and by the CPU unit test
 // tests/cpp/host_math_test.cpp, so that this logic is exercised without a GPU.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -26,6 +27,53 @@ inline float key_to_float_ceil(uint64_t key)
     float f = (float)x;
     if ((double)f < x) f = std::nextafterf(f, INFINITY);
     return f;
+}
+
+// ---- prediction of the next median of D2 from the recent ones (bracket of the one-pass median, svgd_b200_api.cu: median_scale) ----
+// m[0] is the most recent value, n the number of valid entries.  Six extrapolations; which one fits depends on the optimizer:
+// Adam's trajectory is smooth (the cubic wins), AdaGrad's first dozens of steps overshoot with period two (the increments
+// alternate around their trend: the predictors that continue the increment of TWO steps ago win).
+constexpr int MEDIAN_HISTORY = 8;
+constexpr int MEDIAN_PREDICTORS = 6;
+inline int median_predictor_needs(int kind)
+{
+    static const int needs[MEDIAN_PREDICTORS] = {1, 2, 3, 4, 3, 5};
+    return needs[kind];
+}
+inline double median_predict(const double *m, int kind)
+{
+    switch (kind) {
+    case 0: return m[0];                                            // constant
+    case 1: return 2.0 * m[0] - m[1];                               // linear
+    case 2: return 3.0 * m[0] - 3.0 * m[1] + m[2];                  // quadratic
+    case 3: return 4.0 * m[0] - 6.0 * m[1] + 4.0 * m[2] - m[3];     // cubic
+    case 4: return m[0] + (m[1] - m[2]);                            // the increment of two steps ago
+    default: return m[0] + 2.0 * (m[1] - m[2]) - (m[3] - m[4]);     // ... extrapolated linearly within its parity class
+    }
+}
+// Picks the extrapolation that would have predicted the last (up to) two medians best; returns the prediction of the next one and,
+// in *err, that predictor's worst relative back-test error (INFINITY if the history is too short for any back-test).
+inline double median_predict_best(const double *m, int n, int *kind_out, double *err)
+{
+    int best = -1;
+    double best_err = INFINITY;
+    for (int k = 0; k < MEDIAN_PREDICTORS; ++k) {
+        const int need = median_predictor_needs(k);
+        double e = -1.0;
+        for (int s = 1; s <= 2; ++s) { // predict m[s - 1] from m[s ...]
+            if (n < need + s) break;
+            const double target = m[s - 1];
+            const double rel = std::fabs(median_predict(m + s, k) - target) / std::fabs(target);
+            e = std::max(e, rel);
+        }
+        if (e >= 0.0 && e < best_err) { best_err = e; best = k; }
+    }
+    if (best < 0) { // no back-test possible yet: the highest order the history allows, as before
+        best = n >= 4 ? 3 : n == 3 ? 2 : n == 2 ? 1 : 0;
+    }
+    if (kind_out) *kind_out = best;
+    if (err) *err = best_err;
+    return median_predict(m, best);
 }
 
 // Cholesky A = R^T R with R upper triangular; returns false if A is not positive definite.  Rinv = R^-1.

@@ -220,6 +220,7 @@ struct Phi2Args {
     const __half *WB;      // [n_pad128 / 128][4 KB] column exponent-offset chunks, core-matrix order
     int64_t row0, n_rows;  // this rank's rows
     int n_jtiles, n_ipairs;
+    int max_seg;           // longest run of j-tiles accumulated in TMEM before the partial sums are flushed (see p2_segment)
     int poly;              // pairs (of 16) per 32-column chunk whose exponentials use ex2_poly
     int dbg;               // development: 1 = exp warps only hand the barriers on, 2 = TMEM load/store without the math
     int *err;
@@ -233,7 +234,9 @@ __device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, lo
     if (pos >= end) return false;
     s.ip = (int)(pos / p.n_jtiles);
     s.jb = (int)(pos - (long long)s.ip * p.n_jtiles);
-    const long long seg_end = min(end, (long long)(s.ip + 1) * p.n_jtiles);
+    // The tensor core adds into its fp32 accumulator with truncation: the bias of a sum grows with the number of additions made on
+    // top of it.  Segments are therefore capped; the partial sums of an i-pair are combined by (round-to-nearest) atomics in phi_buf.
+    const long long seg_end = min(min(end, (long long)(s.ip + 1) * p.n_jtiles), pos + p.max_seg);
     s.je = s.jb + (int)(seg_end - pos);
     pos = seg_end;
     return true;

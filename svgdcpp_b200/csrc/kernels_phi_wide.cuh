@@ -128,6 +128,7 @@ struct PhiWArgs {
     int64_t row0, n_rows;  // this launch's rows
     int n_junits;          // 64-particle column units (n_pad128 / 64)
     int n_itiles;          // 128-row i-tiles of this launch
+    int max_seg;           // longest run of column units accumulated in TMEM before the partial sums are flushed (see p2_segment)
     int dbg;
     int *err;
 };
@@ -142,7 +143,7 @@ __device__ __forceinline__ bool pw_segment(const PhiWArgs &p, long long &pos, lo
     s.it = (int)(L / G);
     s.g = (int)(L - (long long)s.it * G);
     s.jb = (int)(pos - L * p.n_junits);
-    const long long seg_end = min(end, (L + 1) * p.n_junits);
+    const long long seg_end = min(min(end, (L + 1) * p.n_junits), pos + p.max_seg);
     s.je = s.jb + (int)(seg_end - pos);
     pos = seg_end;
     return true;

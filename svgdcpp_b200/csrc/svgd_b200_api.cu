@@ -145,7 +145,8 @@ struct svgdb_ctx {
     HostScratch *hs = nullptr;
     // bracket prediction for the next median: (up to) cubic extrapolation of the last medians of D2
     int n_hist = 0;              // valid entries of med_hist (most recent first)
-    double med_hist[4] = {0.0, 0.0, 0.0, 0.0};
+    double med_hist[MEDIAN_HISTORY] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double pred_err = 0.0;       // worst back-test error of the extrapolation chosen for the current step
     double delta = 0.0;          // relative half-width of the predicted bracket
     double density = 2.0;        // candidates per (pair x unit relative width of D2) seen by the last predicted pass
     double resid[2] = {0.0, 0.0}; // recent relative prediction errors
@@ -174,6 +175,7 @@ struct svgdb_ctx {
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
+    int phi_max_seg = 0; // SVGDB_PHI_MAX_SEG (measurement aid): column tiles accumulated in TMEM between flushes (0: default per variant)
     int tc32_variant = SVGDB_TC32_AUTO; // svgdb_set_tc32_variant / SVGDB_TC32_VARIANT: arithmetic of the tensor-core pair kernel
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
     int host_chunks = 1;  // SVGDB_HOST_CHUNKS=0 (measurement aid): svgdb_step_host moves the particles in one piece each way
@@ -181,7 +183,7 @@ struct svgdb_ctx {
     // measurement
     svgdb_stats stats{};
     bool profiling = false;
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [5], [6]: around the pair-interaction kernel
+    cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [5], [6]: around the pair-interaction kernel; [7], [8]: around grad log p (side stream)
 
     std::string err;
 };
@@ -351,6 +353,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_MAX_SEG")) ctx->phi_max_seg = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_HOST_CHUNKS")) ctx->host_chunks = std::atoi(e);
     return SVGDB_OK;
 }
@@ -572,12 +575,17 @@ int median_scale(svgdb_ctx *ctx)
     double predicted = 0.0;
     if (ctx->n_hist > 0 && total > 65536ull) { // (tiny problems: one pass collecting everything is cheaper than any logic)
         const double *m = ctx->med_hist;
-        // cubic extrapolation once four medians are known (measured at the headline shape, Adam transient: median
-        // relative error 9e-6 against 5e-5 for the quadratic and 1.6e-3 for the linear one), lower orders before that
-        predicted = ctx->n_hist >= 4 ? 4.0 * m[0] - 6.0 * m[1] + 4.0 * m[2] - m[3]
-                  : ctx->n_hist == 3 ? 3.0 * m[0] - 3.0 * m[1] + m[2] : ctx->n_hist == 2 ? 2.0 * m[0] - m[1] : m[0];
+        // the extrapolation that fits the recent medians best (host_math.hpp): cubic on Adam's smooth trajectories (measured at the
+        // headline shape: relative error 9e-6), the parity-aware ones while AdaGrad's early steps overshoot with period two
+        int kind = 0;
+        double back_err = INFINITY;
+        predicted = median_predict_best(m, ctx->n_hist, &kind, &back_err);
         if (!(predicted > 0.0) || !std::isfinite(predicted)) predicted = m[0];
-        const double dl = std::min(delta_max, std::max(ctx->delta, 2e-5));
+        ctx->pred_err = std::isfinite(back_err) ? back_err : 0.0;
+        // half-width: 4x the chosen extrapolation's worst back-test error over the last two medians (before any back-test is
+        // possible: the width kept from the previous steps), never below 2e-5
+        const double want = std::isfinite(back_err) ? 4.0 * back_err : ctx->delta;
+        const double dl = std::min(delta_max, std::max(want, 2e-5));
         uint64_t klo = key_of(std::max(predicted * (1.0 - dl), 0.0)), khi = key_of(predicted * (1.0 + dl)) + 1;
         ctx->dist_fold_next = true;
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
@@ -692,11 +700,9 @@ int finish_median(svgdb_ctx *ctx)
             ctx->resid[0] = ctx->resid[1] = 0.0;
             ctx->delta = std::min(delta_max, 1e-3);
         }
-        ctx->med_hist[3] = ctx->med_hist[2];
-        ctx->med_hist[2] = ctx->med_hist[1];
-        ctx->med_hist[1] = ctx->med_hist[0];
+        for (int k = MEDIAN_HISTORY - 1; k > 0; --k) ctx->med_hist[k] = ctx->med_hist[k - 1];
         ctx->med_hist[0] = m_now;
-        ctx->n_hist = std::min(4, ctx->n_hist + 1);
+        ctx->n_hist = std::min(MEDIAN_HISTORY, ctx->n_hist + 1);
         if (!(m_now > 0.0) || !std::isfinite(m_now)) ctx->n_hist = 0;
     }
     return SVGDB_OK;
@@ -737,7 +743,9 @@ int kick_grad(svgdb_ctx *ctx)
     ctx->grad_pending = false;
     CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    if (ctx->profiling) cudaEventRecord(ctx->ev[7], ctx->side_stream);
     TRY(launch_grad(ctx, ctx->side_stream));
+    if (ctx->profiling) cudaEventRecord(ctx->ev[8], ctx->side_stream);
     CU(cudaEventRecord(ctx->ev_join, ctx->side_stream));
     return SVGDB_OK;
 }
@@ -1094,6 +1102,7 @@ int launch_phi_wide(svgdb_ctx *ctx, bool debug_phi)
     a.n_rows = ctx->n_rows;
     a.n_junits = (int)(ctx->n_pad128 / 64);
     a.n_itiles = (int)((ctx->n_rows + 127) / 128);
+    a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 64 : 128); // column units (64 particles) per flush
     a.dbg = 0;
     a.err = ctx->tc_err;
     const bool precise = tc32_precise(ctx);
@@ -1173,6 +1182,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         a.n_rows = rows;
         a.n_jtiles = (int)(ctx->n_pad128 / 128);
         a.n_ipairs = chunk_ipairs[ch];
+        a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 32 : 128); // j-tiles (128 particles) per flush
         a.poly = ctx->phi_poly;
         a.dbg = ctx->phi_dbg_mode;
         a.err = ctx->tc_err;
@@ -1484,6 +1494,8 @@ int one_step(svgdb_ctx *ctx)
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_comm += ms;
         cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->stats.ms_phi += ms;
         if (ctx->n_rows > 0 && cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->stats.ms_phi_kernel += ms;
+        if (ctx->n_rows > 0 && ctx->scale_method != SVGDB_SCALE_HESSIAN && cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]) == cudaSuccess) ctx->stats.ms_grad_kernel += ms;
+        cudaGetLastError();
         cudaEventElapsedTime(&ms, ctx->ev[4], end); ctx->stats.ms_comm += ms;
         cudaEventDestroy(end);
     }
@@ -1540,9 +1552,9 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_med, cudaEventDisableTiming));
     {
-        // candidate buffer of the median select: 2^25 keys up to N = 92K, then N^2 / 256 keys (the bracket that fits it keeps
-        // the same relative width), at most 2^31 keys (16 GiB)
-        const long double want = (long double)n_total * (long double)n_total / 256.0L;
+        // candidate buffer of the median select: 2^25 keys up to N = 46K, then N^2 / 64 keys (the bracket that fits it keeps
+        // the same relative width: it must absorb the extrapolation error of the median), at most 2^31 keys (16 GiB)
+        const long double want = (long double)n_total * (long double)n_total / 64.0L;
         if (want > (long double)ctx->capacity) ctx->capacity = (uint64_t)std::min<long double>(want, 2147483648.0L);
     }
     if (const char *s = std::getenv("SVGDB_CAND_CAPACITY")) {

@@ -78,6 +78,36 @@ int main()
         CHECK(up[0] > 0 && up[0] <= up[1] && up[1] <= up[2] && up[2] <= up[3] && up[3] == n);
     }
 
+    // median extrapolation: on a smooth (cubic) sequence the cubic is chosen and exact; on a sequence whose increments alternate
+    // around a linear trend (AdaGrad's early overshoot, measured on the config-4 recipe) a parity-aware predictor is chosen and
+    // beats the cubic by an order of magnitude
+    {
+        double m[MEDIAN_HISTORY];
+        auto cubic = [](double t) { return 100.0 + 0.3 * t - 0.02 * t * t + 0.001 * t * t * t; };
+        for (int k = 0; k < MEDIAN_HISTORY; ++k) m[k] = cubic(10.0 - k); // m[0] most recent (t = 10)
+        int kind = -1;
+        double err = 1.0;
+        double p = median_predict_best(m, MEDIAN_HISTORY, &kind, &err);
+        CHECK(kind == 3);
+        CHECK(err < 1e-12);
+        CHECK(std::fabs(p - cubic(11.0)) < 1e-9);
+        // increments d_t = -(0.0025 - 0.00002 t) * (1 + 0.25 (-1)^t): period-two oscillation around a slowly decaying trend
+        double seq[16];
+        seq[0] = 6000.0;
+        for (int t = 1; t < 16; ++t) seq[t] = seq[t - 1] * (1.0 - (0.0025 - 0.00002 * t) * (1.0 + 0.25 * ((t & 1) ? -1.0 : 1.0)));
+        for (int k = 0; k < MEDIAN_HISTORY; ++k) m[k] = seq[14 - k]; // history up to t = 14, predict t = 15
+        p = median_predict_best(m, MEDIAN_HISTORY, &kind, &err);
+        CHECK(kind == 4 || kind == 5);
+        const double e_best = std::fabs(p - seq[15]) / seq[15], e_cubic = std::fabs(median_predict(m, 3) - seq[15]) / seq[15];
+        CHECK(e_best < 1e-4);
+        CHECK(e_best * 10.0 < e_cubic);
+        // short histories fall back to what is available
+        p = median_predict_best(m, 1, &kind, &err);
+        CHECK(kind == 0 && p == m[0] && !std::isfinite(err));
+        p = median_predict_best(m, 2, &kind, &err);
+        CHECK(kind == 0 || kind == 1);
+    }
+
     if (failures == 0) std::printf("host_math_test: all checks passed\n");
     return failures == 0 ? 0 : 1;
 }
