@@ -36,7 +36,7 @@ def main():
     prec = _capi.PRECISION_TC32 if args.precision == "tc32" else _capi.PRECISION_F64
     dp = C.POINTER(C.c_double)
     failures = 0
-    for n, d, iters in [(301, 5, 6), (1000, 64, 5), (2500, 33, 4), (9001, 64, 3)]:
+    for n, d, iters in [(301, 5, 6), (1000, 64, 5), (1500, 33, 4), (4100, 64, 2), (600, 160, 3)]:
         rng = np.random.default_rng(n)
         A = rng.standard_normal((d, d))
         cov = np.ascontiguousarray(A @ A.T / d + 0.5 * np.eye(d))
@@ -73,7 +73,7 @@ def main():
         # two more iterations through the host-buffer call, every rank moving only its own rows (svgdb_step_host under sharding)
         r0, nr = C.c_int64(0), C.c_int64(0)
         check(lib.svgdb_local_rows(ctx, C.byref(r0), C.byref(nr)))
-        mine = np.ascontiguousarray(X[r0.value:r0.value + nr.value])
+        mine = X[r0.value:r0.value + nr.value].copy()  # (a contiguous slice would alias X)
         check(lib.svgdb_step_host(ctx, mine.ctypes.data_as(dp), mine.ctypes.data_as(dp), 2))
         X2 = np.empty_like(X0)
         check(lib.svgdb_get_particles(ctx, X2.ctypes.data_as(dp)))
@@ -83,14 +83,14 @@ def main():
             import oracle_binding as oracle
 
             a_ref = oracle.rbf_median_scale(X0)
-            G_ref = oracle.mvn_sum_logp_grad(X0, mu[None], cov[None])
+            G_ref = oracle.mvn_sum_logp_grad(X0, mu[None], cov[None], lse=True)
             phi_ref = oracle.phi(X0, G_ref, a_ref)
-            X_ref = oracle.svgd_run(X0, iters, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1)
+            X_ref = oracle.svgd_run(X0, iters, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1, lse=True)
             e_a = abs(a.value - a_ref) / a_ref
             e_phi = np.max(np.abs(phi - phi_ref)) / np.max(np.abs(phi_ref))
             e_x = np.sqrt(np.mean((X - X_ref) ** 2)) / np.sqrt(np.mean(X_ref ** 2))
             tol = (1e-12, 1e-11, 1e-9) if prec == _capi.PRECISION_F64 else (1e-5, 2e-4, 1e-3)
-            X2_ref = oracle.svgd_run(X0, iters + 2, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1)
+            X2_ref = oracle.svgd_run(X0, iters + 2, mu[None], cov[None], opt_kind=oracle.OPT_ADAM, lr=0.1, lse=True)
             e_x2 = np.sqrt(np.mean((X2 - X2_ref) ** 2)) / np.sqrt(np.mean(X2_ref ** 2))
             ok = e_a < tol[0] and e_phi < tol[1] and e_x < tol[2] and e_x2 < tol[2] and cnt.value == iters and np.all(np.isfinite(s1))
             print("world=%d %s n=%d d=%d: a err %.2e, phi err %.2e, trajectory rms err %.2e, after 2 more steps through svgdb_step_host %.2e -> %s"
