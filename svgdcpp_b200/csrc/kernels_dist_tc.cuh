@@ -73,6 +73,54 @@ __global__ void split_dist2_kernel(const double *__restrict__ X, const double *_
     }
 }
 
+// The operands of the F16 variant of a folded pass (dist2_tc32_kernel<..., F16 = true>): y = s (x - mean) with s a power of two
+// chosen by the host so that the median of |y_i - y_j|^2 is ~512 (fp16 has the dynamic range of the particle cloud, not more),
+//   XA2[row] = -2 [hi | lo] fp16 (row particle: two terms, 22 bits),   XB[row] = hi fp16 (column particle: its fp16 image),
+//   UA[row] = [r r r 1 1 1 0..] with r = |hi + lo|^2,  WB = [1 1 1 r^ r^ r^ 1 1 1 0..] with r^ = |hi|^2 (three-term bf16 splits):
+// the accumulator is the exact squared distance between particle i and the fp16 image of particle j, times s^2.
+__global__ void split_dist2h_kernel(const double *__restrict__ X, const double *__restrict__ colsum, int64_t n, int64_t row_begin, int64_t n_rows_a,
+                                    int64_t n_rows_b, int d, double s, __half *__restrict__ XA2, __half *__restrict__ XB,
+                                    __nv_bfloat16 *__restrict__ UA, __nv_bfloat16 *__restrict__ WB, double *__restrict__ rt)
+{
+    const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows_a) return;
+    double r_full = 0.0, r_hi = 0.0, r_x = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        double xc = 0.0;
+        if (row < n && k < d) xc = X[row * d + k] - colsum[k] / (double)n;
+        r_x += xc * xc;
+        const double y = s * xc;
+        const __half hi = __double2half(y);
+        const double hid = (double)__half2float(hi);
+        const __half lo = __double2half(y - hid);
+        const double full = hid + (double)__half2float(lo);
+        r_full += full * full;
+        r_hi += hid * hid;
+        XA2[row * P2_A_LD + k] = __float2half_rn(-2.0f * __half2float(hi)); // exact: a power-of-two multiple
+        XA2[row * P2_A_LD + 64 + k] = __float2half_rn(-2.0f * __half2float(lo));
+        if (row < n_rows_b) XB[row * 64 + k] = hi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        r_full += __shfl_xor_sync(0xffffffffu, r_full, o);
+        r_hi += __shfl_xor_sync(0xffffffffu, r_hi, o);
+        r_x += __shfl_xor_sync(0xffffffffu, r_x, o);
+    }
+    if (lane == 0 && row < n_rows_b) rt[row] = r_x;
+    if (lane < 16) {
+        __nv_bfloat16 a0, a1, a2, b0, b1, b2;
+        split3_bf16((row < n) ? r_full : (double)INFINITY, a0, a1, a2);
+        split3_bf16((row < n) ? r_hi : (double)INFINITY, b0, b1, b2);
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+        UA[row * 16 + lane] = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane < 6 ? one : zero;
+        if (row < n_rows_b)
+            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<uint8_t *>(WB) + (row >> 7) * P2_W_BYTES + p2_ex_offset((uint32_t)(row & 127), (uint32_t)lane)) =
+                lane < 3 ? one : lane == 3 ? b0 : lane == 4 ? b1 : lane == 5 ? b2 : lane < 9 ? one : zero;
+    }
+}
+
 // warp-collective: move `count` staged distances to the global candidate list as keys
 __device__ __noinline__ void dist_flush2(const float *mybuf, unsigned int count, unsigned long long *cand, unsigned long long *cand_count,
                                          unsigned long long capacity)
@@ -108,6 +156,7 @@ struct Dist2Args {
     // FOLD instantiations: -lo_f rides in the norm K chunk as a three-term bf16 split (exact: 24 bits), so the accumulator IS
     // t = d2 - lo_f and the epilogue needs no subtraction; fold_l01 = bf16 pair (L0, L1), fold_l2 = (L2, 0)
     unsigned int fold_l01, fold_l2;
+    float out_scale;         // FOLD: collected values are (t + lo_f) * out_scale (1 / s^2 of the F16 variant, else 1)
     unsigned int width_bits; // IEEE bits of a float > fl(hi_f - lo_f): d2 is collected iff 0 <= fl(d2 - lo_f) < width
     int open_low;            // lo_f = -inf (nothing lies below): collect d2 < hi_f by a plain compare
     unsigned long long lo_key;
@@ -162,7 +211,12 @@ __device__ __forceinline__ long long d2_total_units(const Dist2Args &p)
 // FMNMX3 over |t| per two values; a chunk whose smallest |t| is below the width takes the exact collecting path).  The values of
 // a pass are the roundings of ITS OWN accumulation, so passes that must agree with each other on every single distance
 // (histogram narrowing followed by a collecting pass) all run unfolded.
-template <int MODE, bool GATED, bool FOLD>
+// F16 (folded collecting passes only): two products on fp16 operands instead of three on bf16 -- the row particle keeps two terms, the
+// column particle is its fp16 image (split_dist2h_kernel): 8 + 1 MMAs per unit instead of 12 + 1.  The values of such a pass are
+// exact distances to the rounded column particles: a zero-mean perturbation of ~1e-5 relative per pair, which moves the median of
+// n^2 of them by far less than the 1e-5 tolerance of the scale.  Lower bracket end, width and the folded -lo are given in the
+// scaled units of the operands (powers of two: every comparison is unchanged); candidates are scaled back (out_scale).
+template <int MODE, bool GATED, bool FOLD, bool F16 = false>
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Dist2Args p)
 {
@@ -187,6 +241,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
     unsigned int *shist32 = (unsigned int *)wbuf;           // [HIST_BINS] the 32-bit variant
     constexpr bool HIST32 = MODE == MODE_HIST && GATED;
     static_assert(!(FOLD && MODE == MODE_HIST), "histogram passes run unfolded");
+    static_assert(!F16 || FOLD, "the fp16 two-product operands serve folded collecting passes only");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -223,9 +278,9 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                 }
                 if (elect_one()) {
                     uint8_t *st = smem + slot * D2_STAGE;
-                    mbar_arrive_expect_tx(full + slot, D2_TX);
+                    mbar_arrive_expect_tx(full + slot, F16 ? 16384u + P2_W_BYTES : D2_TX);
                     tma_load_2d(st, &mapB, 0, jt * TC_TILE, full + slot);
-                    tma_load_2d(st + 16384, &mapB, 64, jt * TC_TILE, full + slot);
+                    if (!F16) tma_load_2d(st + 16384, &mapB, 64, jt * TC_TILE, full + slot);
                     bulk_load_1d(st + D2_XB_BYTES, reinterpret_cast<const uint8_t *>(p.WB) + (size_t)jt * P2_W_BYTES, P2_W_BYTES, full + slot);
                 }
                 __syncwarp();
@@ -233,7 +288,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
         }
     } else if (warp > D2_CWARPS) { // ---- MMA issuer of i-tile w
         const int w = warp - D2_CWARPS - 1;
-        const uint32_t idesc = make_idesc_bf16(TC_TILE, 64);
+        const uint32_t idesc_c = make_idesc_bf16(TC_TILE, 64);                      // norm chunk: always bf16
+        const uint32_t idesc = F16 ? make_idesc_f16(TC_TILE, 64) : idesc_c;          // products
         const uint32_t st_lo0 = desc_lo_k_sw128(smem_u32(smem));
         const uint32_t aex_lo = (desc_lo_k_sw128(smem_u32(sAex + w * P2_AEX_BYTES))) | DESC_LO_K_NOSW_LBO;
         const uint32_t wb_lo0 = desc_lo_k_sw128(smem_u32(smem + D2_XB_BYTES)) | DESC_LO_K_NOSW_LBO;
@@ -264,11 +320,13 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                         umma_f16_ts2<true>(dS, aT + 40, bh + 2, idesc);
                         umma_f16_ts2<true>(dS, aT + 48, bh + 4, idesc);
                         umma_f16_ts2<true>(dS, aT + 56, bh + 6, idesc);
-                        umma_f16_ts2<true>(dS, aT, bl, idesc);           // (-2 hi_i) . lo_j
-                        umma_f16_ts2<true>(dS, aT + 8, bl + 2, idesc);
-                        umma_f16_ts2<true>(dS, aT + 16, bl + 4, idesc);
-                        umma_f16_ts2<true>(dS, aT + 24, bl + 6, idesc);
-                        umma_f16_ss_desc(dS, aex_lo, DESC_HI_K_NOSW, wb_lo0 + slot * (D2_STAGE >> 4) + k * (2048 >> 4), DESC_HI_K_NOSW, idesc); // + r_i + r_j
+                        if (!F16) {
+                            umma_f16_ts2<true>(dS, aT, bl, idesc);       // (-2 hi_i) . lo_j
+                            umma_f16_ts2<true>(dS, aT + 8, bl + 2, idesc);
+                            umma_f16_ts2<true>(dS, aT + 16, bl + 4, idesc);
+                            umma_f16_ts2<true>(dS, aT + 24, bl + 6, idesc);
+                        }
+                        umma_f16_ss_desc(dS, aex_lo, DESC_HI_K_NOSW, wb_lo0 + slot * (D2_STAGE >> 4) + k * (2048 >> 4), DESC_HI_K_NOSW, idesc_c); // + r_i + r_j
                         umma_commit(s_full + 3 * w + buf);
                         if (k == 1) umma_commit(empty + slot);
                         if (k == 1 && jt + 1 == sg.je) umma_commit(seg_done + w);
@@ -315,7 +373,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     if (count + tot * cur_wgt > (unsigned int)TC_WBUF) { dist_flush2(mybuf, count, p.cand, p.cand_count, p.capacity); count = 0; }
                     if (tot * cur_wgt > (unsigned int)TC_WBUF) { // more than an empty buffer holds: straight to global
                         for (uint32_t e = 0; e < mine; ++e)
-                            dist_append_global2(lds_f32(priv_base + 128u * e) + (FOLD ? p.lo_f : 0.0f), cur_wgt, p.cand, p.cand_count, p.capacity);
+                            dist_append_global2(FOLD ? (lds_f32(priv_base + 128u * e) + p.lo_f) * p.out_scale : lds_f32(priv_base + 128u * e), cur_wgt, p.cand,
+                                                p.cand_count, p.capacity);
                     } else {
                         uint32_t incl = mine; // inclusive scan over lanes
 #pragma unroll
@@ -325,7 +384,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                         }
                         uint32_t dst = wbuf_base + 4u * (count + (incl - mine) * cur_wgt);
                         for (uint32_t e = 0; e < mine; ++e) {
-                            const float v = lds_f32(priv_base + 128u * e) + (FOLD ? p.lo_f : 0.0f); // staged as t = d2 - lo when folded
+                            const float v = FOLD ? (lds_f32(priv_base + 128u * e) + p.lo_f) * p.out_scale : lds_f32(priv_base + 128u * e); // staged as t = d2 - lo when folded
                             sts_f32(dst, v); dst += 4u;
                             if (cur_wgt == 2u) { sts_f32(dst, v); dst += 4u; }
                         }

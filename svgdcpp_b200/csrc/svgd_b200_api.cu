@@ -171,6 +171,9 @@ struct svgdb_ctx {
     CUtensorMap mapBD{};
     int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
     int dist_gated = -1;   // SVGDB_DIST_GATED=0/1 forces the flat / gated counting epilogue (default: chosen per pass)
+    bool dist_ops_f16 = false;   // the distance operands in memory are the scaled fp16 ones of the two-product variant (split_dist2h_kernel)
+    double dist_s2 = 1.0;        // ... scaled by s with s^2 = dist_s2, a power of two
+    int dist_f16 = 1;            // SVGDB_DIST_F16=0 (measurement aid): always the three-product bf16 operands
     bool dist_fold_next = false; // the next collecting pass runs over a predicted bracket (set by median_scale): it may fold -lo into the operands
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
@@ -350,6 +353,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     }
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
     if (const char *e = std::getenv("SVGDB_DIST_FOLD")) ctx->dist_fold = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_DIST_F16")) ctx->dist_f16 = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
@@ -833,9 +837,39 @@ int launch_colsum(svgdb_ctx *ctx, const double *X, int64_t rows)
     return SVGDB_OK;
 }
 
+// centred operand rows [r0, r1) of the d <= 64 distance pass, in the variant ctx->dist_ops_f16 says
+int launch_split_dist2(svgdb_ctx *ctx, int64_t r0, int64_t r1)
+{
+    using namespace svgdb::tc;
+    if (r1 <= r0) return SVGDB_OK;
+    const unsigned blocks = (unsigned)((r1 - r0 + 7) / 8);
+    if (ctx->dist_ops_f16)
+        split_dist2h_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->N, r0, r1, ctx->n_pad128, ctx->d, std::sqrt(ctx->dist_s2),
+                                                             ctx->XA2, ctx->XB2, reinterpret_cast<__nv_bfloat16 *>(ctx->UA2),
+                                                             reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
+    else
+        split_dist2_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->N, r0, r1, ctx->n_pad128, ctx->d,
+                                                            reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD, reinterpret_cast<__nv_bfloat16 *>(ctx->UA2),
+                                                            reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
+    KERNEL_CHECK();
+    return SVGDB_OK;
+}
+
 int launch_dist_operands(svgdb_ctx *ctx)
 {
     using namespace svgdb::tc;
+    // The first pass of a step with a median history is a folded collecting pass over a predicted bracket: it runs on the scaled
+    // fp16 operands (two products).  Anything else -- no history yet, narrowing passes after a miss -- runs on the bf16 ones.
+    TRY(finish_median(ctx));
+    ctx->dist_ops_f16 = false;
+    if (!ctx->wide && ctx->dist_f16 != 0 && ctx->dist_fold != 0 && ctx->scale_method == SVGDB_SCALE_MEDIAN && ctx->n_hist > 0 &&
+        (double)ctx->N * (double)ctx->N > 65536.0 && ctx->med_hist[0] > 0.0 && std::isfinite(ctx->med_hist[0])) {
+        const int k = (int)std::lround(std::log2(512.0 / ctx->med_hist[0]));
+        if (k > -100 && k < 100) {
+            ctx->dist_ops_f16 = true;
+            ctx->dist_s2 = std::ldexp(1.0, k); // the median of the scaled squared distances lands in [362, 724)
+        }
+    }
     if (ctx->wide) { // 64 < d <= 256: kernels_dist_wide.cuh (no chunked upload on this path)
         TRY(launch_colsum(ctx, ctx->X[ctx->cur], ctx->N));
         const int64_t rows_a = ctx->n_pad128 + 256;
@@ -858,18 +892,14 @@ int launch_dist_operands(svgdb_ctx *ctx)
         colsum_scale_kernel<<<1, 64, 0, ctx->stream>>>(ctx->colsum, ctx->d, (double)ctx->N / (double)rows_now);
         KERNEL_CHECK();
     }
-    split_dist2_kernel<<<(unsigned)((rows_end + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->X[ctx->cur], ctx->colsum, ctx->N, 0, rows_end, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
-        reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
-    KERNEL_CHECK();
-    return SVGDB_OK;
+    return launch_split_dist2(ctx, 0, rows_end);
 }
 
 int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, int shift)
 {
     using namespace svgdb::tc;
-    const float lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
-    const float hi_f = key_to_float_ceil(hi);
+    float lo_f = lo == 0 ? -INFINITY : key_to_float_ceil(lo); // nothing lies below an open lower end (D2 may round slightly negative)
+    float hi_f = key_to_float_ceil(hi);
     CU(cudaMemsetAsync(ctx->below, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->max_below, 0, sizeof(unsigned long long), ctx->stream));
     // Symmetric enumeration over all rows at any world size; i-pairs are dealt cyclically to the ranks.
@@ -895,6 +925,24 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
     // histograms and the collecting pass that follows them) run unfolded.
     const bool fold = mode == MODE_COLLECT && ctx->dist_fold_next && ctx->dist_fold != 0 && std::isfinite(lo_f) && std::isfinite(hi_f);
     ctx->dist_fold_next = false;
+    const bool f16 = fold && ctx->dist_ops_f16 && !ctx->wide;
+    if (!f16 && ctx->dist_ops_f16) { // this pass needs the bf16 operands (a narrowing or unfolded pass after a miss): rebuild them
+        ctx->dist_ops_f16 = false;
+        TRY(launch_split_dist2(ctx, 0, ctx->n_pad128 + 256));
+    }
+    float out_scale = 1.0f;
+    if (f16) { // the operands are scaled by s, the distances by s^2 (a power of two: bracket end, width and every comparison scale exactly)
+        const float s2 = (float)ctx->dist_s2;
+        float wdt;
+        std::memcpy(&wdt, &width_bits, 4);
+        wdt *= s2;
+        lo_f *= s2;
+        hi_f *= s2;
+        if (!std::isfinite(wdt) || !std::isfinite(lo_f) || !std::isfinite(hi_f) || !(wdt > 0.0f))
+            return fail(ctx, SVGDB_ERR_NUMERIC, "median select: the predicted bracket leaves the fp32 range after scaling");
+        std::memcpy(&width_bits, &wdt, 4);
+        out_scale = (float)(1.0 / ctx->dist_s2);
+    }
     uint32_t fold_l01 = 0, fold_l2 = 0;
     if (fold) {
         float rem = -lo_f;
@@ -980,10 +1028,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
                 using namespace svgdb::tc;
                 CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[ch], 0));
                 const int64_t r0 = (int64_t)ctx->up_ipairs[ch - 1] * 256, r1 = last ? ctx->n_pad128 + 256 : (int64_t)ctx->up_ipairs[ch] * 256;
-                split_dist2_kernel<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
-                    ctx->X[ctx->cur], ctx->colsum, ctx->N, r0, r1, ctx->n_pad128, ctx->d, reinterpret_cast<__nv_bfloat16 *>(ctx->XA2), ctx->XBD,
-                    reinterpret_cast<__nv_bfloat16 *>(ctx->UA2), reinterpret_cast<__nv_bfloat16 *>(ctx->WB2), ctx->rt);
-                KERNEL_CHECK();
+                TRY(launch_split_dist2(ctx, r0, r1));
             }
         }
         if (n_ipairs > 0) {
@@ -1003,6 +1048,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
             b.width_bits = width_bits;
             b.fold_l01 = fold_l01;
             b.fold_l2 = fold_l2;
+            b.out_scale = out_scale;
             b.lo_key = lo;
             b.shift = shift;
             b.below = ctx->below;
@@ -1032,7 +1078,10 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
                     if (dhi > 0.0) width_rel = (dhi - dlo) / dhi;
                 }
                 const bool gated = ctx->dist_gated >= 0 ? ctx->dist_gated != 0 : ctx->density * width_rel * 1024.0 < 0.5;
-                if (fold) {
+                if (f16) {
+                    if (gated) dist2_tc32_kernel<MODE_COLLECT, true, true, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapB2, b);
+                    else dist2_tc32_kernel<MODE_COLLECT, false, true, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapB2, b);
+                } else if (fold) {
                     if (gated) dist2_tc32_kernel<MODE_COLLECT, true, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
                     else dist2_tc32_kernel<MODE_COLLECT, false, true><<<grid, D2_THREADS, D2_SMEM, ctx->stream>>>(ctx->mapBD, b);
                 } else {
@@ -1606,6 +1655,8 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         SVGDB_D2_ATTR(MODE_COLLECT, false, true)
         SVGDB_D2_ATTR(MODE_COLLECT, true, true)
 #undef SVGDB_D2_ATTR
+        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
+        CU(cudaFuncSetAttribute(svgdb::tc::dist2_tc32_kernel<MODE_COLLECT, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::D2_SMEM));
     }
 #endif
     CU(cudaMalloc(&ctx->a_dev, sizeof(double)));
