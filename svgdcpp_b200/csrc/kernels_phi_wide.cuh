@@ -418,11 +418,13 @@ struct OptWArgs {
     double *s1, *s2;
     const double *lb, *ub;
     double *X_out, *phi_out;
+    const int *miss; // see OptTcArgs
 };
 __global__ void opt_update_wide_kernel(OptWArgs p)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.n_rows * p.d) return;
+    if (p.miss != nullptr && *p.miss != 0) return;
     int64_t li = idx / p.d;
     int c = (int)(idx - li * p.d);
     int64_t i = p.row0 + li;

@@ -60,6 +60,7 @@ struct OptTcArgs {
     double *s1, *s2;
     const double *lb, *ub;
     double *X_out, *phi_out;
+    const int *miss; // device flag of an optimistic step whose predicted median bracket missed: nothing persistent may change
 };
 
 // phi = (Phi + 2 a x~ rowsum)/n in FP64, then the optimizer increment and clamp (FP64 state).
@@ -67,6 +68,7 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.n_rows * p.d) return;
+    if (p.miss != nullptr && *p.miss != 0) return;
     int64_t li = idx / p.d;
     int c = (int)(idx - li * p.d);
     int64_t i = p.row0 + li;

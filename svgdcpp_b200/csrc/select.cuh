@@ -34,17 +34,50 @@ struct MedianResult {
     double scale;                      // a
 };
 
+// The verdict on a collecting pass over a PREDICTED bracket, taken on the device so that the step needs no host round trip:
+// the pass returned exact counts (all-reduced over the ranks), so whether the bracket held the median is arithmetic on them.
+struct StepDecision {
+    unsigned long long kk;      // rank of the upper middle value among the candidates (k_hi - below)
+    unsigned long long m_local; // this rank's candidates
+    unsigned long long below, mid; // the pass's global counts (for the host's bookkeeping, read later)
+    int hit;                    // the bracket held: the select below works on the right candidates
+    int pad;
+};
+// pass_words = [below, cand_total] (global).  need_both: the pass does not track the largest value below the bracket, so for an
+// even count the lower middle value must be a candidate too.  miss_sticky is raised on a miss: everything that would change
+// persistent state (the optimizer update) checks it, the host reads it after the step and repeats the step the slow way.
+__global__ void median_decide_kernel(const unsigned long long *pass_words, const unsigned long long *cand_count_local, unsigned long long k_hi,
+                                     int even, int need_both, unsigned long long capacity, StepDecision *dec, int *miss_sticky)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long b = pass_words[0], mid = pass_words[1];
+    const bool hit = (need_both ? b < k_hi : b <= k_hi) && (k_hi < b + mid) && (mid <= capacity) && (!even || k_hi >= 1ull);
+    dec->hit = hit ? 1 : 0;
+    dec->kk = hit ? k_hi - b : 0ull;
+    const unsigned long long ml = *cand_count_local;
+    dec->m_local = ml < capacity ? ml : capacity;
+    dec->below = b;
+    dec->mid = mid;
+    if (!hit) *miss_sticky = 1;
+}
+
+// dec != nullptr: the rank comes from the device-side verdict instead of `rank`
 __global__ void select_init_kernel(SelectState *st, unsigned long long base, unsigned long long prefix, unsigned long long mask,
-                                   unsigned long long rank)
+                                   unsigned long long rank, const StepDecision *dec = nullptr)
 {
     for (int t = threadIdx.x; t < SELECT_MAX_BINS; t += blockDim.x) st->hist[t] = 0ull;
-    if (threadIdx.x == 0) { st->base = base; st->prefix = prefix; st->mask = mask; st->rank = rank; st->n_less = 0ull; st->max_less = 0ull; st->need_scan = 1ull; }
+    if (threadIdx.x == 0) {
+        st->base = base; st->prefix = prefix; st->mask = mask; st->rank = dec ? dec->kk : rank;
+        st->n_less = 0ull; st->max_less = 0ull; st->need_scan = 1ull;
+    }
 }
 
 // histogram of the `bits`-wide digit at `shift` over the candidates that match the decided prefix
 __global__ void __launch_bounds__(256)
-select_hist_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, int shift, int bits, SelectState *st)
+select_hist_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, int shift, int bits, SelectState *st,
+                   const StepDecision *dec = nullptr)
 {
+    if (dec) m = dec->m_local;
     __shared__ unsigned int sh[SELECT_MAX_BINS];
     const int nbins = 1 << bits;
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) sh[b] = 0u;
@@ -108,9 +141,10 @@ __global__ void __launch_bounds__(256) select_pick_kernel(SelectState *st, int s
 
 // largest candidate below the answer, only when the last pick could not tell (the answer is the smallest key of its group)
 __global__ void __launch_bounds__(256)
-select_max_less_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, SelectState *st)
+select_max_less_kernel(const unsigned long long *__restrict__ cand, unsigned long long m, SelectState *st, const StepDecision *dec = nullptr)
 {
     if (st->need_scan == 0ull) return;
+    if (dec) m = dec->m_local;
     const unsigned long long base = st->base, key_hi = st->prefix;
     unsigned long long best = 0ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < m;
@@ -130,9 +164,10 @@ select_max_less_kernel(const unsigned long long *__restrict__ cand, unsigned lon
 __global__ void median_finalize_kernel(const SelectState *st, unsigned long long kk, int even,
                                        const unsigned long long *max_below_global, int direct,
                                        unsigned long long direct_key, double log_n, MedianResult *out,
-                                       double *a_out)
+                                       double *a_out, const StepDecision *dec = nullptr)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (dec) kk = dec->kk;
     unsigned long long key_hi = direct ? direct_key : st->base + st->prefix;
     unsigned long long key_lo = key_hi;
     if (even) {

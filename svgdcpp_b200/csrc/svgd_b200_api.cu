@@ -77,6 +77,7 @@ struct HostScratch { // pinned
     unsigned long long below, cand_total, max_below, cand_count; // the first three mirror the device's pass_words
     unsigned long long hist[HIST_BINS];
     MedianResult med;
+    StepDecision dec; // mirror of the device-side verdict of an optimistic step
 };
 
 } // namespace
@@ -171,6 +172,17 @@ struct svgdb_ctx {
     CUtensorMap mapBD{};
     int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
     int dist_gated = -1;   // SVGDB_DIST_GATED=0/1 forces the flat / gated counting epilogue (default: chosen per pass)
+    // optimistic steps (tensor-core path, median history available): the bracket verdict is taken on the device and read by the host
+    // after the step has been enqueued; a miss is repaired by repeating the step synchronously
+    int optimistic = -1;           // SVGDB_OPTIMISTIC=0 / 1 forces it off / on; default (-1): on when the rows are sharded over several ranks --
+                                   // on one GPU the host round trip hides behind grad log p on the side stream and the extra kernels cost 1.5 %,
+                                   // on eight the round trip and the launches behind it are a tenth of the step
+    bool opt_suspended = false;    // a repair or an inspection call is running: synchronous
+    bool pending_verify = false;   // the last step's verdict has not been read yet
+    double pending_dl = 0.0;       // half-width of that step's bracket (density bookkeeping)
+    double miss_boost = 1.0;       // widening factor of the predicted bracket: x4 on a miss, halved on every hit down to 1
+    StepDecision *dec_dev = nullptr;
+    int *miss_dev = nullptr;
     bool dist_ops_f16 = false;   // the distance operands in memory are the scaled fp16 ones of the two-product variant (split_dist2h_kernel)
     double dist_s2 = 1.0;        // ... scaled by s with s^2 = dist_s2, a power of two
     int dist_f16 = 1;            // SVGDB_DIST_F16=0 (measurement aid): always the three-product bf16 operands
@@ -354,6 +366,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
     if (const char *e = std::getenv("SVGDB_DIST_FOLD")) ctx->dist_fold = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_DIST_F16")) ctx->dist_f16 = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_OPTIMISTIC")) ctx->optimistic = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
@@ -430,6 +443,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
 #endif
 int reduce_pass_words(svgdb_ctx *ctx, int mode);
 int finish_median(svgdb_ctx *ctx);
+int settle_step(svgdb_ctx *ctx);
 void prof_mark(svgdb_ctx *ctx, int i);
 int kick_grad(svgdb_ctx *ctx);
 
@@ -508,9 +522,12 @@ int read_pass_results(svgdb_ctx *ctx, int mode, uint64_t *mid_total)
     return SVGDB_OK;
 }
 
-int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n)
+// dec != nullptr: rank and candidate count come from the device-side verdict (optimistic step); the grid covers the whole buffer
+// (the kernels stride over whatever the device says the count is; `expected` only sizes the grid)
+int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even, double log_n, const StepDecision *dec = nullptr,
+               uint64_t expected = 0)
 {
-    uint64_t m_local = std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
+    uint64_t m_local = dec ? std::min<uint64_t>(std::max<uint64_t>(expected, 2048), ctx->capacity) : std::min<uint64_t>(ctx->hs->cand_count, ctx->capacity);
     // The candidates are selected on key - base, base = the bracket's lower end: its span, not the raw bit patterns, decides
     // how many bits matter (a bracket of relative width 2e-4 spans ~2^11 fp32 values: one 12-bit pass).  Keys of the
     // tensor-core path are fp32 distances widened to double: their low 29 bits are zero, and so are those of key - base
@@ -522,14 +539,14 @@ int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even,
     while (top < 64 && (span >> top) != 0ull) ++top;
     if (top < bottom + 1) top = bottom + 1;
     const uint64_t low_mask = top >= 64 ? ~0ull : ((1ull << top) - 1ull);
-    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, base, 0ull, ~low_mask, kk);
+    select_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, base, 0ull, ~low_mask, kk, dec);
     KERNEL_CHECK();
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m_local + 2047) / 2048, (uint64_t)ctx->sm_count * 8));
     // digits of up to SELECT_MAX_BITS bits from the top differing bit down to `bottom`
     int hi_bit = top;
     while (hi_bit > bottom) {
         const int bits = std::min(SELECT_MAX_BITS, hi_bit - bottom), shift = hi_bit - bits;
-        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, bits, ctx->sel);
+        select_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, shift, bits, ctx->sel, dec);
         KERNEL_CHECK();
         TRY(allreduce_u64(ctx, ctx->sel->hist, (size_t)1 << bits, ncclSum));
         select_pick_kernel<<<1, 256, 0, ctx->stream>>>(ctx->sel, shift, bits, shift == bottom ? 1 : 0);
@@ -538,12 +555,12 @@ int run_select(svgdb_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t kk, bool even,
     }
     if (even) {
         // multi-GPU: each rank decides need_scan from the same all-reduced histogram, the candidates are rank-local
-        select_max_less_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, ctx->sel);
+        select_max_less_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->cand, m_local, ctx->sel, dec);
         KERNEL_CHECK();
         TRY(allreduce_u64(ctx, &ctx->sel->max_less, 1, ncclMax));
     }
     median_finalize_kernel<<<1, 32, 0, ctx->stream>>>(ctx->sel, kk, even ? 1 : 0, ctx->max_below, 0, 0ull, log_n,
-                                                      ctx->medres, ctx->a_dev);
+                                                      ctx->medres, ctx->a_dev, dec);
     KERNEL_CHECK();
     return SVGDB_OK;
 }
@@ -589,10 +606,33 @@ int median_scale(svgdb_ctx *ctx)
         // half-width: 4x the chosen extrapolation's worst back-test error over the last two medians (before any back-test is
         // possible: the width kept from the previous steps), never below 2e-5
         const double want = std::isfinite(back_err) ? 4.0 * back_err : ctx->delta;
-        const double dl = std::min(delta_max, std::max(want, 2e-5));
+        const double dl = std::min(delta_max, std::max(want, 2e-5) * ctx->miss_boost);
         uint64_t klo = key_of(std::max(predicted * (1.0 - dl), 0.0)), khi = key_of(predicted * (1.0 + dl)) + 1;
         ctx->dist_fold_next = true;
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
+        const bool need_both_dev = even && ctx->precision == SVGDB_PRECISION_TC32;
+        const bool optimistic = ctx->optimistic < 0 ? ctx->world > 1 : ctx->optimistic != 0;
+        if (optimistic && !ctx->opt_suspended && ctx->precision == SVGDB_PRECISION_TC32) {
+            // No host round trip: the verdict on the bracket is taken on the device, the select and everything after it are enqueued
+            // at once, and the host reads the verdict when the step has been enqueued (settle_step).
+            median_decide_kernel<<<1, 32, 0, ctx->stream>>>(ctx->pass_words, ctx->cand_count, k_hi, even ? 1 : 0, need_both_dev ? 1 : 0, ctx->capacity,
+                                                            ctx->dec_dev, ctx->miss_dev);
+            KERNEL_CHECK();
+            uint64_t hi_sel = khi;
+#ifdef SVGDB_WITH_TC32
+            if (ctx->collect_hi_ext > hi_sel) hi_sel = ctx->collect_hi_ext;
+#endif
+            const double expect = 4.0 * ctx->density * 2.0 * dl * (double)total / (double)ctx->world; // in-bracket pairs this rank should see, with a margin
+            TRY(run_select(ctx, klo, hi_sel, 0, even, log_n, ctx->dec_dev, (uint64_t)std::min(expect, 1e18)));
+            CU(cudaMemcpyAsync(&ctx->hs->dec, ctx->dec_dev, sizeof(StepDecision), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(&ctx->hs->med, ctx->medres, sizeof(MedianResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->ev_med, ctx->stream));
+            ctx->med_pending = true;
+            ctx->pending_verify = true;
+            ctx->pending_dl = dl;
+            ctx->last_pred = predicted;
+            return SVGDB_OK;
+        }
         TRY(read_pass_results(ctx, MODE_COLLECT, &mid));
         uint64_t b = ctx->hs->below;
         ctx->density = std::max(0.25, (double)mid / (2.0 * dl * (double)total)); // exact in-bracket count, even on overflow
@@ -604,7 +644,9 @@ int median_scale(svgdb_ctx *ctx)
         if (hit) {
             lo = klo; hi = khi; below_known = b; collected = true;
             ++ctx->stats.median_bracket_hits;
+            ctx->miss_boost = std::max(1.0, 0.5 * ctx->miss_boost);
         } else {
+            ctx->miss_boost = std::min(64.0, ctx->miss_boost * 4.0);
             ctx->delta = std::min(delta_max, std::max(ctx->delta, 2e-5) * 4.0);
         }
     }
@@ -683,6 +725,13 @@ int finish_median(svgdb_ctx *ctx)
     if (!ctx->med_pending) return SVGDB_OK;
     ctx->med_pending = false;
     CU(cudaEventSynchronize(ctx->ev_med));
+    if (ctx->pending_verify) { // an optimistic step: its verdict arrived with the result
+        if (ctx->hs->dec.hit == 0) return SVGDB_OK; // a miss: the result is meaningless; settle_step() repeats the step
+        const double total = (double)ctx->N * (double)ctx->N;
+        ctx->density = std::max(0.25, (double)ctx->hs->dec.mid / (2.0 * ctx->pending_dl * total));
+        ++ctx->stats.median_bracket_hits;
+        ctx->miss_boost = std::max(1.0, 0.5 * ctx->miss_boost);
+    }
     const double delta_max = bracket_delta_max(ctx, (double)ctx->N * (double)ctx->N);
     ctx->stats.last_scale = ctx->hs->med.scale;
     {
@@ -1192,6 +1241,7 @@ int launch_phi_wide(svgdb_ctx *ctx, bool debug_phi)
     o.ub = ctx->ub;
     o.X_out = ctx->X[ctx->cur ^ 1];
     o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+    o.miss = ctx->miss_dev;
     const int64_t cnt = ctx->n_rows * ctx->d;
     opt_update_wide_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
     KERNEL_CHECK();
@@ -1285,6 +1335,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         o.ub = ctx->ub;
         o.X_out = ctx->X[ctx->cur ^ 1];
         o.phi_out = debug_phi ? ctx->phi_dbg : nullptr;
+        o.miss = ctx->miss_dev;
         opt_update_tc32_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(o);
         KERNEL_CHECK();
         if (stream_rows) {
@@ -1515,8 +1566,34 @@ int prepare_and_phi(svgdb_ctx *ctx, bool debug_phi)
     return SVGDB_OK;
 }
 
+int one_step(svgdb_ctx *ctx);
+
+// Reads the verdict of the last optimistic step (by now the step has been enqueued in full; usually it has long finished) and, if
+// its predicted bracket missed the median, repeats that step with the synchronous median: nothing persistent was changed by the
+// missed attempt (the optimizer update is predicated on the device-side flag), its X_next is simply overwritten.
+int settle_step(svgdb_ctx *ctx)
+{
+    if (!ctx->pending_verify) return SVGDB_OK;
+    TRY(finish_median(ctx)); // waits for the verdict; on a hit also books the median into the prediction history
+    ctx->pending_verify = false;
+    if (ctx->hs->dec.hit != 0) return SVGDB_OK;
+    // miss: undo the bookkeeping of the attempt and run the step again, this time waiting for every pass's counts
+    CU(cudaMemsetAsync(ctx->miss_dev, 0, sizeof(int), ctx->stream));
+    ctx->cur ^= 1;
+    --ctx->counter;
+    --ctx->stats.iterations;
+    ctx->delta = std::min(bracket_delta_max(ctx, (double)ctx->N * (double)ctx->N), std::max(ctx->delta, 2e-5) * 4.0);
+    ctx->miss_boost = std::min(64.0, ctx->miss_boost * 4.0);
+    const bool keep = ctx->opt_suspended;
+    ctx->opt_suspended = true;
+    const int rc = one_step(ctx);
+    ctx->opt_suspended = keep;
+    return rc;
+}
+
 int one_step(svgdb_ctx *ctx)
 {
+    TRY(settle_step(ctx));
     ++ctx->counter; // Adam increments its counter before the bias correction (Adam.hpp:80-82)
     if (ctx->opt.kind == OPT_ADAM) {
         ctx->opt.bias1 = 1.0 - std::pow(ctx->opt.beta1, (double)ctx->counter);
@@ -1667,6 +1744,10 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaMalloc(&ctx->cand_count, 8));
     CU(cudaMalloc(&ctx->hist, HIST_BINS * 8));
     CU(cudaMalloc(&ctx->sel, sizeof(SelectState)));
+    CU(cudaMalloc(&ctx->dec_dev, sizeof(StepDecision)));
+    CU(cudaMalloc(&ctx->miss_dev, sizeof(int)));
+    CU(cudaMemsetAsync(ctx->dec_dev, 0, sizeof(StepDecision), ctx->stream));
+    CU(cudaMemsetAsync(ctx->miss_dev, 0, sizeof(int), ctx->stream));
     CU(cudaMalloc(&ctx->medres, sizeof(MedianResult)));
     CU(cudaMallocHost(&ctx->hs, sizeof(HostScratch)));
     {
@@ -1691,7 +1772,7 @@ void svgdb_destroy(svgdb_ctx *ctx)
     cudaFree(ctx->a_dev); cudaFree(ctx->lb); cudaFree(ctx->ub); cudaFree(ctx->means_dev); cudaFree(ctx->prec_dev);
     cudaFree(ctx->Hsum_dev); cudaFree(ctx->Wsum_dev); cudaFree(ctx->R_dev); cudaFree(ctx->Rt_dev); cudaFree(ctx->Rinv_dev); cudaFree(ctx->Y_dev); cudaFree(ctx->GH_dev);
     cudaFree(ctx->pass_words); cudaFree(ctx->cand_count); cudaFree(ctx->hist); cudaFree(ctx->cand);
-    cudaFree(ctx->sel); cudaFree(ctx->medres);
+    cudaFree(ctx->sel); cudaFree(ctx->medres); cudaFree(ctx->dec_dev); cudaFree(ctx->miss_dev);
     if (ctx->hs) cudaFreeHost(ctx->hs);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1935,7 +2016,7 @@ int svgdb_step(svgdb_ctx *ctx, int64_t iters)
     if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
     CU(cudaSetDevice(ctx->device));
     for (int64_t it = 0; it < iters; ++it) TRY(one_step(ctx));
-    return SVGDB_OK;
+    return settle_step(ctx); // the last step's bracket verdict (repairs the step if it missed); everything else stays asynchronous
 }
 
 int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int64_t iters)
@@ -1989,9 +2070,14 @@ int svgdb_step_host(svgdb_ctx *ctx, const double *rows_in, double *rows_out, int
     cudaGetLastError();
     ctx->stream_out = pinned && ctx->host_chunks != 0 ? rows_out : nullptr;
     ctx->streamed = false;
-    const int rc = one_step(ctx);
+    int rc = one_step(ctx);
     ctx->stream_out = nullptr;
     ctx->up_chunks = 0;
+    if (rc == SVGDB_OK && ctx->pending_verify) {
+        CU(cudaStreamSynchronize(ctx->copy_stream)); // the streamed rows of a missed attempt must have landed before the repair's rows are copied over them
+        rc = settle_step(ctx);
+        if (rc == SVGDB_OK && ctx->hs->dec.hit == 0) ctx->streamed = false; // repaired: fetch the rows again below
+    }
     if (rc != SVGDB_OK) {
         cudaStreamSynchronize(ctx->copy_stream); // nothing may still be reading or writing the caller's buffers
         return rc;
@@ -2012,7 +2098,13 @@ int svgdb_compute_phi(svgdb_ctx *ctx, double *phi, double *scale_out)
     if (!ctx) return SVGDB_ERR_INVALID;
     TRY(check_ready(ctx));
     CU(cudaSetDevice(ctx->device));
-    TRY(prepare_and_phi(ctx, true));
+    {
+        const bool keep = ctx->opt_suspended;
+        ctx->opt_suspended = true; // inspection: the scale is read back right away
+        const int rc = prepare_and_phi(ctx, true);
+        ctx->opt_suspended = keep;
+        TRY(rc);
+    }
     if (phi) {
         // gather the local rows of every rank through V's storage (phi is debug output)
         double *tmp = ctx->V;
@@ -2043,7 +2135,13 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
     if (ctx->precision == SVGDB_PRECISION_TC32) TRY(launch_dist_operands(ctx));
 #endif
     if (ctx->precision != SVGDB_PRECISION_TC32) TRY(launch_rownorm(ctx));
-    TRY(compute_scale_dev(ctx));
+    {
+        const bool keep = ctx->opt_suspended;
+        ctx->opt_suspended = true; // inspection: the scale is read back right away
+        const int rc = compute_scale_dev(ctx);
+        ctx->opt_suspended = keep;
+        TRY(rc);
+    }
     double a = 0.0;
     CU(cudaMemcpyAsync(&a, ctx->a_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
