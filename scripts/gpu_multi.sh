@@ -1,20 +1,27 @@
 #!/usr/bin/env bash
-# multi-GPU: parity tests at every available rank count, then bench lines (c3 and c4) under torch.distributed.run
+# multi-GPU: parity check at NG ranks, then bench lines under torch.distributed.run.
+#   usage: gpu_multi.sh NG "<workload> [ENV=VAL ...]" ...      (SKIP_CHECK=1 skips the parity check)
 set -u
 NG=${1:-2}; shift || true
 OUT=gpurun_out/multi$NG; mkdir -p $OUT
-if [ "${SKIP_PYTEST:-0}" != "1" ]; then
-  timeout 900 python -m pytest tests/test_gpu_multi.py -q -x -s -p no:cacheprovider > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
-  grep -E "world=|passed|failed|exit|rror" $OUT/pytest.log | tail -40
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
+if [ "${SKIP_CHECK:-0}" != "1" ]; then
+  for prec in tc32 f64; do
+    timeout 600 $TR --master-port 29540 tests/multi_gpu_check.py --precision $prec > $OUT/check_$prec.log 2>&1; echo "check $prec exit $?" | tee -a $OUT/check_$prec.log
+    grep -E "world=" $OUT/check_$prec.log | tail -8
+  done
 fi
-for wl in "$@"; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus $NG --workload $wl --steps 20 --warmup 10 --no-cpu-baseline > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err
-  echo "bench $wl exit $?"; tail -2 $OUT/bench_$wl.err | cut -c1-300
-  python - $OUT/bench_$wl.json <<'PY'
+k=0
+for spec in "$@"; do
+  set -- $spec; wl=$1; shift; k=$((k+1))
+  tag=${wl}_$k
+  env "$@" timeout 900 $TR --master-port $((29600+k)) bench.py --gpus $NG --workload $wl --steps 20 --warmup 10 --no-cpu-baseline > $OUT/bench_$tag.json 2> $OUT/bench_$tag.err
+  echo "bench $wl $* exit $?"; grep -v "OMP_NUM_THREADS\|\*\*\*\*" $OUT/bench_$tag.err | tail -2 | cut -c1-300
+  python - $OUT/bench_$tag.json <<'PY'
 import json, sys
 try:
     d = json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith("{")][-1])
-    print("  n_gpus %d ms/step %.3f e2e %.3f kernel_ms %.3f phases %s parity %s" % (d["n_gpus"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["kernel_ms"], {k: round(v, 3) for k, v in d["roofline"]["phase_ms_per_step"].items()}, d["parity"]))
+    print("  n_gpus %d ms/step %.3f e2e %.3f kernel_ms %.3f phases %s parity_ok %s phi_err %.3g passes/step %.2f" % (d["n_gpus"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["kernel_ms"], {k: round(v, 3) for k, v in d["roofline"]["phase_ms_per_step"].items()}, d["parity"]["ok"], d["parity"]["phi_sampled_rows_max_err_over_max_phi"], d["config"]["median_passes_per_step"]))
 except Exception as e:
     print("  no bench line:", e)
 PY

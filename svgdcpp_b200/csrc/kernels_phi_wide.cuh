@@ -43,7 +43,7 @@ struct PWCfg {
 };
 
 constexpr int PW_EWARPS = 8;
-constexpr int PW_THREADS = (PW_EWARPS + 2) * 32;
+constexpr int PW_THREADS = (PW_EWARPS + 3) * 32; // + X^ / offset-chunk producer, MMA issuer, V producer
 
 // ---- operand preparation (one warp per particle; any DP) ---------------------------------------------------------------
 // XA[row] = [hi(DP) | lo(DP)] (row operand), XB[row] = [hi(DP)] or [hi(DP) | lo(DP)] (column operand, PRECISE), UA / WB as in
@@ -127,7 +127,7 @@ struct PhiWArgs {
     const __half *WB;      // [n_pad128 / 128][4 KB]
     int64_t row0, n_rows;  // this launch's rows
     int n_junits;          // 64-particle column units (n_pad128 / 64)
-    int n_itiles;          // 128-row i-tiles of this launch
+    int n_itiles;          // i-tile groups of this launch: 128 rows per CTA of the cluster (CL tiles per group)
     int max_seg;           // longest run of column units accumulated in TMEM before the partial sums are flushed (see p2_segment)
     int dbg;
     int *err;
@@ -149,7 +149,11 @@ __device__ __forceinline__ bool pw_segment(const PhiWArgs &p, long long &pos, lo
     return true;
 }
 
-template <int DP, bool PRECISE>
+// CL = 2: launched as clusters of two CTAs that walk the SAME column units with two consecutive i-tiles.  Every box of a stage is
+// fetched from L2 once and multicast into both CTAs' shared memory (each CTA issues half of the boxes); a stage is refilled when
+// both CTAs' MMAs have released it (the commits arrive on both CTAs' `empty` barriers).  Measured without it (ncu, d = 256): the
+// kernel runs at exactly the rate at which 148 SMs can pull 100 KB per unit from L2 (5.5 TB/s), the tensor pipe idles half the time.
+template <int DP, bool PRECISE, int CL>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ PhiWArgs p)
 {
@@ -157,18 +161,28 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     constexpr int KC = Cfg::KC, GW = Cfg::GW, G = Cfg::G, STAGES = Cfg::STAGES;
     constexpr uint32_t STAGE = Cfg::STAGE, XB_BYTES = Cfg::XB_BYTES, V_BYTES = Cfg::V_BYTES;
     constexpr uint32_t COL_PHI = Cfg::COL_PHI, COL_A = Cfg::COL_A;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
 
+    // work is dealt to clusters: a cluster takes a contiguous range of (i-tile group, column group, column unit); its CTA r works on
+    // i-tile CL * group + r.  (p.n_itiles counts i-tile GROUPS of CL tiles.)
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const long long n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
     const long long units = (long long)p.n_itiles * G * p.n_junits;
-    const long long u_beg = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
-    if (u_beg >= u_end) return;
+    const long long u_beg = units * cluster_id / n_clusters, u_end = units * (cluster_id + 1) / n_clusters;
+    if (CL == 1 && u_beg >= u_end) return;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sAex = smem + STAGES * STAGE;  // [P2_AEX_BYTES] row exponent-offset chunk of the i-tile
     uint64_t *bars = (uint64_t *)(sAex + P2_AEX_BYTES);
-    uint64_t *full = bars;                  // [STAGES] TMA bytes landed
-    uint64_t *empty = full + STAGES;        // [STAGES] every MMA reading the stage has completed
-    uint64_t *s_full = empty + STAGES;      // [2] S of the buffer complete
+    // A stage's X^ part (with the offset chunk) is consumed by S(u), its V part one unit later by PV(u): two rings over the same
+    // slots, each with its own barriers and its own producer warp, so that X^(u + 2) is on its way while S(u + 1) and PV(u) run
+    // (with one ring the slot of unit u was released only by PV(u) and needed again by the very next MMA batch, S(u + 2)).
+    uint64_t *full = bars;                  // [STAGES] X^ + chunk bytes landed
+    uint64_t *empty = full + STAGES;        // [STAGES] every S MMA reading the slot has completed (in every CTA of the cluster)
+    uint64_t *vfull = empty + STAGES;       // [STAGES] V bytes landed
+    uint64_t *vempty = vfull + STAGES;      // [STAGES] every PV MMA reading the slot has completed
+    uint64_t *s_full = vempty + STAGES;     // [2] S of the buffer complete
     uint64_t *e_ready = s_full + 2;         // [2] E of the buffer written (8 warp arrivals)
     uint64_t *phi_full = e_ready + 2;       // every MMA of the segment complete
     uint64_t *a_ready = phi_full + 1;       // row operand in TMEM, Phi flushed (8 warp arrivals)
@@ -176,7 +190,7 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL); mbar_init(vfull + s, 1); mbar_init(vempty + s, CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, PW_EWARPS); }
         mbar_init(phi_full, 1);
         mbar_init(a_ready, PW_EWARPS);
@@ -185,6 +199,7 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     if (warp == PW_EWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all(); // the peer's barriers are initialised before anything of ours can arrive on them
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
@@ -200,16 +215,45 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (elect_one()) {
                     uint8_t *st = smem + slot * STAGE;
                     const int j0 = ju * 64;
-                    mbar_arrive_expect_tx(full + slot, STAGE);
+                    mbar_arrive_expect_tx(full + slot, XB_BYTES + Cfg::W_BYTES); // all of the X^ part's bytes, whoever fetches them
+                    // with a cluster, CTA r fetches the boxes of parity r and multicasts them
+                    auto box = [&](int idx, uint8_t *dst, const CUtensorMap *m, int c0, int c1) {
+                        if (CL == 1) tma_load_2d(dst, m, c0, c1, full + slot);
+                        else if ((uint32_t)(idx % CL) == crank) tma_load_2d_mc(dst, m, c0, c1, full + slot, MC_MASK);
+                    };
+                    constexpr int NXB = KC * (PRECISE ? 2 : 1);
 #pragma unroll
-                    for (int c = 0; c < KC * (PRECISE ? 2 : 1); ++c) // hi chunks, then lo chunks (columns [DP, 2 DP) of the operand rows)
-                        tma_load_2d(st + c * 8192, &mapB, c * 64, j0, full + slot);
+                    for (int c = 0; c < NXB; ++c) // hi chunks, then lo chunks (columns [DP, 2 DP) of the operand rows)
+                        box(c, st + c * 8192, &mapB, c * 64, j0);
+                    const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.WB) + (size_t)ju * 2048;
+                    if (CL == 1) bulk_load_1d(st + XB_BYTES + V_BYTES, wsrc, 2048, full + slot);
+                    else if (crank == 0) bulk_load_1d_mc(st + XB_BYTES + V_BYTES, wsrc, 2048, full + slot, MC_MASK);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == PW_EWARPS + 2) { // ---- TMA producer of the V^T tiles
+        long long pos = u_beg;
+        PWSeg sg;
+        uint32_t u = 0;
+        bool ok = true;
+        while (ok && pw_segment<G>(p, pos, u_end, sg)) {
+            for (int ju = sg.jb; ok && ju < sg.je; ++ju, ++u) {
+                const uint32_t slot = u % STAGES, use = u / STAGES;
+                if (!mbar_wait(vempty + slot, (use & 1) ^ 1, p.err, 111)) { ok = false; break; }
+                if (elect_one()) {
+                    uint8_t *st = smem + slot * STAGE + XB_BYTES;
+                    const int j0 = ju * 64;
+                    mbar_arrive_expect_tx(vfull + slot, V_BYTES);
+                    auto box = [&](int idx, uint8_t *dst, int c0, int c1) {
+                        if (CL == 1) tma_load_2d(dst, &mapV, c0, c1, vfull + slot);
+                        else if ((uint32_t)(idx % CL) == crank) tma_load_2d_mc(dst, &mapV, c0, c1, vfull + slot, MC_MASK);
+                    };
 #pragma unroll
                     for (int b = 0; b < GW / 64; ++b) {
-                        tma_load_2d(st + XB_BYTES + b * 8192, &mapV, j0, sg.g * GW + b * 64, full + slot);                 // v_hi rows of the group
-                        tma_load_2d(st + XB_BYTES + GW * 128 + b * 8192, &mapV, j0, DP + sg.g * GW + b * 64, full + slot); // v_lo rows
+                        box(2 * b, st + b * 8192, j0, sg.g * GW + b * 64);                      // v_hi rows of the group
+                        box(2 * b + 1, st + GW * 128 + b * 8192, j0, DP + sg.g * GW + b * 64);  // v_lo rows
                     }
-                    bulk_load_1d(st + XB_BYTES + V_BYTES, reinterpret_cast<const uint8_t *>(p.WB) + (size_t)ju * 2048, 2048, full + slot);
                 }
                 __syncwarp();
             }
@@ -249,13 +293,16 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 }
                 umma_f16_ss_desc(dS, aex_lo, DESC_HI_K_NOSW, wb_lo0 + slot * (STAGE >> 4), DESC_HI_K_NOSW, idesc_s);          // + u_i + w_j
                 umma_commit(s_full + buf);
+                if (CL == 1) umma_commit(empty + slot);       // the X^ part of the slot may be refilled
+                else umma_commit_mc(empty + slot, MC_MASK);   // ... once both CTAs of the cluster are done with it
             }
             __syncwarp();
             return true;
         };
         // Phi += E(u) . [v_hi ; v_lo] of the group
         auto issue_pv = [&](uint32_t u, bool first, bool last) -> bool {
-            const uint32_t slot = u % STAGES, buf = u & 1u;
+            const uint32_t slot = u % STAGES, use = u / STAGES, buf = u & 1u;
+            if (!mbar_wait(vfull + slot, use & 1, p.err, 123)) return false;
             if (!mbar_wait(e_ready + buf, (u >> 1) & 1, p.err, 122)) return false;
             tc_fence_after();
             if (elect_one()) {
@@ -273,7 +320,8 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_f16_ts2<true>(dP, e + 16 + ecol[ks], vh + ks * 2, idesc_pv);           // E_lo . v_hi
                 }
-                umma_commit(empty + slot);
+                if (CL == 1) umma_commit(vempty + slot);
+                else umma_commit_mc(vempty + slot, MC_MASK); // both CTAs of the cluster must be done with a slot before either refills it
                 if (last) umma_commit(phi_full);
             }
             __syncwarp();
@@ -303,7 +351,7 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         bool ok = true;
         for (uint32_t seg = 0; ok && pw_segment<G>(p, pos, u_end, sg); ++seg) {
             const uint32_t nu = (uint32_t)(sg.je - sg.jb);
-            const int64_t iw0 = p.row0 + (int64_t)sg.it * TC_TILE;
+            const int64_t iw0 = p.row0 + ((int64_t)sg.it * CL + crank) * TC_TILE;
             const int64_t i = iw0 + row;
             { // row operand of particle i -> TMEM: hi half by the h = 0 warp, lo half by the h = 1 warp (previous segment complete: phi_full)
                 const uint4 *src = reinterpret_cast<const uint4 *>(p.XA + i * (2 * DP) + DP * h);
@@ -403,6 +451,7 @@ phiw_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all(); // nobody leaves while the peer may still multicast into its shared memory or arrive on its barriers
     if (warp == PW_EWARPS) tmem_dealloc(tmem, 512);
 }
 

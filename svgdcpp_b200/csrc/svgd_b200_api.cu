@@ -174,9 +174,9 @@ struct svgdb_ctx {
     int dist_gated = -1;   // SVGDB_DIST_GATED=0/1 forces the flat / gated counting epilogue (default: chosen per pass)
     // optimistic steps (tensor-core path, median history available): the bracket verdict is taken on the device and read by the host
     // after the step has been enqueued; a miss is repaired by repeating the step synchronously
-    int optimistic = -1;           // SVGDB_OPTIMISTIC=0 / 1 forces it off / on; default (-1): on when the rows are sharded over several ranks --
-                                   // on one GPU the host round trip hides behind grad log p on the side stream and the extra kernels cost 1.5 %,
-                                   // on eight the round trip and the launches behind it are a tenth of the step
+    int optimistic = 0;            // SVGDB_OPTIMISTIC=1: on.  Off by default: measured on B200 it does not pay -- on one GPU the
+                                   // host round trip hides behind grad log p on the side stream (2.67 vs 2.63 ms per step with it), on eight the
+                                   // step is bound by the collectives and the replicated operand preparation (0.727 vs 0.713 ms)
     bool opt_suspended = false;    // a repair or an inspection call is running: synchronous
     bool pending_verify = false;   // the last step's verdict has not been read yet
     double pending_dl = 0.0;       // half-width of that step's bracket (density bookkeeping)
@@ -190,6 +190,7 @@ struct svgdb_ctx {
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
+    int phi_cluster = 1; // SVGDB_PHI_CLUSTER=0 (measurement aid): the wide pair kernel without 2-CTA clusters / TMA multicast
     int phi_max_seg = 0; // SVGDB_PHI_MAX_SEG (measurement aid): column tiles accumulated in TMEM between flushes (0: default per variant)
     int tc32_variant = SVGDB_TC32_AUTO; // svgdb_set_tc32_variant / SVGDB_TC32_VARIANT: arithmetic of the tensor-core pair kernel
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
@@ -371,6 +372,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_MAX_SEG")) ctx->phi_max_seg = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_CLUSTER")) ctx->phi_cluster = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_HOST_CHUNKS")) ctx->host_chunks = std::atoi(e);
     return SVGDB_OK;
 }
@@ -611,7 +613,7 @@ int median_scale(svgdb_ctx *ctx)
         ctx->dist_fold_next = true;
         TRY(launch_dist_pass(ctx, MODE_COLLECT, klo, khi, 0));
         const bool need_both_dev = even && ctx->precision == SVGDB_PRECISION_TC32;
-        const bool optimistic = ctx->optimistic < 0 ? ctx->world > 1 : ctx->optimistic != 0;
+        const bool optimistic = ctx->optimistic != 0;
         if (optimistic && !ctx->opt_suspended && ctx->precision == SVGDB_PRECISION_TC32) {
             // No host round trip: the verdict on the bracket is taken on the device, the select and everything after it are enqueued
             // at once, and the host reads the verdict when the step has been enqueued (settle_step).
@@ -1199,27 +1201,47 @@ int launch_phi_wide(svgdb_ctx *ctx, bool debug_phi)
     a.row0 = ctx->row0;
     a.n_rows = ctx->n_rows;
     a.n_junits = (int)(ctx->n_pad128 / 64);
-    a.n_itiles = (int)((ctx->n_rows + 127) / 128);
+    const int cl = ctx->phi_cluster != 0 ? 2 : 1; // CTAs per cluster sharing the column tiles by TMA multicast
+    a.n_itiles = (int)((ctx->n_rows + 128 * cl - 1) / (128 * cl));
     a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 64 : 128); // column units (64 particles) per flush
     a.dbg = 0;
     a.err = ctx->tc_err;
     const bool precise = tc32_precise(ctx);
     const int groups = dp == 256 ? 2 : 1;
     const long long units = (long long)a.n_itiles * groups * a.n_junits;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count, units));
+    const unsigned n_clusters = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count / cl, units));
     prof_mark(ctx, 5);
-#define SVGDB_PW_LAUNCH(DPV)                                                                                                                        \
-    case DPV:                                                                                                                                       \
-        if (precise) phiw_tc32_kernel<DPV, true><<<grid, PW_THREADS, PWCfg<DPV, true>::SMEM, ctx->stream>>>(ctx->mapBWP, ctx->mapVW, a);            \
-        else phiw_tc32_kernel<DPV, false><<<grid, PW_THREADS, PWCfg<DPV, false>::SMEM, ctx->stream>>>(ctx->mapBW, ctx->mapVW, a);                   \
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(n_clusters * cl);
+        cfg.blockDim = dim3(PW_THREADS);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)cl;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+#define SVGDB_PW_LAUNCH(DPV, PR, CLV)                                                                                   \
+    do {                                                                                                                \
+        cfg.dynamicSmemBytes = PWCfg<DPV, PR>::SMEM;                                                                    \
+        CU(cudaLaunchKernelEx(&cfg, phiw_tc32_kernel<DPV, PR, CLV>, PR ? ctx->mapBWP : ctx->mapBW, ctx->mapVW, a));       \
+    } while (0)
+#define SVGDB_PW_DP(DPV)                                                                                                \
+    case DPV:                                                                                                           \
+        if (precise) { if (cl == 2) SVGDB_PW_LAUNCH(DPV, true, 2); else SVGDB_PW_LAUNCH(DPV, true, 1); }                \
+        else { if (cl == 2) SVGDB_PW_LAUNCH(DPV, false, 2); else SVGDB_PW_LAUNCH(DPV, false, 1); }                      \
         break;
-    switch (dp) {
-        SVGDB_PW_LAUNCH(128)
-        SVGDB_PW_LAUNCH(192)
-        SVGDB_PW_LAUNCH(256)
-    default: return fail(ctx, SVGDB_ERR_DIMENSION, "internal: no wide pair kernel for this dimension");
-    }
+        switch (dp) {
+            SVGDB_PW_DP(128)
+            SVGDB_PW_DP(192)
+            SVGDB_PW_DP(256)
+        default: return fail(ctx, SVGDB_ERR_DIMENSION, "internal: no wide pair kernel for this dimension");
+        }
+#undef SVGDB_PW_DP
 #undef SVGDB_PW_LAUNCH
+    }
     KERNEL_CHECK();
     prof_mark(ctx, 6);
     OptWArgs o{};
@@ -1707,8 +1729,10 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         if (d > svgdb::tc::TC_D) {
             using namespace svgdb::tc;
 #define SVGDB_WIDE_ATTR(DPV)                                                                                                                              \
-    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, false>::SMEM));                    \
-    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, true>::SMEM));                      \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, false>::SMEM));                 \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, true>::SMEM));                   \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, false>::SMEM));                 \
+    CU(cudaFuncSetAttribute(phiw_tc32_kernel<DPV, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWCfg<DPV, true>::SMEM));                   \
     CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_HIST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));        \
     CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_COLLECT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));     \
     CU(cudaFuncSetAttribute(distw_tc32_kernel<DPV, MODE_COLLECT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DWCfg<DPV>::SMEM));

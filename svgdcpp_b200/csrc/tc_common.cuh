@@ -81,6 +81,32 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
                  : "memory");
 }
 
+// ---- thread-block clusters: TMA multicast and the barrier traffic that goes with it ---------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// every thread of every CTA of the cluster
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// The box lands at the same shared-memory offset in every CTA of `mask` and completes bytes on the mbarrier at `bar`'s offset in each.
+__device__ __forceinline__ void tma_load_2d_mc(void *dst_smem, const CUtensorMap *m, int c0, int c1, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_mc(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *holder_smem, uint32_t ncols) // whole warp
 {
@@ -167,6 +193,14 @@ __device__ __forceinline__ void umma_f16_ts2r(uint32_t d_tmem, uint32_t a_tmem, 
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ... and on the mbarrier at `bar`'s offset in every CTA of `mask` (a pipeline stage filled by multicast is free when all readers are done)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
 }
 
 // ---- TMEM <-> registers: warp w touches lanes 32*(w%4) .. +31, thread = one lane (matrix row) ---------
