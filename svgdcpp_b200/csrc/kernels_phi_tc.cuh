@@ -256,17 +256,23 @@ __device__ __forceinline__ bool p2_segment(const Phi2Args &p, long long &pos, lo
 constexpr int P2_EWARPS = 16;
 constexpr int P2_THREADS = (P2_EWARPS + 3) * 32;
 
-template <int POLY, bool PRECISE>
+// CL = 2: clusters of two CTAs walk the SAME j-tiles with two consecutive i-pairs (512 particle rows per cluster); every box of a
+// stage is fetched from L2 once and multicast into both CTAs (each issues half of the boxes), a stage is refilled when the MMAs of
+// both CTAs have released it.  The kernel pulls 7 GB per launch from L2 at the headline shape (4.1 TB/s): this halves it.
+template <int POLY, bool PRECISE, int CL = 1>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p)
 {
     using Cfg = P2Cfg<PRECISE>;
     constexpr int P2_STAGES = Cfg::STAGES;
     constexpr uint32_t P2_XB_BYTES = Cfg::XB_BYTES, P2_STAGE = Cfg::STAGE, P2_TX = Cfg::TX;
-    // this CTA's contiguous range of (i-pair, j-tile) work units
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+    // the cluster's contiguous range of (i-pair group, j-tile) work units (p.n_ipairs counts groups of CL i-pairs; CTA r takes pair CL g + r)
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const long long n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
     const long long units = (long long)p.n_ipairs * p.n_jtiles;
-    const long long u_beg = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
-    if (u_beg >= u_end) return;
+    const long long u_beg = units * cluster_id / n_clusters, u_end = units * (cluster_id + 1) / n_clusters;
+    if (CL == 1 && u_beg >= u_end) return;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -282,7 +288,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2); }
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CL); }
         for (int s = 0; s < 4; ++s) { mbar_init(s_full + s, 1); mbar_init(e_ready + s, 8); }
         for (int s = 0; s < 2; ++s) { mbar_init(phi_full + s, 1); mbar_init(a_ready + s, 8); }
         fence_barrier_init();
@@ -290,6 +296,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     if (warp == P2_EWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all(); // the peer's barriers are initialised before anything of ours can arrive on them
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
@@ -305,13 +312,24 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (elect_one()) {
                     uint8_t *st = smem + slot * P2_STAGE;
                     const int j0 = jt * TC_TILE;
-                    mbar_arrive_expect_tx(full + slot, P2_TX);
-                    tma_load_2d(st, &mapB, 0, j0, full + slot);
-                    if (PRECISE) tma_load_2d(st + 16384, &mapB, 64, j0, full + slot); // lo_j
+                    mbar_arrive_expect_tx(full + slot, P2_TX); // all of the stage's bytes, whoever fetches them
+                    const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.WB) + (size_t)jt * P2_W_BYTES;
+                    if (CL == 1) {
+                        tma_load_2d(st, &mapB, 0, j0, full + slot);
+                        if (PRECISE) tma_load_2d(st + 16384, &mapB, 64, j0, full + slot); // lo_j
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
-                    bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, reinterpret_cast<const uint8_t *>(p.WB) + (size_t)jt * P2_W_BYTES, P2_W_BYTES, full + slot);
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
+                        bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, wsrc, P2_W_BYTES, full + slot);
+                    } else if (crank == 0) { // CTA 0: the particle operand and its offset chunk; CTA 1: the four V boxes (about half of the bytes each)
+                        tma_load_2d_mc(st, &mapB, 0, j0, full + slot, MC_MASK);
+                        if (PRECISE) tma_load_2d_mc(st + 16384, &mapB, 64, j0, full + slot, MC_MASK);
+                        bulk_load_1d_mc(st + P2_XB_BYTES + P2_V_BYTES, wsrc, P2_W_BYTES, full + slot, MC_MASK);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tma_load_2d_mc(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot, MC_MASK);
+                    }
                 }
                 __syncwarp();
             }
@@ -378,7 +396,10 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     umma_f16_ts2<true>(dP, e + 48, vh + 4, idesc);
                     umma_f16_ts2<true>(dP, e + 56, vh + 6, idesc);
                 }
-                if (k == 1) umma_commit(empty + slot);
+                if (k == 1) {
+                    if (CL == 1) umma_commit(empty + slot);
+                    else umma_commit_mc(empty + slot, MC_MASK); // both MMA warps of both CTAs must be done with a stage before it is refilled
+                }
                 if (k == 1 && last) umma_commit(phi_full + w);
             }
             __syncwarp();
@@ -415,7 +436,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         bool ok = true;
         for (uint32_t seg = 0; ok && p2_segment(p, pos, u_end, sg); ++seg) {
             const int nt = sg.je - sg.jb;
-            const int64_t iw0 = p.row0 + (int64_t)sg.ip * (2 * TC_TILE) + w * TC_TILE;
+            const int64_t iw0 = p.row0 + ((int64_t)sg.ip * CL + crank) * (2 * TC_TILE) + w * TC_TILE;
             const int64_t i = iw0 + row;
             { // row operand of particle i -> TMEM: hi half by the h = 0 warp, lo half by the h = 1 warp (previous segment complete: phi_full)
                 const uint4 *src = reinterpret_cast<const uint4 *>(p.XA2 + i * P2_A_LD + 64 * h);
@@ -554,6 +575,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all(); // nobody leaves while the peer may still multicast into its shared memory or arrive on its barriers
     if (warp == P2_EWARPS) tmem_dealloc(tmem, 512);
 }
 

@@ -190,7 +190,9 @@ struct svgdb_ctx {
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
     int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
-    int phi_cluster = 1; // SVGDB_PHI_CLUSTER=0 (measurement aid): the wide pair kernel without 2-CTA clusters / TMA multicast
+    int phi_cluster = -1; // 2-CTA clusters with TMA multicast of the column tiles in the pair kernels.  Default (-1): on for the wide kernel (d > 64:
+                          // -10 % at d = 256), off for d <= 64 (measured: no gain, 1.83 ms either way -- that kernel is not bound by L2 traffic);
+                          // SVGDB_PHI_CLUSTER=0 / 1 forces it
     int phi_max_seg = 0; // SVGDB_PHI_MAX_SEG (measurement aid): column tiles accumulated in TMEM between flushes (0: default per variant)
     int tc32_variant = SVGDB_TC32_AUTO; // svgdb_set_tc32_variant / SVGDB_TC32_VARIANT: arithmetic of the tensor-core pair kernel
     int phi_dbg_mode = 0; // SVGDB_PHI_DBG (development): see Phi2Args::dbg
@@ -1201,7 +1203,7 @@ int launch_phi_wide(svgdb_ctx *ctx, bool debug_phi)
     a.row0 = ctx->row0;
     a.n_rows = ctx->n_rows;
     a.n_junits = (int)(ctx->n_pad128 / 64);
-    const int cl = ctx->phi_cluster != 0 ? 2 : 1; // CTAs per cluster sharing the column tiles by TMA multicast
+    const int cl = (ctx->phi_cluster < 0 ? true : ctx->phi_cluster != 0) ? 2 : 1; // CTAs per cluster sharing the column tiles by TMA multicast
     a.n_itiles = (int)((ctx->n_rows + 128 * cl - 1) / (128 * cl));
     a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 64 : 128); // column units (64 particles) per flush
     a.dbg = 0;
@@ -1302,27 +1304,47 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         a.row0 = ctx->row0 + off;
         a.n_rows = rows;
         a.n_jtiles = (int)(ctx->n_pad128 / 128);
-        a.n_ipairs = chunk_ipairs[ch];
+        const int cl = (ctx->phi_cluster < 0 ? false : ctx->phi_cluster != 0) ? 2 : 1; // CTAs per cluster sharing the column tiles by TMA multicast
+        a.n_ipairs = (chunk_ipairs[ch] + cl - 1) / cl; // i-pair groups
         a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 32 : 128); // j-tiles (128 particles) per flush
         a.poly = ctx->phi_poly;
         a.dbg = ctx->phi_dbg_mode;
         a.err = ctx->tc_err;
         a.trace = ctx->tc_trace;
         const long long units = (long long)a.n_ipairs * a.n_jtiles;
-        const unsigned grid = (unsigned)std::min<long long>(ctx->sm_count, units); // persistent: one CTA per SM
+        const unsigned n_clusters = (unsigned)std::max<long long>(1, std::min<long long>(ctx->sm_count / cl, units)); // persistent: one CTA per SM
         if (ch == 0) prof_mark(ctx, 5);
         const bool precise = tc32_precise(ctx);
-#define SVGDB_PHI2_CASE(P)                                                                                                            \
-    case P:                                                                                                                           \
-        if (precise) phi2_tc32_kernel<P, true><<<grid, P2_THREADS, P2Cfg<true>::SMEM, ctx->stream>>>(ctx->mapBD, ctx->mapV2, a);      \
-        else phi2_tc32_kernel<P, false><<<grid, P2_THREADS, P2Cfg<false>::SMEM, ctx->stream>>>(ctx->mapB2, ctx->mapV2, a);            \
+        {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(n_clusters * cl);
+            cfg.blockDim = dim3(P2_THREADS);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = (unsigned)cl;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+#define SVGDB_P2_LAUNCH(P, PR, CLV)                                                                                   \
+    do {                                                                                                              \
+        cfg.dynamicSmemBytes = P2Cfg<PR>::SMEM;                                                                       \
+        CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, PR, CLV>, PR ? ctx->mapBD : ctx->mapB2, ctx->mapV2, a));        \
+    } while (0)
+#define SVGDB_PHI2_CASE(P)                                                                                            \
+    case P:                                                                                                           \
+        if (precise) { if (cl == 2) SVGDB_P2_LAUNCH(P, true, 2); else SVGDB_P2_LAUNCH(P, true, 1); }                  \
+        else { if (cl == 2) SVGDB_P2_LAUNCH(P, false, 2); else SVGDB_P2_LAUNCH(P, false, 1); }                        \
         break;
-        switch (ctx->phi_poly) {
-            SVGDB_PHI2_CASE(0)
-            SVGDB_PHI2_CASE(4)
-        default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 or 4");
-        }
+            switch (ctx->phi_poly) {
+                SVGDB_PHI2_CASE(0)
+                SVGDB_PHI2_CASE(4)
+            default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 or 4");
+            }
 #undef SVGDB_PHI2_CASE
+#undef SVGDB_P2_LAUNCH
+        }
         KERNEL_CHECK();
         if (ch == n_chunks - 1) prof_mark(ctx, 6);
         if (ch == 0 && ctx->tc_trace) {
@@ -1742,8 +1764,10 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
 #undef SVGDB_WIDE_ATTR
         }
 #define SVGDB_PHI2_ATTR(P)                                                                                                                        \
-    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
-    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));   \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));
         SVGDB_PHI2_ATTR(0)
         SVGDB_PHI2_ATTR(4)
 #undef SVGDB_PHI2_ATTR
