@@ -6,7 +6,7 @@ NG=${1:-2}; shift || true
 OUT=gpurun_out/multi$NG; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
 if [ "${SKIP_CHECK:-0}" != "1" ]; then
-  for prec in tc32 f64; do
+  for prec in ${CHECK_PRECS:-tc32 f64}; do
     timeout 600 $TR --master-port 29540 tests/multi_gpu_check.py --precision $prec > $OUT/check_$prec.log 2>&1; echo "check $prec exit $?" | tee -a $OUT/check_$prec.log
     grep -E "world=" $OUT/check_$prec.log | tail -8
   done
