@@ -9,8 +9,10 @@
 #define SVGDCPP_B200_SVGD_HPP
 
 #include <cmath>
+#include <exception>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 #include "Core.hpp"
 #include "Kernel/Kernel.hpp"
@@ -32,6 +34,10 @@ struct SVGDOptions {
     int Device = 0;                                  /* CUDA device ordinal */
     int PrecisionMode = SVGDB_PRECISION_F64;         /* svgdb_precision */
     int Tc32Variant = SVGDB_TC32_AUTO;               /* svgdb_tc32_variant: arithmetic of the tensor-core pair kernel (TC32 mode only) */
+    /* GPUs to shard the particle rows over (row blocks, NCCL all-gathers over NVLink; DESIGN.md "Multi-GPU").  Empty: `Device`
+     * alone -- or, with `Parallel` set (the reference's "use what the machine has", SVGD.hpp:49, 239-249), every visible GPU.
+     * More than one GPU: every call runs one host thread per GPU for its duration; the coordinate matrix stays one host matrix. */
+    std::vector<int> Devices;
     SVGDOptions() {}
 };
 
@@ -39,10 +45,7 @@ class SVGD {
 public:
     SVGD(const SVGDOptions &o)
         : SVGD(o.Dimension, o.NumIterations, o.CoordinateMatrixPtr, o.KernelPtr, o.ModelPtr, o.OptimizerPtr, o.LowerBound, o.UpperBound,
-               o.Parallel, o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath, o.Device, o.PrecisionMode)
-    {
-        Check(svgdb_set_tc32_variant(ctx_, o.Tc32Variant));
-    }
+               o.Parallel, o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath, o.Device, o.PrecisionMode, o.Devices, o.Tc32Variant) {}
 
     SVGD(const size_t &dim, const size_t &iter, const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const std::shared_ptr<Kernel> &kernel_ptr,
          const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const bool &parallel = false)
@@ -52,7 +55,8 @@ public:
     SVGD(const size_t &dim, const size_t &iter, const std::shared_ptr<Eigen::MatrixXd> &coord_mat_ptr, const std::shared_ptr<Kernel> &kernel_ptr,
          const std::shared_ptr<Model> &model_ptr, const std::shared_ptr<Optimizer> &optimizer_ptr, const Eigen::VectorXd &bound_lower,
          const Eigen::VectorXd &bound_upper, const bool &parallel = false, const bool &log_intermediate_matrices = false,
-         const std::string &intermediate_matrices_output_path = "log.txt", int device = 0, int precision_mode = SVGDB_PRECISION_F64)
+         const std::string &intermediate_matrices_output_path = "log.txt", int device = 0, int precision_mode = SVGDB_PRECISION_F64,
+         const std::vector<int> &devices = {}, int tc32_variant = SVGDB_TC32_AUTO)
         : num_iterations_(iter), parallel_(parallel), log_intermediate_matrices_(log_intermediate_matrices),
           intermediate_matrices_output_path_(intermediate_matrices_output_path)
     {
@@ -79,57 +83,76 @@ public:
         if (model_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Model object pointer.");
         if (optimizer_ptr_ == nullptr) throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] Invalid Optimizer object pointer.");
 
-        int rc = svgdb_create(&ctx_, device, static_cast<int64_t>(coord_matrix_ptr_->cols()), dimension_, precision_mode);
-        if (rc != SVGDB_OK) {
-            std::string msg = ctx_ ? svgdb_last_error(ctx_) : "svgdb_create failed";
-            svgdb_destroy(ctx_);
-            ctx_ = nullptr;
-            svgdcpp_b200::ThrowOnError(rc, msg.c_str());
+        /* which GPUs */
+        devices_ = devices;
+        if (devices_.empty()) {
+            int visible = 0;
+            if (parallel_ && svgdb_device_count(&visible) == SVGDB_OK && visible > 1)
+                for (int k = 0; k < visible; ++k) devices_.push_back(k);
+            else
+                devices_.push_back(device);
+        }
+        if (static_cast<int64_t>(devices_.size()) > coord_matrix_ptr_->cols()) devices_.resize(static_cast<size_t>(coord_matrix_ptr_->cols()));
+        if (model_ptr_->Dimension() != dimension_) throw DimensionMismatchException("Model dimension does not match the particle coordinate matrix.");
+        const int world = static_cast<int>(devices_.size());
+        ctxs_.assign(static_cast<size_t>(world), nullptr);
+        unsigned char nccl_id[128] = {0};
+        if (world > 1) svgdcpp_b200::ThrowOnError(svgdb_nccl_unique_id(nccl_id, sizeof(nccl_id)), "NCCL is not available for a multi-GPU run");
+        std::vector<double> lb(dimension_), ub(dimension_);
+        if (check_bounds_) {
+            // a 1-row bound is replicated over every coordinate (reference replicate(1, n), :203,215)
+            const int nb_l = static_cast<int>(bound_lower.rows()), nb_u = static_cast<int>(bound_upper.rows());
+            for (int k = 0; k < dimension_; ++k) { lb[k] = bound_lower(nb_l == 1 ? 0 : k); ub[k] = bound_upper(nb_u == 1 ? 0 : k); }
         }
         try {
-            if (check_bounds_) {
-                // a 1-row bound is replicated over every coordinate (reference replicate(1, n), :203,215)
-                const int nb_l = static_cast<int>(bound_lower.rows()), nb_u = static_cast<int>(bound_upper.rows());
-                std::vector<double> lb(dimension_), ub(dimension_);
-                for (int k = 0; k < dimension_; ++k) { lb[k] = bound_lower(nb_l == 1 ? 0 : k); ub[k] = bound_upper(nb_u == 1 ? 0 : k); }
-                Check(svgdb_set_bounds(ctx_, lb.data(), ub.data(), dimension_));
-            }
-            if (model_ptr_->Dimension() != dimension_) throw DimensionMismatchException("Model dimension does not match the particle coordinate matrix.");
-            model_ptr_->Upload(ctx_);
-            kernel_ptr_->Upload(ctx_);
-            optimizer_ptr_->Upload(ctx_);
+            OnEveryRank([&](int r) {
+                svgdb_ctx *&c = ctxs_[static_cast<size_t>(r)];
+                int rc = svgdb_create(&c, devices_[static_cast<size_t>(r)], static_cast<int64_t>(coord_matrix_ptr_->cols()), dimension_, precision_mode);
+                if (rc != SVGDB_OK) svgdcpp_b200::ThrowOnError(rc, c ? svgdb_last_error(c) : "svgdb_create failed");
+                if (world > 1) CheckOn(c, svgdb_comm_init(c, world, r, nccl_id, sizeof(nccl_id)));
+                CheckOn(c, svgdb_set_tc32_variant(c, tc32_variant));
+                if (check_bounds_) CheckOn(c, svgdb_set_bounds(c, lb.data(), ub.data(), dimension_));
+                model_ptr_->Upload(c);
+                kernel_ptr_->Upload(c);
+                optimizer_ptr_->Upload(c);
+            });
         } catch (...) {
-            svgdb_destroy(ctx_);
-            ctx_ = nullptr;
+            for (svgdb_ctx *c : ctxs_) svgdb_destroy(c);
+            ctxs_.clear();
             throw;
         }
-        if (parallel_) std::cout << SVGDCPP_LOG_PREFIX << "device path: all particle pairs run in parallel on the GPU." << std::endl;
+        ctx_ = ctxs_[0];
+        if (parallel_)
+            std::cout << SVGDCPP_LOG_PREFIX << "device path: all particle pairs run in parallel on " << world << " GPU" << (world > 1 ? "s." : ".") << std::endl;
     }
 
     SVGD(const SVGD &) = delete;
     SVGD &operator=(const SVGD &) = delete;
-    ~SVGD() { svgdb_destroy(ctx_); }
+    ~SVGD()
+    {
+        for (svgdb_ctx *c : ctxs_) svgdb_destroy(c);
+    }
 
     void Initialize()
     {
         model_ptr_->Initialize();
         kernel_ptr_->Initialize();
         optimizer_ptr_->Initialize();
-        Check(svgdb_initialize(ctx_));
+        for (svgdb_ctx *c : ctxs_) CheckOn(c, svgdb_initialize(c));
     }
 
     void UpdateKernelParameters(const std::vector<Eigen::MatrixXd> &params)
     {
         kernel_ptr_->UpdateParameters(params);
         kernel_ptr_->Initialize();
-        kernel_ptr_->Upload(ctx_);
+        for (svgdb_ctx *c : ctxs_) kernel_ptr_->Upload(c);
     }
 
     void UpdateModelParameters(const std::vector<Eigen::MatrixXd> &params)
     {
         model_ptr_->UpdateParameters(params);
         model_ptr_->Initialize();
-        model_ptr_->Upload(ctx_);
+        for (svgdb_ctx *c : ctxs_) model_ptr_->Upload(c);
     }
 
     void Run()
@@ -138,6 +161,8 @@ public:
             Step(num_iterations_);
             return;
         }
+        if (ctxs_.size() > 1)
+            throw std::invalid_argument(SVGDCPP_LOG_PREFIX + "[Argument Error] LogIntermediateMatrices is an inspection path for one GPU.");
         /* Reference Run() with LogIntermediateMatrices (:338-366): after every step, the gradient / kernel / kernel-gradient matrices
          * that step used and the updated coordinates, in Eigen's default text format.  The device step never forms the n x n
          * matrices, so they are computed on demand from the pre-step particles (svgdb_compute_kernel_matrices; small n only). */
@@ -164,23 +189,63 @@ public:
     {
         model_ptr_->Step();
         if (iters == 0) return;
-        /* upload, iterate, download; the download of the last iteration overlaps its pair kernel (svgdb_step_host) */
-        Check(svgdb_step_host(ctx_, coord_matrix_ptr_->data(), coord_matrix_ptr_->data(), static_cast<int64_t>(iters)));
+        /* upload, iterate, download; the download of the last iteration overlaps its pair kernel (svgdb_step_host).  Several GPUs:
+         * every rank moves its own block of rows of the (particle-contiguous) coordinate matrix, the rest travels over NVLink. */
+        double *x = coord_matrix_ptr_->data();
+        OnEveryRank([&](int r) {
+            svgdb_ctx *c = ctxs_[static_cast<size_t>(r)];
+            int64_t row0 = 0, n_rows = 0;
+            CheckOn(c, svgdb_local_rows(c, &row0, &n_rows));
+            double *mine = x + row0 * dimension_;
+            CheckOn(c, svgdb_step_host(c, mine, mine, static_cast<int64_t>(iters)));
+        });
     }
 
     /* ComputePhi of the reference (:407-454) for inspection: phi is dim x n. */
     Eigen::MatrixXd ComputePhi(double *scale_out = nullptr)
     {
         Eigen::MatrixXd phi(dimension_, coord_matrix_ptr_->cols());
-        Check(svgdb_set_particles(ctx_, coord_matrix_ptr_->data()));
-        Check(svgdb_compute_phi(ctx_, phi.data(), scale_out));
+        std::vector<Eigen::MatrixXd> others(ctxs_.size() > 1 ? ctxs_.size() - 1 : 0, Eigen::MatrixXd(dimension_, coord_matrix_ptr_->cols()));
+        OnEveryRank([&](int r) { // every rank takes part in the collectives and receives the whole phi
+            svgdb_ctx *c = ctxs_[static_cast<size_t>(r)];
+            CheckOn(c, svgdb_set_particles(c, coord_matrix_ptr_->data()));
+            CheckOn(c, svgdb_compute_phi(c, r == 0 ? phi.data() : others[static_cast<size_t>(r - 1)].data(), r == 0 ? scale_out : nullptr));
+        });
         return phi;
     }
+
+    int NumDevices() const { return static_cast<int>(ctxs_.size()); }
 
     svgdb_ctx *Context() { return ctx_; }
 
 protected:
     void Check(int rc) { svgdcpp_b200::ThrowOnError(rc, svgdb_last_error(ctx_)); }
+    static void CheckOn(svgdb_ctx *c, int rc) { svgdcpp_b200::ThrowOnError(rc, svgdb_last_error(c)); }
+
+    /* Runs f(rank) for every GPU of this object: in place for one GPU, on one host thread per GPU otherwise (the library's
+     * collectives need all ranks inside the call at the same time).  The first exception is rethrown on the caller's thread. */
+    template <class F>
+    void OnEveryRank(F f)
+    {
+        const int world = static_cast<int>(ctxs_.size());
+        if (world <= 1) {
+            f(0);
+            return;
+        }
+        std::vector<std::exception_ptr> errors(static_cast<size_t>(world));
+        std::vector<std::thread> threads;
+        for (int r = 0; r < world; ++r)
+            threads.emplace_back([&, r]() {
+                try {
+                    f(r);
+                } catch (...) {
+                    errors[static_cast<size_t>(r)] = std::current_exception();
+                }
+            });
+        for (std::thread &t : threads) t.join();
+        for (const std::exception_ptr &e : errors)
+            if (e) std::rethrow_exception(e);
+    }
 
     int dimension_ = -1;
     size_t num_iterations_;
@@ -192,6 +257,8 @@ protected:
     std::shared_ptr<Model> model_ptr_;
     std::shared_ptr<Optimizer> optimizer_ptr_;
     std::shared_ptr<Eigen::MatrixXd> coord_matrix_ptr_;
-    svgdb_ctx *ctx_ = nullptr;
+    svgdb_ctx *ctx_ = nullptr;          /* rank 0 (the only one with a single GPU) */
+    std::vector<svgdb_ctx *> ctxs_;     /* one context per GPU */
+    std::vector<int> devices_;
 };
 #endif

@@ -15,8 +15,10 @@
  *   - Every call returns SVGDB_OK (0) or a negative svgdb_status; nothing throws across the
  *     ABI.  svgdb_last_error() gives the message of the last failure on that context.
  *   - A context is driven by one host thread (like the non-copyable reference SVGD object,
- *     SVGD.hpp:256).  One context drives one GPU; multi-GPU = one process (or context) per GPU
- *     joined by svgdb_comm_init (particle rows are sharded, see DESIGN.md "Multi-GPU").
+ *     SVGD.hpp:256).  One context drives one GPU; multi-GPU = one context per GPU -- in one process
+ *     each (torch.distributed.run style) or in one process with one host thread per context (what the
+ *     facade's SVGDOptions::Devices does) -- joined by svgdb_comm_init (particle rows are sharded, see
+ *     DESIGN.md "Multi-GPU").  Every entry point selects its context's device itself.
  *   - There is no CPU fallback: without a CUDA device svgdb_create fails with SVGDB_ERR_CUDA.
  */
 #ifndef SVGD_B200_H
@@ -88,6 +90,9 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
 void svgdb_destroy(svgdb_ctx *ctx);
 const char *svgdb_last_error(const svgdb_ctx *ctx);
 const char *svgdb_version(void);
+
+/* Number of visible CUDA devices (what the facade's `Parallel` flag spreads a run over). */
+int svgdb_device_count(int *count);
 
 /* Use the caller's CUDA stream (a cudaStream_t) for all work; NULL restores the ctx's own. */
 int svgdb_set_stream(svgdb_ctx *ctx, void *cuda_stream);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "svgdb_destroy": (None, [_ctx]),
     "svgdb_last_error": (C.c_char_p, [_ctx]),
     "svgdb_version": (C.c_char_p, []),
+    "svgdb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "svgdb_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "svgdb_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "svgdb_comm_init": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),

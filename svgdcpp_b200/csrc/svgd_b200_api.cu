@@ -1812,6 +1812,7 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
 void svgdb_destroy(svgdb_ctx *ctx)
 {
     if (!ctx) return;
+    cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -1834,9 +1835,23 @@ void svgdb_destroy(svgdb_ctx *ctx)
     delete ctx;
 }
 
+int svgdb_device_count(int *count)
+{
+    if (!count) return SVGDB_ERR_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return SVGDB_ERR_CUDA;
+    }
+    *count = n;
+    return SVGDB_OK;
+}
+
 int svgdb_set_stream(svgdb_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return SVGDB_OK;
@@ -1856,6 +1871,7 @@ int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique
     if (!ctx) return SVGDB_ERR_INVALID;
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SVGDB_ERR_INVALID, "bad world/rank");
     if (world > ctx->N) return fail(ctx, SVGDB_ERR_DIMENSION, "more ranks than particles");
+    CU(cudaSetDevice(ctx->device));
     if (ctx->comm) { nccl().CommDestroy(ctx->comm); ctx->comm = nullptr; }
     if (world > 1) {
         if (!nccl().ok) return fail(ctx, SVGDB_ERR_NCCL, nccl().why);
@@ -1876,6 +1892,7 @@ int svgdb_comm_init(svgdb_ctx *ctx, int world, int rank, const void *nccl_unique
 int svgdb_set_particles(svgdb_ctx *ctx, const double *X)
 {
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
+    CU(cudaSetDevice(ctx->device)); // one process may drive several contexts (one per GPU): every entry point selects its own
     CU(cudaMemcpyAsync(ctx->X[ctx->cur], X, (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     // the caller may reuse or free X as soon as this returns, also when X is pinned memory (svgdb_host_alloc)
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1886,6 +1903,7 @@ int svgdb_set_particles(svgdb_ctx *ctx, const double *X)
 int svgdb_get_particles(svgdb_ctx *ctx, double *X)
 {
     if (!ctx || !X) return fail(ctx, SVGDB_ERR_INVALID, "null particle matrix");
+    CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(X, ctx->X[ctx->cur], (size_t)ctx->N * ctx->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
 #ifdef SVGDB_WITH_TC32
@@ -1920,6 +1938,7 @@ extern "C" {
 int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local)
 {
     if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    CU(cudaSetDevice(ctx->device));
     TRY(set_particles_rows_async(ctx, rows_local));
     CU(cudaStreamSynchronize(ctx->stream)); // rows_local may be reused or freed on return
     return SVGDB_OK;
@@ -1928,6 +1947,7 @@ int svgdb_set_particles_rows(svgdb_ctx *ctx, const double *rows_local)
 int svgdb_get_particles_rows(svgdb_ctx *ctx, double *rows_local)
 {
     if (!ctx || (!rows_local && ctx->n_rows > 0)) return fail(ctx, SVGDB_ERR_INVALID, "null particle rows");
+    CU(cudaSetDevice(ctx->device));
     if (ctx->n_rows > 0)
         CU(cudaMemcpyAsync(rows_local, ctx->X[ctx->cur] + (size_t)ctx->row0 * ctx->d, (size_t)ctx->n_rows * ctx->d * sizeof(double),
                            cudaMemcpyDeviceToHost, ctx->stream));
@@ -1942,6 +1962,7 @@ int svgdb_set_model_mvn_sum(svgdb_ctx *ctx, int32_t C, const double *means, cons
 {
     if (!ctx || !means || !covs) return fail(ctx, SVGDB_ERR_INVALID, "null model parameters");
     if (C < 1) return fail(ctx, SVGDB_ERR_INVALID, "a mixture needs at least one component");
+    CU(cudaSetDevice(ctx->device));
     const int d = ctx->d;
     std::vector<double> prec((size_t)C * d * d), inv;
     for (int c = 0; c < C; ++c) {
@@ -2024,6 +2045,7 @@ int svgdb_set_optimizer(svgdb_ctx *ctx, int kind, double lr, double beta1, doubl
 int svgdb_set_bounds(svgdb_ctx *ctx, const double *lb, const double *ub, int32_t n_bound)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     cudaFree(ctx->lb); cudaFree(ctx->ub);
     ctx->lb = ctx->ub = nullptr;
     if (!lb && !ub) return SVGDB_OK;
@@ -2042,6 +2064,7 @@ int svgdb_set_bounds(svgdb_ctx *ctx, const double *lb, const double *ub, int32_t
 int svgdb_initialize(svgdb_ctx *ctx)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     TRY(check_ready(ctx));
     if (!ctx->opt_set) return fail(ctx, SVGDB_ERR_UNSET, "Optimizer is unset.");
     size_t local = (size_t)ctx->rows_per_rank * ctx->d * sizeof(double);
@@ -2200,6 +2223,7 @@ int svgdb_compute_scale(svgdb_ctx *ctx, double *scale_out)
 int svgdb_get_scale_matrix(svgdb_ctx *ctx, double *A_dxd)
 {
     if (!ctx || !A_dxd) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     if (ctx->scale_method != SVGDB_SCALE_HESSIAN) {
         TRY(finish_median(ctx));
         const double a = ctx->scale_method == SVGDB_SCALE_FIXED ? ctx->fixed_a : ctx->stats.last_scale;
@@ -2287,6 +2311,7 @@ int svgdb_compute_kernel_matrices(svgdb_ctx *ctx, double *K, double *gradK, doub
 int svgdb_get_opt_state(svgdb_ctx *ctx, double *s1, double *s2, uint64_t *counter)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     // optimizer state is row-sharded; gather through V's storage one array at a time
     double *src[2] = {ctx->s1, ctx->s2};
     double *dst[2] = {s1, s2};
@@ -2306,6 +2331,7 @@ int svgdb_get_opt_state(svgdb_ctx *ctx, double *s1, double *s2, uint64_t *counte
 int svgdb_set_opt_state(svgdb_ctx *ctx, const double *s1, const double *s2, uint64_t counter)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     size_t bytes = (size_t)std::max<int64_t>(ctx->n_rows, 0) * ctx->d * sizeof(double);
     if (s1 && bytes) CU(cudaMemcpyAsync(ctx->s1, s1 + (size_t)ctx->row0 * ctx->d, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (s2 && bytes) CU(cudaMemcpyAsync(ctx->s2, s2 + (size_t)ctx->row0 * ctx->d, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -2317,6 +2343,7 @@ int svgdb_set_opt_state(svgdb_ctx *ctx, const double *s1, const double *s2, uint
 int svgdb_sync(svgdb_ctx *ctx)
 {
     if (!ctx) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     TRY(finish_median(ctx));
 #ifdef SVGDB_WITH_TC32
@@ -2335,6 +2362,7 @@ int svgdb_set_profiling(svgdb_ctx *ctx, int enabled)
 int svgdb_get_stats(svgdb_ctx *ctx, svgdb_stats *out)
 {
     if (!ctx || !out) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     TRY(finish_median(ctx)); // stats.last_scale
     *out = ctx->stats;
     return SVGDB_OK;
@@ -2352,6 +2380,7 @@ int svgdb_reset_stats(svgdb_ctx *ctx)
 int svgdb_time_steps(svgdb_ctx *ctx, int64_t iters, float *ms_out)
 {
     if (!ctx || !ms_out) return SVGDB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));

@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import math
+import threading
 
 import numpy as np
 
@@ -286,6 +287,7 @@ class SVGDOptions:  # SVGD.hpp:27-52 (+ device / precision / sharding fields wit
         self.Device = 0
         self.Precision = _capi.PRECISION_F64
         self.Tc32Variant = _capi.TC32_AUTO
+        self.Devices = []   # GPUs to shard the particle rows over; empty: Device alone, or every visible GPU with Parallel set
 
 
 class SVGD:
@@ -294,14 +296,15 @@ class SVGD:
 
     def __init__(self, dim, iter=None, coord_mat=None, kernel=None, model=None, optimizer=None,
                  bound_lower=None, bound_upper=None, parallel=False, log_intermediate_matrices=False,
-                 intermediate_matrices_output_path="log.txt", device=0, precision=_capi.PRECISION_F64, tc32_variant=_capi.TC32_AUTO):
+                 intermediate_matrices_output_path="log.txt", device=0, precision=_capi.PRECISION_F64, tc32_variant=_capi.TC32_AUTO,
+                 devices=None):
         if isinstance(dim, SVGDOptions):
             o = dim
             dim, iter, coord_mat, kernel, model, optimizer = (o.Dimension, o.NumIterations, o.CoordinateMatrixPtr,
                                                               o.KernelPtr, o.ModelPtr, o.OptimizerPtr)
             bound_lower, bound_upper, parallel = o.LowerBound, o.UpperBound, o.Parallel
             log_intermediate_matrices, intermediate_matrices_output_path = o.LogIntermediateMatrices, o.IntermediateMatricesOutputPath
-            device, precision, tc32_variant = o.Device, o.Precision, o.Tc32Variant
+            device, precision, tc32_variant, devices = o.Device, o.Precision, o.Tc32Variant, list(o.Devices)
         self._lib = _capi.load()
         self._ctx = C.c_void_p()
         if coord_mat is None:
@@ -331,17 +334,49 @@ class SVGD:
         self.intermediate_matrices_output_path_ = intermediate_matrices_output_path
         self.kernel_, self.model_, self.optimizer_ = kernel, model, optimizer
 
-        rc = self._lib.svgdb_create(C.byref(self._ctx), int(device), self.num_particles_, self.dimension_, int(precision))
-        self._check(rc)
-        self._check(self._lib.svgdb_set_tc32_variant(self._ctx, int(tc32_variant)))
+        # which GPUs: `devices`, else `device` alone -- or every visible GPU when the reference's `parallel` flag is set (SVGD.hpp:49, 239-249)
+        devs = [int(x) for x in devices] if devices else []
+        if not devs:
+            cnt = C.c_int(0)
+            if self.parallel_ and self._lib.svgdb_device_count(C.byref(cnt)) == _capi.OK and cnt.value > 1:
+                devs = list(range(cnt.value))
+            else:
+                devs = [int(device)]
+        devs = devs[:max(1, self.num_particles_)]
+        world = len(devs)
+        self._ctxs = [C.c_void_p() for _ in devs]
+        self._ctx = self._ctxs[0]
+        uid = (C.c_ubyte * 128)()
+        if world > 1 and self._lib.svgdb_nccl_unique_id(C.cast(uid, C.c_void_p), 128) != _capi.OK:
+            raise RuntimeError("SVGDCpp: [Runtime Error] NCCL is not available for a multi-GPU run")
+        lbf = ubf = None
         if self.check_bounds_:
             lbf = np.ascontiguousarray(np.broadcast_to(lb, (self.dimension_,)) if lb.size == 1 else lb)
             ubf = np.ascontiguousarray(np.broadcast_to(ub, (self.dimension_,)) if ub.size == 1 else ub)
-            self._check(self._lib.svgdb_set_bounds(self._ctx, _ptr(lbf), _ptr(ubf), self.dimension_))
-        self._push_model()
-        self._push_kernel()
         o = optimizer
-        self._check(self._lib.svgdb_set_optimizer(self._ctx, o.kind, o.learning_rate_, o.decay_rate_1_, o.decay_rate_2_, o.stabilizer_))
+
+        def setup(r):
+            ctx = self._ctxs[r]
+            rc = self._lib.svgdb_create(C.byref(ctx), devs[r], self.num_particles_, self.dimension_, int(precision))
+            self._check_on(ctx, rc)
+            if world > 1:
+                self._check_on(ctx, self._lib.svgdb_comm_init(ctx, world, r, C.cast(uid, C.c_void_p), 128))
+            self._check_on(ctx, self._lib.svgdb_set_tc32_variant(ctx, int(tc32_variant)))
+            if self.check_bounds_:
+                self._check_on(ctx, self._lib.svgdb_set_bounds(ctx, _ptr(lbf), _ptr(ubf), self.dimension_))
+            self._push_model(ctx)
+            self._push_kernel(ctx)
+            self._check_on(ctx, self._lib.svgdb_set_optimizer(ctx, o.kind, o.learning_rate_, o.decay_rate_1_, o.decay_rate_2_, o.stabilizer_))
+
+        try:
+            self._on_every_rank(setup)
+        except Exception:
+            for ctx in self._ctxs:
+                if ctx:
+                    self._lib.svgdb_destroy(ctx)
+            self._ctxs = []
+            self._ctx = C.c_void_p()
+            raise
         # pinned staging buffer (particle-major): the device-to-host copy of a step overlaps its pair kernel only from pinned memory
         self._hp = C.c_void_p()
         count = self.num_particles_ * self.dimension_
@@ -353,17 +388,47 @@ class SVGD:
     # -- plumbing ------------------------------------------------------------------------------
     def _check(self, rc):
         if rc != _capi.OK:
-            try:
-                _raise_for(rc, self._ctx)
-            finally:
-                pass
+            _raise_for(rc, self._ctx)
 
-    def _push_model(self):
+    @staticmethod
+    def _check_on(ctx, rc):
+        if rc != _capi.OK:
+            _raise_for(rc, ctx)
+
+    def _on_every_rank(self, fn):
+        """fn(rank) for every GPU of this object: in place for one, on one host thread per GPU otherwise (the library's collectives
+        need all ranks inside the call at once; ctypes releases the GIL during the calls).  The first exception is re-raised here."""
+        world = len(self._ctxs)
+        if world <= 1:
+            fn(0)
+            return
+        errors = [None] * world
+
+        def run(r):
+            try:
+                fn(r)
+            except BaseException as e:  # noqa: BLE001 - re-raised below
+                errors[r] = e
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+
+    def _push_model(self, ctx=None):
+        if ctx is None:
+            for c in self._ctxs:
+                self._push_model(c)
+            return
         m = self.model_
         if m._hook is not None:
             fn, user = m._hook
             self._hook_keepalive = fn
-            self._check(self._lib.svgdb_set_model_device_hook(self._ctx, C.cast(fn, C.c_void_p), user))
+            self._check_on(ctx, self._lib.svgdb_set_model_device_hook(ctx, C.cast(fn, C.c_void_p), user))
             return
         if not m._components:
             raise UnsetException("Model function is unset.")
@@ -371,26 +436,35 @@ class SVGD:
         covs = np.ascontiguousarray(np.stack([c[1] for c in m._components]))           # C x d x d
         if means.shape[1] != self.dimension_:
             raise DimensionMismatchException("Model dimension does not match the particle coordinate matrix.")
-        self._check(self._lib.svgdb_set_model_mvn_sum(self._ctx, means.shape[0], _ptr(means), _ptr(covs)))
+        self._check_on(ctx, self._lib.svgdb_set_model_mvn_sum(ctx, means.shape[0], _ptr(means), _ptr(covs)))
 
-    def _push_kernel(self):
+    def _push_kernel(self, ctx=None):
+        if ctx is None:
+            for c in self._ctxs:
+                self._push_kernel(c)
+            return
         k = self.kernel_
         if k.dimension_ != self.dimension_:
             raise DimensionMismatchException("Kernel dimension does not match the particle coordinate matrix.")
-        self._check(self._lib.svgdb_set_kernel_rbf(self._ctx, int(k.scale_method_), k.fixed_scale_))
+        self._check_on(ctx, self._lib.svgdb_set_kernel_rbf(ctx, int(k.scale_method_), k.fixed_scale_))
 
     def _upload(self):
         self._host[...] = np.asarray(self.coord_matrix_, dtype=np.float64).T
-        self._check(self._lib.svgdb_set_particles(self._ctx, _ptr(self._host)))
+        for ctx in self._ctxs:
+            self._check_on(ctx, self._lib.svgdb_set_particles(ctx, _ptr(self._host)))
 
     def _download(self):
         self._check(self._lib.svgdb_get_particles(self._ctx, _ptr(self._host)))
         self.coord_matrix_[...] = self._host.T
 
+    def NumDevices(self):
+        return len(self._ctxs)
+
     # -- reference API ---------------------------------------------------------------------------
     def Initialize(self):  # SVGD.hpp:268-296
         self.model_.Initialize()
-        self._check(self._lib.svgdb_initialize(self._ctx))
+        for ctx in self._ctxs:
+            self._check_on(ctx, self._lib.svgdb_initialize(ctx))
 
     def UpdateKernelParameters(self, params):  # SVGD.hpp:304-321: params[0] = A (= a I for the constant scale)
         self.kernel_.UpdateParameters(params)
@@ -404,13 +478,23 @@ class SVGD:
         if int(iters) < 1:
             return
         self._host[...] = np.asarray(self.coord_matrix_, dtype=np.float64).T
-        self._check(self._lib.svgdb_step_host(self._ctx, _ptr(self._host), _ptr(self._host), int(iters)))
+
+        def step(r):  # every rank moves its own block of rows of the staging buffer; the rest travels over NVLink
+            ctx = self._ctxs[r]
+            r0, nr = C.c_int64(0), C.c_int64(0)
+            self._check_on(ctx, self._lib.svgdb_local_rows(ctx, C.byref(r0), C.byref(nr)))
+            mine = self._host[r0.value:r0.value + nr.value]
+            self._check_on(ctx, self._lib.svgdb_step_host(ctx, _ptr(mine), _ptr(mine), int(iters)))
+
+        self._on_every_rank(step)
         self.coord_matrix_[...] = self._host.T
 
     def Run(self):  # SVGD.hpp:338-366
         if not self.log_intermediate_matrices_:
             self.Step(self.num_iterations_)
             return
+        if len(self._ctxs) > 1:
+            raise ValueError("SVGDCpp: [Argument Error] LogIntermediateMatrices is an inspection path for one GPU.")
         # LogIntermediateMatrices: one step at a time, the matrices of that step formed on demand (inspection path, small n)
         chunks = []
         for it in range(self.num_iterations_):
@@ -439,10 +523,11 @@ class SVGD:
     def ComputePhi(self):
         """SVGD::ComputePhi (SVGD.hpp:407-454) on the current coordinates: (phi as dim x n, scale a)."""
         self._upload()
-        phi = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
-        a = C.c_double(0.0)
-        self._check(self._lib.svgdb_compute_phi(self._ctx, _ptr(phi), C.byref(a)))
-        return phi.T.copy(), a.value
+        world = len(self._ctxs)
+        phis = [np.empty((self.num_particles_, self.dimension_), dtype=np.float64) for _ in range(world)]
+        scales = [C.c_double(0.0) for _ in range(world)]
+        self._on_every_rank(lambda r: self._check_on(self._ctxs[r], self._lib.svgdb_compute_phi(self._ctxs[r], _ptr(phis[r]), C.byref(scales[r]))))
+        return phis[0].T.copy(), scales[0].value
 
     def GetScaleMatrix(self):
         """The kernel's inverse scale matrix (GaussianRBFKernel::GetParameters()[0]) of the last Step / Compute call."""
@@ -452,15 +537,15 @@ class SVGD:
 
     def ComputeScale(self):
         self._upload()
-        a = C.c_double(0.0)
-        self._check(self._lib.svgdb_compute_scale(self._ctx, C.byref(a)))
-        return a.value
+        scales = [C.c_double(0.0) for _ in self._ctxs]
+        self._on_every_rank(lambda r: self._check_on(self._ctxs[r], self._lib.svgdb_compute_scale(self._ctxs[r], C.byref(scales[r]))))
+        return scales[0].value
 
     def EvaluateLogModelGrad(self):
         self._upload()
-        G = np.empty((self.num_particles_, self.dimension_), dtype=np.float64)
-        self._check(self._lib.svgdb_compute_log_model_grad(self._ctx, _ptr(G)))
-        return G.T.copy()
+        Gs = [np.empty((self.num_particles_, self.dimension_), dtype=np.float64) for _ in self._ctxs]
+        self._on_every_rank(lambda r: self._check_on(self._ctxs[r], self._lib.svgdb_compute_log_model_grad(self._ctxs[r], _ptr(Gs[r]))))
+        return Gs[0].T.copy()
 
     def Stats(self):
         st = _capi.Stats()
@@ -471,8 +556,11 @@ class SVGD:
         return self._ctx
 
     def close(self):
-        if getattr(self, "_ctx", None) is not None and self._ctx:
-            self._lib.svgdb_destroy(self._ctx)
+        for ctx in getattr(self, "_ctxs", []):
+            if ctx:
+                self._lib.svgdb_destroy(ctx)
+        self._ctxs = []
+        if getattr(self, "_ctx", None) is not None:
             self._ctx = C.c_void_p()
         if getattr(self, "_hp", None) is not None and self._hp:
             self._host = None
