@@ -56,7 +56,7 @@ def test_facade_devices(tmp_path):
 
     devs = [str(k) for k in range(min(ranks, 4))]
     out = _build_and_run("multi_device", tmp_path, src_dir=os.path.join("tests", "cpp"), args=devs)
-    lines = out.strip().splitlines()
+    lines = [l for l in out.strip().splitlines() if not l.startswith("NCCL version")]  # (NCCL announces itself on stdout)
     dim, n, iters = 3, 700, 6
     assert lines[0] == "devices 1" and lines[dim + 1] == "devices %d" % len(devs)
     one = np.array([[float(t) for t in l.split()] for l in lines[1:dim + 1]])
