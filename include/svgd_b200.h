@@ -53,7 +53,7 @@ typedef enum { SVGDB_PRECISION_F64 = 0, SVGDB_PRECISION_TC32 = 1 } svgdb_precisi
 /* Arithmetic variant of the tensor-core pair kernel under SVGDB_PRECISION_TC32 (no reference counterpart; ignored in F64 mode).
  * FAST: column particle and kernel values carry one fp16 term each (phi within 2e-4 of max|phi|; the error terms are zero-mean
  * and average over a row's neighbours).  PRECISE: both particles and the kernel values carry two fp16 terms (1.5x the MMAs; phi
- * within 1e-5 of max|phi|).  AUTO (default): FAST for one Gaussian target with at least 16,384 particles, PRECISE otherwise
+ * within 1e-5 of max|phi|).  AUTO (default): FAST for one Gaussian target with at least 16,384 particles in d >= 8, PRECISE otherwise
  * (mixtures, gradient hooks, small particle sets). */
 typedef enum { SVGDB_TC32_AUTO = 0, SVGDB_TC32_FAST = 1, SVGDB_TC32_PRECISE = 2 } svgdb_tc32_variant;
 

@@ -10,6 +10,9 @@ def run(workload, variant, max_seg):
     if workload == "c3":
         n, d = 65536, 64
         x0, means, covs = synth.mvn_problem(n, d)
+    elif workload.startswith("mvn"):  # mvn<d>: the config-3 recipe at another dimension
+        n, d = 65536, int(workload[3:])
+        x0, means, covs = synth.mvn_problem(n, d)
     else:
         n, d = 65536, 256
         x0, means, covs = synth.gmm_problem(n, d, 16)
@@ -24,7 +27,9 @@ def run(workload, variant, max_seg):
     lib.svgdb_time_kernel(s._ctx, 1, 3, 0, 0.0, C.byref(ms))
     s.close()
     scale = np.max(np.abs(phi)); worst = 0.0
-    for i in np.random.default_rng(0).integers(0, n, 6):
+    Xc = X - X.mean(0)
+    rows = list(np.random.default_rng(0).integers(0, n, 6)) + [int(np.argmax(np.einsum("ij,ij->i", Xc, Xc)))]  # + the outermost particle
+    for i in rows:
         diff = X - X[i]; k = np.exp(-a * np.einsum("ij,ij->i", diff, diff))
         ref = (k @ G + (-2 * a * diff * k[:, None]).sum(0)) / n
         worst = max(worst, np.max(np.abs(phi[i] - ref)) / scale)

@@ -27,6 +27,7 @@
 //     flush of Phi happen ~3 times per SM instead of once per (i-pair, j-split) CTA.
 #pragma once
 #include "kernels_tc32.cuh"
+#include <cuda_fp8.h>
 #include <type_traits>
 
 namespace svgdb {
@@ -40,12 +41,18 @@ constexpr uint32_t P2_AEX_BYTES = 4096;               // per i-tile: 128 rows x 
 //   fast    : S = (hi_i + lo_i) . hi_j,  E = fp16(2^15 k),  Phi += E . (v_hi + v_lo)                  16 + 1 MMAs per 128 x 64 unit
 //   PRECISE : S = hi_i.hi_j + lo_i.hi_j + hi_i.lo_j (both particles 22 bits),  E = E_hi + E_lo (two fp16 terms),
 //             Phi += E_hi.v_hi + E_hi.v_lo + E_lo.v_hi                                                  24 + 1 MMAs per unit
-template <bool PRECISE>
+//   F8LO (FAST only): the two correction terms -- lo_i . y^_j of the first contraction and E . v_lo of the second, each 2^-11 of its
+//             main term -- run as kind::f8f6f4 on e5m2 copies (lo_i 2^10 and y^_j 2^-10; the top byte of the fp16 E and e5m2(v_lo)):
+//             13 MMAs per unit instead of 17; adds zero-mean noise of ~1e-4 relative per kernel value / 3e-5 per product.
+template <bool PRECISE, bool F8LO = false>
 struct P2Cfg {
-    static constexpr int STAGES = PRECISE ? 3 : 4;
+    static_assert(!(PRECISE && F8LO), "the fp8 term belongs to the FAST variant");
+    static constexpr int STAGES = (PRECISE || F8LO) ? 3 : 4;
     static constexpr uint32_t XB_BYTES = PRECISE ? 32768u : 16384u; // 128 particles x 64 fp16 hi (+ 64 fp16 lo): 128 B rows, SWIZZLE_128B boxes
-    static constexpr uint32_t STAGE = XB_BYTES + P2_V_BYTES + P2_W_BYTES; // 52 KB / 68 KB (1024-aligned)
-    static constexpr uint32_t TX = STAGE;
+    static constexpr uint32_t X8_BYTES = F8LO ? 8192u : 0u;         // 128 particles x 64 e5m2: 64 B rows, SWIZZLE_64B
+    static constexpr uint32_t V8_BYTES = F8LO ? 8192u : 0u;         // v_lo as e5m2: two boxes (j-halves) of 64 coordinates x 64 particles
+    static constexpr uint32_t STAGE = XB_BYTES + P2_V_BYTES + P2_W_BYTES + X8_BYTES + V8_BYTES; // 52 KB / 68 KB / 68 KB (1024-aligned)
+    static constexpr uint32_t TX = F8LO ? STAGE - 2 * P2_VBOX : STAGE; // (the fp16 v_lo boxes are not fetched in the F8LO variant)
     static constexpr uint32_t SMEM = STAGES * STAGE + 2 * P2_AEX_BYTES + 256 + 1024;
 };
 // K-major operand of 16 fp16 columns WITHOUT swizzle: 8 x 16 B core matrices; row r, column k lives at
@@ -75,9 +82,11 @@ __device__ __forceinline__ void split3_f16(double v, __half &t0, __half &t1, __h
 // so that the accumulator of the first contraction IS the exponent.  WB is stored per 128-particle tile in the
 // core-matrix order the MMA reads (p2_ex_offset), UA as plain rows.
 // precise != 0: the column operand keeps both terms, XB2[row] = [hi | lo] (128 columns per row), and w = -|hi + lo|^2/2.
+// XB8 != nullptr (F8LO): additionally the e5m2 copies -- XA2[row] bytes [128, 192) = e5m2(lo 2^10), XB8[row] = e5m2(hi 2^-10).
 __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__restrict__ colsum, const double *__restrict__ a_ptr,
                                   int64_t n, int64_t n_rows_a, int64_t n_rows_b, int d, __half *__restrict__ XA2,
-                                  __half *__restrict__ XB2, __half *__restrict__ UA, __half *__restrict__ WB, int precise)
+                                  __half *__restrict__ XB2, __half *__restrict__ UA, __half *__restrict__ WB, int precise,
+                                  uint8_t *__restrict__ XB8 = nullptr)
 {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
@@ -97,7 +106,12 @@ __global__ void split_phi2_kernel(const double *__restrict__ X, const double *__
         s_full += full * full;
         s_hi += hid * hid;
         XA2[row * P2_A_LD + k] = hi;
-        XA2[row * P2_A_LD + 64 + k] = lo;
+        if (XB8 != nullptr) {
+            reinterpret_cast<uint8_t *>(XA2 + row * P2_A_LD + 64)[k] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(lo) * 1024.0f, __NV_SATFINITE, __NV_E5M2);
+            if (row < n_rows_b) XB8[row * 64 + k] = (uint8_t)__nv_cvt_float_to_fp8((float)hid * (1.0f / 1024.0f), __NV_SATFINITE, __NV_E5M2);
+        } else {
+            XA2[row * P2_A_LD + 64 + k] = lo;
+        }
         if (row < n_rows_b) {
             if (precise) {
                 XB2[row * 128 + k] = hi;
@@ -138,8 +152,9 @@ __global__ void make_v32_kernel(const double *__restrict__ X, const double *__re
 }
 
 // V^T (fp16, [128][ldn]): rows [0,64) v_hi, [64,128) v_lo of v~.  One block = 64 particles, transposed through shared memory.
+// VT8 != nullptr (F8LO): additionally v_lo as e5m2, [64][ldn] bytes.
 __global__ void __launch_bounds__(256)
-make_vt2_kernel(const float *__restrict__ V32, int64_t n, int64_t ldn, int d, __half *__restrict__ VT)
+make_vt2_kernel(const float *__restrict__ V32, int64_t n, int64_t ldn, int d, __half *__restrict__ VT, uint8_t *__restrict__ VT8 = nullptr)
 {
     __shared__ __half tile[128][64 + 2];
     const int64_t j0 = (int64_t)blockIdx.x * 64;
@@ -158,7 +173,11 @@ make_vt2_kernel(const float *__restrict__ V32, int64_t n, int64_t ldn, int d, __
     __syncthreads();
     for (int t = threadIdx.x; t < 128 * 64; t += blockDim.x) {
         const int rr = t >> 6, jl = t & 63;
-        if (j0 + jl < ldn) VT[(int64_t)rr * ldn + j0 + jl] = tile[rr][jl];
+        if (j0 + jl < ldn) {
+            VT[(int64_t)rr * ldn + j0 + jl] = tile[rr][jl];
+            if (VT8 != nullptr && rr >= 64)
+                VT8[(int64_t)(rr - 64) * ldn + j0 + jl] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(tile[rr][jl]), __NV_SATFINITE, __NV_E5M2);
+        }
     }
 }
 
@@ -259,11 +278,12 @@ constexpr int P2_THREADS = (P2_EWARPS + 3) * 32;
 // CL = 2: clusters of two CTAs walk the SAME j-tiles with two consecutive i-pairs (512 particle rows per cluster); every box of a
 // stage is fetched from L2 once and multicast into both CTAs (each issues half of the boxes), a stage is refilled when the MMAs of
 // both CTAs have released it.  The kernel pulls 7 GB per launch from L2 at the headline shape (4.1 TB/s): this halves it.
-template <int POLY, bool PRECISE, int CL = 1>
+template <int POLY, bool PRECISE, int CL = 1, bool F8LO = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
-phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p)
+phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p,
+                 const __grid_constant__ CUtensorMap mapB8, const __grid_constant__ CUtensorMap mapV8)
 {
-    using Cfg = P2Cfg<PRECISE>;
+    using Cfg = P2Cfg<PRECISE, F8LO>;
     constexpr int P2_STAGES = Cfg::STAGES;
     constexpr uint32_t P2_XB_BYTES = Cfg::XB_BYTES, P2_STAGE = Cfg::STAGE, P2_TX = Cfg::TX;
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
@@ -318,9 +338,15 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                         tma_load_2d(st, &mapB, 0, j0, full + slot);
                         if (PRECISE) tma_load_2d(st + 16384, &mapB, 64, j0, full + slot); // lo_j
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
+                        for (int c = 0; c < (F8LO ? 2 : 4); ++c) // v_hi for both j-halves (+ v_lo in fp16 unless it goes in e5m2)
                             tma_load_2d(st + P2_XB_BYTES + c * P2_VBOX, &mapV, j0 + (c & 1) * 64, (c >> 1) * 64, full + slot);
                         bulk_load_1d(st + P2_XB_BYTES + P2_V_BYTES, wsrc, P2_W_BYTES, full + slot);
+                        if (F8LO) {
+                            uint8_t *s8 = st + P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES;
+                            tma_load_2d(s8, &mapB8, 0, j0, full + slot);                 // y^_j as e5m2, 128 particles x 64 B
+                            tma_load_2d(s8 + 8192, &mapV8, j0, 0, full + slot);          // v_lo as e5m2: 64 coordinates x particles [j0, j0 + 64)
+                            tma_load_2d(s8 + 8192 + 4096, &mapV8, j0 + 64, 0, full + slot); // ... x particles [j0 + 64, j0 + 128)
+                        }
                     } else if (crank == 0) { // CTA 0: the particle operand and its offset chunk; CTA 1: the four V boxes (about half of the bytes each)
                         tma_load_2d_mc(st, &mapB, 0, j0, full + slot, MC_MASK);
                         if (PRECISE) tma_load_2d_mc(st + 16384, &mapB, 64, j0, full + slot, MC_MASK);
@@ -354,10 +380,17 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dS, aT + 8, bl + 2, idesc);
                 umma_f16_ts2<true>(dS, aT + 16, bl + 4, idesc);
                 umma_f16_ts2<true>(dS, aT + 24, bl + 6, idesc);
-                umma_f16_ts2<true>(dS, aT + 32, bl, idesc);
-                umma_f16_ts2<true>(dS, aT + 40, bl + 2, idesc);
-                umma_f16_ts2<true>(dS, aT + 48, bl + 4, idesc);
-                umma_f16_ts2<true>(dS, aT + 56, bl + 6, idesc);
+                if (F8LO) { // (lo_i 2^10) . (y^_j 2^-10) in e5m2: K = 32 per MMA, 64-byte rows (SWIZZLE_64B), j-half k = rows 64 k .. of the tile
+                    const uint32_t b8 = st_lo0 + slot * (P2_STAGE >> 4) + ((P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES) >> 4) + k * (4096 >> 4);
+                    const uint32_t idesc8 = make_idesc_bf16(TC_TILE, 64);
+                    umma_f8_ts2<true>(dS, aT + 32, b8, idesc8);
+                    umma_f8_ts2<true>(dS, aT + 40, b8 + 2, idesc8);
+                } else {
+                    umma_f16_ts2<true>(dS, aT + 32, bl, idesc);
+                    umma_f16_ts2<true>(dS, aT + 40, bl + 2, idesc);
+                    umma_f16_ts2<true>(dS, aT + 48, bl + 4, idesc);
+                    umma_f16_ts2<true>(dS, aT + 56, bl + 6, idesc);
+                }
                 if (PRECISE) { // hi_i . lo_j
                     const uint32_t bo = bl + (16384 >> 4);
                     umma_f16_ts2<true>(dS, aT, bo, idesc);
@@ -386,10 +419,17 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 umma_f16_ts2<true>(dP, e + 8, vh + 2, idesc);
                 umma_f16_ts2<true>(dP, e + 32, vh + 4, idesc);
                 umma_f16_ts2<true>(dP, e + 40, vh + 6, idesc);
-                umma_f16_ts2<true>(dP, e, vl, idesc);
-                umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
-                umma_f16_ts2<true>(dP, e + 32, vl + 4, idesc);
-                umma_f16_ts2<true>(dP, e + 40, vl + 6, idesc);
+                if (F8LO) { // E (top bytes of the fp16 values: e5m2) . v_lo (e5m2): K = 32 particles per MMA
+                    const uint32_t v8 = st_lo0 + slot * (P2_STAGE >> 4) + ((P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES + 8192) >> 4) + k * (4096 >> 4);
+                    const uint32_t idesc8 = make_idesc_bf16(TC_TILE, 64);
+                    umma_f8_ts2<true>(dP, e + 16, v8, idesc8);
+                    umma_f8_ts2<true>(dP, e + 48, v8 + 2, idesc8);
+                } else {
+                    umma_f16_ts2<true>(dP, e, vl, idesc);
+                    umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
+                    umma_f16_ts2<true>(dP, e + 32, vl + 4, idesc);
+                    umma_f16_ts2<true>(dP, e + 40, vl + 6, idesc);
+                }
                 if (PRECISE) { // E_lo . v_hi  (E_lo sits in the second 16 columns of each 32-column half)
                     umma_f16_ts2<true>(dP, e + 16, vh, idesc);
                     umma_f16_ts2<true>(dP, e + 24, vh + 2, idesc);
@@ -442,6 +482,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 const uint4 *src = reinterpret_cast<const uint4 *>(p.XA2 + i * P2_A_LD + 64 * h);
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
+                    if (F8LO && h == 1 && k == 1) break; // the e5m2 lo term is 64 bytes = 16 columns
                     uint32_t v[16];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -530,6 +571,12 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 }
                 tmem_st16(tS, pk);
                 if constexpr (PRECISE) tmem_st16(tS + 16, pl);
+                if constexpr (F8LO) { // e5m2 copy of E for the E . v_lo term: the top byte of each fp16 value (one PRMT per four values)
+                    uint32_t e8[8];
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) e8[z] = __byte_perm(pk[2 * z], pk[2 * z + 1], 0x7531);
+                    tmem_st8(tS + 16, e8);
+                }
                 const bool more = q + 1 < nunits;
                 const int kn = (int)((q + 1) & 1u);
                 const uint32_t gn = g + ((q + 1) >> 1);

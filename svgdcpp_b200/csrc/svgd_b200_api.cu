@@ -167,7 +167,11 @@ struct svgdb_ctx {
     __half *XA2 = nullptr, *XB2 = nullptr, *VT2 = nullptr;
     float *V32 = nullptr; // v~ = g - 2 a (x - mean) in fp32, [n_pad][d]: what the ranks all-gather in this mode
     __half *UA2 = nullptr, *WB2 = nullptr; // exponent-offset K chunks (row / column side)
-    CUtensorMap mapB2{}, mapV2{};
+    CUtensorMap mapB2{}, mapV2{}, mapB8{}, mapV8{};
+    uint8_t *VT8 = nullptr; // e5m2 copy of v_lo^T (pair kernel, F8LO variant)
+    uint8_t *XB8 = nullptr; // e5m2 copy of the column operand (pair kernel, F8LO variant)
+    int phi_f8 = -1;        // SVGDB_PHI_F8: the FAST pair kernel computes its two correction terms (lo_i . y^_j and E . v_lo) in e5m2:
+                            // 13 MMAs per unit instead of 17.  -1 = automatic (phi_use_f8), 0 = never, 1 = whenever the FAST variant runs
     __nv_bfloat16 *XBD = nullptr; // column operand [hi | lo] of the persistent distance pass (kernels_dist_tc.cuh)
     CUtensorMap mapBD{};
     int dist_dbg_mode = 0; // svgdb_time_kernel measurement aid
@@ -290,6 +294,10 @@ int free_sharded(svgdb_ctx *ctx)
     cudaFree(ctx->rt); cudaFree(ctx->colsum); cudaFree(ctx->tc_err); cudaFree(ctx->tc_trace);
     cudaFree(ctx->XBD);
     ctx->XBD = nullptr;
+    cudaFree(ctx->XB8);
+    ctx->XB8 = nullptr;
+    cudaFree(ctx->VT8);
+    ctx->VT8 = nullptr;
     cudaFree(ctx->V32);
     ctx->V32 = nullptr;
     cudaFree(ctx->XA2); cudaFree(ctx->XB2); cudaFree(ctx->VT2); cudaFree(ctx->UA2); cudaFree(ctx->WB2);
@@ -326,6 +334,53 @@ int make_bf16_map(svgdb_ctx *ctx, CUtensorMap *m, void *base, uint64_t rows, uin
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return SVGDB_OK;
+}
+
+// rows x 64 bytes, contiguous; box = 64 bytes (SWIZZLE_64B) x box_rows
+int make_u8_map_sw64(svgdb_ctx *ctx, CUtensorMap *m, void *base, uint64_t rows, uint32_t box_rows)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((TmapEncodeFn)fn)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled (u8, 64B swizzle) failed with CUresult " + std::to_string((int)r));
+    return SVGDB_OK;
+}
+
+// rows x cols bytes, cols contiguous; box = 64 bytes (SWIZZLE_64B) x box_rows
+int make_u8_map_rows(svgdb_ctx *ctx, CUtensorMap *m, void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((TmapEncodeFn)fn)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SVGDB_ERR_CUDA, "cuTensorMapEncodeTiled (u8 rows, 64B swizzle) failed with CUresult " + std::to_string((int)r));
+    return SVGDB_OK;
+}
+
+// e5m2 correction terms in the FAST pair kernel.  The rounding error of lo_i (2^-3 of a 2^-11 term) is the same for every pair of
+// row i, so it does not average out over j; it does average over the d coordinates of lo_i . y^_j.  Automatic: only where that
+// averaging keeps the row error where it was (measured at N = 65,536 on sampled rows incl. the outermost particle: 5.1e-4 against 2.2e-4
+// at d = 2, 3.5e-5 / 3.1e-5 at d = 8, no difference from d = 16 up) AND where it pays: the pair pass gains 4 - 6 % at d = 64 and loses
+// 2 % at d <= 32, where the zero-padded operands leave the tensor pipe under its power limit and the exp warps' extra work shows.
+bool tc32_precise(const svgdb_ctx *ctx);
+bool phi_use_f8(const svgdb_ctx *ctx)
+{
+    if (tc32_precise(ctx) || ctx->wide) return false;
+    if (ctx->phi_f8 >= 0) return ctx->phi_f8 != 0;
+    return ctx->d >= 48 && ctx->N >= 16384;
 }
 
 int alloc_tc32(svgdb_ctx *ctx)
@@ -365,6 +420,10 @@ int alloc_tc32(svgdb_ctx *ctx)
         TRY(make_bf16_map(ctx, &ctx->mapBD, ctx->XBD, np, 128, 128));
         TRY(make_bf16_map(ctx, &ctx->mapB2, ctx->XB2, np, 64, 128));
         TRY(make_bf16_map(ctx, &ctx->mapV2, ctx->VT2, 128, np, 64));
+        CU(cudaMalloc(&ctx->XB8, np * 64));
+        TRY(make_u8_map_sw64(ctx, &ctx->mapB8, ctx->XB8, np, 128));
+        CU(cudaMalloc(&ctx->VT8, np * 64));
+        TRY(make_u8_map_rows(ctx, &ctx->mapV8, ctx->VT8, 64, np, 64));
     }
     if (const char *e = std::getenv("SVGDB_DIST_GATED")) ctx->dist_gated = std::atoi(e) != 0;
     if (const char *e = std::getenv("SVGDB_DIST_FOLD")) ctx->dist_fold = std::atoi(e);
@@ -375,6 +434,7 @@ int alloc_tc32(svgdb_ctx *ctx)
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_MAX_SEG")) ctx->phi_max_seg = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_CLUSTER")) ctx->phi_cluster = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_F8")) ctx->phi_f8 = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_HOST_CHUNKS")) ctx->host_chunks = std::atoi(e);
     return SVGDB_OK;
 }
@@ -1154,13 +1214,14 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
 
 // Which arithmetic the tensor-core pair kernel runs (kernels_phi_tc.cuh, DESIGN.md "Precision modes").  The fast variant's error
 // terms (fp16 rounding of the column particle and of the kernel values) are zero-mean and average over a row's effective neighbours:
-// it is the default only where that holds by construction -- one Gaussian target and at least 16,384 particles; mixtures, user
-// models behind the gradient hook and small particle sets get the precise variant (1.5x the MMAs).
+// it is the default only where that holds by construction -- one Gaussian target, at least 16,384 particles and d >= 8 (the
+// rounding of y^_j also averages over the coordinates: at d = 2, N = 65,536 the outermost particle's row is off by 2.2e-4 of max|phi|,
+// 3e-5 at d = 8); mixtures, user models behind the gradient hook, small particle sets and d < 8 get the precise variant (1.5x the MMAs).
 bool tc32_precise(const svgdb_ctx *ctx)
 {
     if (ctx->tc32_variant == SVGDB_TC32_FAST) return false;
     if (ctx->tc32_variant == SVGDB_TC32_PRECISE) return true;
-    return !(ctx->model_kind == MODEL_MVN_SUM && ctx->C == 1 && ctx->N >= 16384);
+    return !(ctx->model_kind == MODEL_MVN_SUM && ctx->C == 1 && ctx->N >= 16384 && ctx->d >= 8);
 }
 
 // The particle-side operands of the pair kernel (they need X and the bandwidth, not V) and the zeroed accumulator.
@@ -1183,7 +1244,7 @@ int launch_phi_x_operands(svgdb_ctx *ctx, cudaStream_t stream)
     const bool precise = tc32_precise(ctx);
     split_phi2_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, stream>>>(ctx->X[ctx->cur], ctx->colsum, ctx->a_dev, ctx->N, rows_a, ctx->n_pad128,
                                                                          ctx->d, ctx->XA2, precise ? reinterpret_cast<__half *>(ctx->XBD) : ctx->XB2,
-                                                                         ctx->UA2, ctx->WB2, precise ? 1 : 0);
+                                                                         ctx->UA2, ctx->WB2, precise ? 1 : 0, phi_use_f8(ctx) ? ctx->XB8 : nullptr);
     KERNEL_CHECK();
     return SVGDB_OK;
 }
@@ -1280,7 +1341,8 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
     if (ctx->n_rows <= 0) return SVGDB_OK;
     if (!x_operands_done) TRY(launch_phi_x_operands(ctx, ctx->stream));
     if (ctx->wide) return launch_phi_wide(ctx, debug_phi);
-    make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2);
+    make_vt2_kernel<<<(unsigned)(ctx->n_pad128 / 64), 256, 0, ctx->stream>>>(ctx->V32, ctx->N, ctx->n_pad128, ctx->d, ctx->VT2,
+                                                                              phi_use_f8(ctx) ? ctx->VT8 : nullptr);
     KERNEL_CHECK();
     // Row chunks.  Normally one; when the updated rows are wanted on the host (svgdb_step_host) the rows are processed in four
     // launches of 3/8, 3/8, 1/8, 1/8 of the i-pairs, each followed by its optimizer kernel and a device-to-host copy on the
@@ -1330,12 +1392,15 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
 #define SVGDB_P2_LAUNCH(P, PR, CLV)                                                                                   \
     do {                                                                                                              \
         cfg.dynamicSmemBytes = P2Cfg<PR>::SMEM;                                                                       \
-        CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, PR, CLV>, PR ? ctx->mapBD : ctx->mapB2, ctx->mapV2, a));        \
+        CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, PR, CLV>, PR ? ctx->mapBD : ctx->mapB2, ctx->mapV2, a, ctx->mapB8, ctx->mapV8)); \
     } while (0)
 #define SVGDB_PHI2_CASE(P)                                                                                            \
     case P:                                                                                                           \
         if (precise) { if (cl == 2) SVGDB_P2_LAUNCH(P, true, 2); else SVGDB_P2_LAUNCH(P, true, 1); }                  \
-        else { if (cl == 2) SVGDB_P2_LAUNCH(P, false, 2); else SVGDB_P2_LAUNCH(P, false, 1); }                        \
+        else if (phi_use_f8(ctx) && cl == 1) {                                                                            \
+            cfg.dynamicSmemBytes = P2Cfg<false, true>::SMEM;                                                          \
+            CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, false, 1, true>, ctx->mapB2, ctx->mapV2, a, ctx->mapB8, ctx->mapV8)); \
+        } else { if (cl == 2) SVGDB_P2_LAUNCH(P, false, 2); else SVGDB_P2_LAUNCH(P, false, 1); }                      \
         break;
             switch (ctx->phi_poly) {
                 SVGDB_PHI2_CASE(0)
@@ -1767,7 +1832,8 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));   \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
-    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));   \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false, true>::SMEM));
         SVGDB_PHI2_ATTR(0)
         SVGDB_PHI2_ATTR(4)
 #undef SVGDB_PHI2_ATTR

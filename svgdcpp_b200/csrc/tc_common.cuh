@@ -189,6 +189,20 @@ __device__ __forceinline__ void umma_f16_ts2r(uint32_t d_tmem, uint32_t a_tmem, 
                  : "memory");
 }
 
+// kind::f8f6f4 (here: e5m2 x e5m2 -> f32, K = 32 per instruction), A from TMEM, B a K-major tile of 64-byte rows written by TMA with
+// SWIZZLE_64B (8-row groups 512 B apart).  The instruction descriptor has the bit pattern of make_idesc_bf16 (format field 1 = E5M2).
+constexpr uint32_t DESC_HI_K_SW64 = (512u >> 4) | (1u << 14) | (4u << 29); // SBO = 512 B, version 1, SWIZZLE_64B
+template <bool ACC>
+__device__ __forceinline__ void umma_f8_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(DESC_HI_K_SW64), "r"(idesc), "r"(ACC ? 1u : 0u)
+                 : "memory");
+}
+
 // Arrives on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -231,6 +245,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
