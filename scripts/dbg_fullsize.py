@@ -11,7 +11,10 @@ def run(workload, variant, max_seg):
         n, d = 65536, 64
         x0, means, covs = synth.mvn_problem(n, d)
     elif workload.startswith("mvn"):  # mvn<d>: the config-3 recipe at another dimension
-        n, d = 65536, int(workload[3:])
+        n, d = 65536, workload[3:]  # mvn<d>[n<N>]
+        if "n" in d:
+            d, n = d.split("n"); n = int(n)
+        d = int(d)
         x0, means, covs = synth.mvn_problem(n, d)
     else:
         n, d = 65536, 256

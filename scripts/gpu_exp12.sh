@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+set -u
+for cfg in "0 0 0" "0 0 1" "1 0 0" "1 0 1" "1 1 0" "1 1 1"; do
+  set -- $cfg
+  SVGDB_PHI_F8=$1 SVGDB_PHI_NO_VLO=$2 SVGDB_PHI_DBG=$3 timeout 200 python scripts/tc_clock.py 2>&1 | tail -1
+done
+SVGDB_PHI_F8=0 SVGDB_PHI_DBG=0 timeout 200 python scripts/tc_clock.py 32 2>&1 | tail -1
+SVGDB_PHI_F8=0 SVGDB_PHI_DBG=1 timeout 200 python scripts/tc_clock.py 32 2>&1 | tail -1

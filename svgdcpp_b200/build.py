@@ -48,13 +48,15 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     defines = ["-DSVGDB_WITH_TC32"] if os.path.exists(os.path.join(CSRC, "kernels_tc32.cuh")) else []
     cmd = [_nvcc(), *NVCC_FLAGS, *_host_cxx(), *defines, "-o", LIB_PATH,
            os.path.join(CSRC, "svgd_b200_api.cu"), "-ldl", "-lcuda"]
+    if trace:
+        cmd.insert(1, "-DSVGDB_TC_TRACE_BUILD")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,4 +68,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # --trace: compile the SVGDB_TC_TRACE timeline probes into the pair kernel (development aid, scripts/tc_trace.py)
+    print(build(force="--force" in sys.argv or "--trace" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

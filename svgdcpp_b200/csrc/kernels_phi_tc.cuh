@@ -53,7 +53,8 @@ struct P2Cfg {
     static constexpr uint32_t V8_BYTES = F8LO ? 8192u : 0u;         // v_lo as e5m2: two boxes (j-halves) of 64 coordinates x 64 particles
     static constexpr uint32_t STAGE = XB_BYTES + P2_V_BYTES + P2_W_BYTES + X8_BYTES + V8_BYTES; // 52 KB / 68 KB / 68 KB (1024-aligned)
     static constexpr uint32_t TX = F8LO ? STAGE - 2 * P2_VBOX : STAGE; // (the fp16 v_lo boxes are not fetched in the F8LO variant)
-    static constexpr uint32_t SMEM = STAGES * STAGE + 2 * P2_AEX_BYTES + 256 + 1024;
+    static constexpr uint32_t ONES_BYTES = F8LO ? 2048u : 0u;      // 16 rows x 64 fp16 ones: the B operand of the row-sum MMAs (TCSUM)
+    static constexpr uint32_t SMEM = STAGES * STAGE + 2 * P2_AEX_BYTES + ONES_BYTES + 256 + 1024;
 };
 // K-major operand of 16 fp16 columns WITHOUT swizzle: 8 x 16 B core matrices; row r, column k lives at
 // (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2   (LBO = 128 B between the two K halves, SBO = 256 B per 8 rows)
@@ -242,6 +243,7 @@ struct Phi2Args {
     int max_seg;           // longest run of j-tiles accumulated in TMEM before the partial sums are flushed (see p2_segment)
     int poly;              // pairs (of 16) per 32-column chunk whose exponentials use ex2_poly
     int dbg;               // development: 1 = exp warps only hand the barriers on, 2 = TMEM load/store without the math
+    int no_vlo;            // F8LO only: 1 = leave the E . v_lo term out altogether (v then carries one fp16 term, like E)
     int *err;
     long long *trace;
 };
@@ -278,7 +280,9 @@ constexpr int P2_THREADS = (P2_EWARPS + 3) * 32;
 // CL = 2: clusters of two CTAs walk the SAME j-tiles with two consecutive i-pairs (512 particle rows per cluster); every box of a
 // stage is fetched from L2 once and multicast into both CTAs (each issues half of the boxes), a stage is refilled when the MMAs of
 // both CTAs have released it.  The kernel pulls 7 GB per launch from L2 at the headline shape (4.1 TB/s): this halves it.
-template <int POLY, bool PRECISE, int CL = 1, bool F8LO = false>
+// TCSUM (with F8LO): the row sum Sum_j E_ij comes from the tensor core too -- four N = 16 MMAs per unit of E against a block of ones,
+// accumulated in the 16 TMEM columns the e5m2 lo operand leaves free -- instead of one FHADD per pair in the exp warps.
+template <int POLY, bool PRECISE, int CL = 1, bool F8LO = false, bool TCSUM = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapV, const __grid_constant__ Phi2Args p,
                  const __grid_constant__ CUtensorMap mapB8, const __grid_constant__ CUtensorMap mapV8)
@@ -297,7 +301,8 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sAex = smem + P2_STAGES * P2_STAGE; // [2][P2_AEX_BYTES]
-    uint64_t *bars = (uint64_t *)(sAex + 2 * P2_AEX_BYTES);
+    uint8_t *sOnes = sAex + 2 * P2_AEX_BYTES;    // [Cfg::ONES_BYTES], 1024-aligned
+    uint64_t *bars = (uint64_t *)(sOnes + Cfg::ONES_BYTES);
     uint64_t *full = bars;                  // P2_STAGES: TMA bytes landed
     uint64_t *empty = full + P2_STAGES;     // P2_STAGES: every MMA reading the stage has completed
     uint64_t *s_full = empty + P2_STAGES;   // 4: S_b complete
@@ -313,12 +318,20 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         for (int s = 0; s < 2; ++s) { mbar_init(phi_full + s, 1); mbar_init(a_ready + s, 8); }
         fence_barrier_init();
     }
+    if (TCSUM) {
+        for (uint32_t t = threadIdx.x; t < Cfg::ONES_BYTES / 4; t += P2_THREADS) reinterpret_cast<uint32_t *>(sOnes)[t] = 0x3C003C00u; // fp16 1.0
+        fence_proxy_async();
+    }
     if (warp == P2_EWARPS) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all(); // the peer's barriers are initialised before anything of ours can arrive on them
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { // SM clock of this launch = cycles / nanoseconds over CTA 0's lifetime
+        p.trace[(1 * 64 + 63) * 8 + 0] = clock64();
+        p.trace[(2 * 64 + 63) * 8 + 0] = (long long)globaltimer_ns();
+    }
 
     if (warp == P2_EWARPS) { // ---- TMA producer (whole warp runs the loop, one elected lane issues)
         long long pos = u_beg;
@@ -332,7 +345,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (elect_one()) {
                     uint8_t *st = smem + slot * P2_STAGE;
                     const int j0 = jt * TC_TILE;
-                    mbar_arrive_expect_tx(full + slot, P2_TX); // all of the stage's bytes, whoever fetches them
+                    mbar_arrive_expect_tx(full + slot, (F8LO && p.no_vlo) ? P2_TX - 8192u : P2_TX); // all of the stage's bytes, whoever fetches them
                     const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.WB) + (size_t)jt * P2_W_BYTES;
                     if (CL == 1) {
                         tma_load_2d(st, &mapB, 0, j0, full + slot);
@@ -344,8 +357,10 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                         if (F8LO) {
                             uint8_t *s8 = st + P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES;
                             tma_load_2d(s8, &mapB8, 0, j0, full + slot);                 // y^_j as e5m2, 128 particles x 64 B
-                            tma_load_2d(s8 + 8192, &mapV8, j0, 0, full + slot);          // v_lo as e5m2: 64 coordinates x particles [j0, j0 + 64)
-                            tma_load_2d(s8 + 8192 + 4096, &mapV8, j0 + 64, 0, full + slot); // ... x particles [j0 + 64, j0 + 128)
+                            if (!p.no_vlo) {
+                                tma_load_2d(s8 + 8192, &mapV8, j0, 0, full + slot);          // v_lo as e5m2: 64 coordinates x particles [j0, j0 + 64)
+                                tma_load_2d(s8 + 8192 + 4096, &mapV8, j0 + 64, 0, full + slot); // ... x particles [j0 + 64, j0 + 128)
+                            }
                         }
                     } else if (crank == 0) { // CTA 0: the particle operand and its offset chunk; CTA 1: the four V boxes (about half of the bytes each)
                         tma_load_2d_mc(st, &mapB, 0, j0, full + slot, MC_MASK);
@@ -410,6 +425,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
         auto issue_pv = [&](int b, uint32_t gt, bool first, bool last) -> bool {
             const int w = b >> 1, k = b & 1;
             if (!mbar_wait(e_ready + b, gt & 1, p.err, 22 + b)) return false;
+            if (lane == 0 && w == 0) TC_TRACE(0, gt, 3 + k);
             tc_fence_after();
             const uint32_t slot = gt % P2_STAGES;
             if (elect_one()) {
@@ -422,8 +438,10 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (F8LO) { // E (top bytes of the fp16 values: e5m2) . v_lo (e5m2): K = 32 particles per MMA
                     const uint32_t v8 = st_lo0 + slot * (P2_STAGE >> 4) + ((P2_XB_BYTES + P2_V_BYTES + P2_W_BYTES + 8192) >> 4) + k * (4096 >> 4);
                     const uint32_t idesc8 = make_idesc_bf16(TC_TILE, 64);
-                    umma_f8_ts2<true>(dP, e + 16, v8, idesc8);
-                    umma_f8_ts2<true>(dP, e + 48, v8 + 2, idesc8);
+                    if (!p.no_vlo) {
+                        umma_f8_ts2<true>(dP, e + 16, v8, idesc8);
+                        umma_f8_ts2<true>(dP, e + 48, v8 + 2, idesc8);
+                    }
                 } else {
                     umma_f16_ts2<true>(dP, e, vl, idesc);
                     umma_f16_ts2<true>(dP, e + 8, vl + 2, idesc);
@@ -435,6 +453,14 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                     umma_f16_ts2<true>(dP, e + 24, vh + 2, idesc);
                     umma_f16_ts2<true>(dP, e + 48, vh + 4, idesc);
                     umma_f16_ts2<true>(dP, e + 56, vh + 6, idesc);
+                }
+                if (TCSUM) { // row sums: E_b . ones (N = 16; every column of the result is the row sum)
+                    const uint32_t dR = tmem + P2_COL_A + w * 64 + 48, on = desc_lo_k_sw128(smem_u32(sOnes));
+                    const uint32_t idesc16 = make_idesc_f16(TC_TILE, 16);
+                    umma_f16_ts2r(dR, e, on, idesc16, (first && k == 0) ? 0u : 1u);
+                    umma_f16_ts2<true>(dR, e + 8, on + 2, idesc16);
+                    umma_f16_ts2<true>(dR, e + 32, on + 4, idesc16);
+                    umma_f16_ts2<true>(dR, e + 40, on + 6, idesc16);
                 }
                 if (k == 1) {
                     if (CL == 1) umma_commit(empty + slot);
@@ -529,8 +555,9 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 if (tracer) TC_TRACE(1 + w, gt, 2 + 3 * k);
                 uint32_t pk[16];
                 uint32_t pl[PRECISE ? 16 : 1]; // E_lo = fp16(E - E_hi)
-                auto exp_chunk = [&](auto diag_tag) {
+                auto exp_chunk = [&](auto diag_tag, auto sum_tag) {
                     constexpr bool DIAG = decltype(diag_tag)::value;
+                    constexpr bool ROWSUM = decltype(sum_tag)::value && !TCSUM;
 #pragma unroll
                     for (int q4 = 0; q4 < 8; ++q4) {
                         const float x0 = __uint_as_float(r0[4 * q4]), x1 = __uint_as_float(r0[4 * q4 + 1]);
@@ -551,7 +578,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                             rs0 += e0; rs1 += e1; rs2 += e2; rs3 += e3;
                             pl[2 * q4] = residual_f16x2(pk[2 * q4], e0, e1);
                             pl[2 * q4 + 1] = residual_f16x2(pk[2 * q4 + 1], e2, e3);
-                        } else {
+                        } else if (ROWSUM) {
                             acc_f16x2(rs0, rs1, pk[2 * q4]);
                             acc_f16x2(rs2, rs3, pk[2 * q4 + 1]);
                         }
@@ -565,38 +592,33 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                         for (int z = 0; z < 16; ++z) pl[z] = r0[z] & r0[z + 16];
                     }
                 } else if (has_diag) {
-                    exp_chunk(std::true_type{});
+                    exp_chunk(std::true_type{}, std::true_type{});
                 } else {
-                    exp_chunk(std::false_type{});
+                    exp_chunk(std::false_type{}, std::true_type{});
                 }
                 tmem_st16(tS, pk);
                 if constexpr (PRECISE) tmem_st16(tS + 16, pl);
-                if constexpr (F8LO) { // e5m2 copy of E for the E . v_lo term: the top byte of each fp16 value (one PRMT per four values)
+                if (F8LO && !p.no_vlo) { // e5m2 copy of E for the E . v_lo term: the top byte of each fp16 value (one PRMT per four values)
                     uint32_t e8[8];
 #pragma unroll
                     for (int z = 0; z < 8; ++z) e8[z] = __byte_perm(pk[2 * z], pk[2 * z + 1], 0x7531);
                     tmem_st8(tS + 16, e8);
                 }
-                const bool more = q + 1 < nunits;
-                const int kn = (int)((q + 1) & 1u);
-                const uint32_t gn = g + ((q + 1) >> 1);
-                const uint32_t tSn = tmem + (2 * w + kn) * 64 + 32 * h + lane_base;
-                bool fetched = false;
-                if (more && __all_sync(0xffffffffu, mbar_try_wait(s_full + 2 * w + kn, gn & 1))) {
-                    tc_fence_after();
-                    tmem_ld32(tSn, r0);
-                    fetched = true;
-                }
+                // E_b complete -> the tile's MMA warp first (PV(b), then the next S into this buffer: that chain is what this warp will wait for
+                // two units from now), then the next unit's S.  (Polling for the next S before the arrival -- to overlap its TMEM load with the
+                // store drain -- found it incomplete four times out of five and only delayed the hand-off by the poll.)
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(e_ready + b);
                 if (tracer) TC_TRACE(1 + w, gt, 3 + 3 * k);
-                if (more && !fetched) {
+                if (q + 1 < nunits) {
+                    const int kn = (int)((q + 1) & 1u);
+                    const uint32_t gn = g + ((q + 1) >> 1);
                     if (tracer) TC_TRACE(1 + w, gn, 1 + 3 * kn);
                     if (!mbar_wait(s_full + 2 * w + kn, gn & 1, p.err, 40 + 2 * w + kn)) { ok = false; break; }
                     tc_fence_after();
-                    tmem_ld32(tSn, r0);
+                    tmem_ld32(tmem + (2 * w + kn) * 64 + 32 * h + lane_base, r0);
                 }
             }
             g += nt;
@@ -615,7 +637,16 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                         for (int z = 0; z < 16; ++z) atomicAdd(dst + c0 + z, __uint_as_float(v[z]) * TC_E_UNSCALE);
                     }
                 }
-                if (valid) atomicAdd(p.phi_buf + i * TC_PHI_LD + TC_ONES_ROW, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
+                if (TCSUM) {
+                    if (h == 0) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + P2_COL_A + w * 64 + 48 + lane_base, v);
+                        tmem_ld_wait();
+                        if (valid) atomicAdd(p.phi_buf + i * TC_PHI_LD + TC_ONES_ROW, __uint_as_float(v[0]) * TC_E_UNSCALE);
+                    }
+                } else if (valid) {
+                    atomicAdd(p.phi_buf + i * TC_PHI_LD + TC_ONES_ROW, ((rs0 + rs1) + (rs2 + rs3)) * TC_E_UNSCALE);
+                }
                 tc_fence_before(); // the a_ready arrival of the next segment orders these loads before its first MMA
             }
         }
@@ -624,6 +655,10 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
     __syncthreads();
     if (CL > 1) cluster_sync_all(); // nobody leaves while the peer may still multicast into its shared memory or arrive on its barriers
     if (warp == P2_EWARPS) tmem_dealloc(tmem, 512);
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        p.trace[(1 * 64 + 63) * 8 + 7] = clock64();
+        p.trace[(2 * 64 + 63) * 8 + 7] = (long long)globaltimer_ns();
+    }
 }
 
 } // namespace tc

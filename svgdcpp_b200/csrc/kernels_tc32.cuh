@@ -89,10 +89,16 @@ __global__ void opt_update_tc32_kernel(OptTcArgs p)
 
 // Development aid: timeline of CTA 0 of the pair-interaction kernel (SVGDB_TC_TRACE=<file>).
 // trace slots: role 0 = MMA issuer of i-tile 0, 1 / 2 = one exp warp of i-tile 0 / 1; 8 events per j-tile, 64 j-tiles
+// Compiled in only with -DSVGDB_TC_TRACE_BUILD (python -m svgdcpp_b200.build --trace): the predicates cost the exp warps ~15 % of their
+// instructions per unit even when no trace buffer is given.
+#ifdef SVGDB_TC_TRACE_BUILD
 #define TC_TRACE(role, t, ev)                                                                      \
     do {                                                                                           \
         if (p.trace != nullptr && blockIdx.x == 0 && (t) < 64) p.trace[((role) * 64 + (t)) * 8 + (ev)] = clock64(); \
     } while (0)
+#else
+#define TC_TRACE(role, t, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x)
 {

@@ -193,7 +193,10 @@ struct svgdb_ctx {
     bool dist_fold_next = false; // the next collecting pass runs over a predicted bracket (set by median_scale): it may fold -lo into the operands
     int dist_fold = 1;           // SVGDB_DIST_FOLD=0 (measurement aid) disables that
     uint64_t collect_hi_ext = 0; // exclusive key bound of what the last persistent distance pass may have collected (>= its hi)
-    int phi_poly = 0;    // SVGDB_PHI_POLY=k: k of 16 exponential pairs per chunk on the FMA pipe
+    int phi_tcsum = 1;   // SVGDB_PHI_TCSUM: the e5m2 variant takes the row sums from the tensor core (four N = 16 MMAs per unit) instead of the exp warps
+    int phi_no_vlo = -1; // SVGDB_PHI_NO_VLO: the e5m2 variant of the FAST pair kernel leaves E . v_lo out (v carries one fp16 term, like E and the
+                         // column particle: 11 MMAs per unit).  -1 = automatic: from 32,768 particles (measured error)
+    int phi_poly = 1;    // SVGDB_PHI_POLY=k (0 ... 4): k of the 16 exponential pairs of a 32-column chunk on the FMA pipe (measured optimum 1)
     int phi_cluster = -1; // 2-CTA clusters with TMA multicast of the column tiles in the pair kernels.  Default (-1): on for the wide kernel (d > 64:
                           // -10 % at d = 256), off for d <= 64 (measured: no gain, 1.83 ms either way -- that kernel is not bound by L2 traffic);
                           // SVGDB_PHI_CLUSTER=0 / 1 forces it
@@ -430,6 +433,8 @@ int alloc_tc32(svgdb_ctx *ctx)
     if (const char *e = std::getenv("SVGDB_DIST_F16")) ctx->dist_f16 = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_OPTIMISTIC")) ctx->optimistic = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_POLY")) ctx->phi_poly = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_NO_VLO")) ctx->phi_no_vlo = std::atoi(e);
+    if (const char *e = std::getenv("SVGDB_PHI_TCSUM")) ctx->phi_tcsum = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_TC32_VARIANT")) ctx->tc32_variant = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_DBG")) ctx->phi_dbg_mode = std::atoi(e);
     if (const char *e = std::getenv("SVGDB_PHI_MAX_SEG")) ctx->phi_max_seg = std::atoi(e);
@@ -1370,6 +1375,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         a.n_ipairs = (chunk_ipairs[ch] + cl - 1) / cl; // i-pair groups
         a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 32 : 128); // j-tiles (128 particles) per flush
         a.poly = ctx->phi_poly;
+        a.no_vlo = ctx->phi_no_vlo >= 0 ? ctx->phi_no_vlo : (ctx->N >= 32768 ? 1 : 0);
         a.dbg = ctx->phi_dbg_mode;
         a.err = ctx->tc_err;
         a.trace = ctx->tc_trace;
@@ -1399,13 +1405,19 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         if (precise) { if (cl == 2) SVGDB_P2_LAUNCH(P, true, 2); else SVGDB_P2_LAUNCH(P, true, 1); }                  \
         else if (phi_use_f8(ctx) && cl == 1) {                                                                            \
             cfg.dynamicSmemBytes = P2Cfg<false, true>::SMEM;                                                          \
-            CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, false, 1, true>, ctx->mapB2, ctx->mapV2, a, ctx->mapB8, ctx->mapV8)); \
+            if (ctx->phi_tcsum)                                                                                        \
+                CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, false, 1, true, true>, ctx->mapB2, ctx->mapV2, a, ctx->mapB8, ctx->mapV8)); \
+            else                                                                                                       \
+                CU(cudaLaunchKernelEx(&cfg, phi2_tc32_kernel<P, false, 1, true, false>, ctx->mapB2, ctx->mapV2, a, ctx->mapB8, ctx->mapV8)); \
         } else { if (cl == 2) SVGDB_P2_LAUNCH(P, false, 2); else SVGDB_P2_LAUNCH(P, false, 1); }                      \
         break;
             switch (ctx->phi_poly) {
                 SVGDB_PHI2_CASE(0)
+                SVGDB_PHI2_CASE(1)
+                SVGDB_PHI2_CASE(2)
+                SVGDB_PHI2_CASE(3)
                 SVGDB_PHI2_CASE(4)
-            default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 or 4");
+            default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 ... 4");
             }
 #undef SVGDB_PHI2_CASE
 #undef SVGDB_P2_LAUNCH
@@ -1833,8 +1845,12 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));   \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false>::SMEM)); \
     CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<true>::SMEM));   \
-    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false, true>::SMEM));
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false, true>::SMEM)); \
+    CU(cudaFuncSetAttribute(svgdb::tc::phi2_tc32_kernel<P, false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svgdb::tc::P2Cfg<false, true>::SMEM));
         SVGDB_PHI2_ATTR(0)
+        SVGDB_PHI2_ATTR(1)
+        SVGDB_PHI2_ATTR(2)
+        SVGDB_PHI2_ATTR(3)
         SVGDB_PHI2_ATTR(4)
 #undef SVGDB_PHI2_ATTR
 #define SVGDB_D2_ATTR(M, G, F) \
