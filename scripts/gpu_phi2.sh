@@ -17,7 +17,7 @@ for cfg in "$@"; do
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read())
-    print("  ms/step %.3f  phi %.3f ms  frac %.3f  finite %s" % (d["ms_per_step"], d["roofline"]["phase_ms_per_step"]["phi"], d["roofline"]["frac_sustained"], d["config"]["finite"]))
+    print("  ms/step %.3f  phi %.3f ms  median %.3f ms  frac %.3f  finite %s" % (d["ms_per_step"], d["roofline"]["phase_ms_per_step"]["phi"], d["roofline"]["phase_ms_per_step"]["median"], d["roofline"]["frac_sustained"], d["config"]["finite"]))
 except Exception as e:
     print("  no bench line:", e)
 PY

@@ -442,7 +442,9 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
             for (int jt = sg.jb; ok && jt < sg.je; ++jt) {
                 // symmetric enumeration: tiles below the diagonal are covered by their transposes (weight 2)
                 const unsigned int wgt = jt < itile ? 0u : (jt == itile ? 1u : 2u);
-#pragma unroll
+                // (not unrolled, rare paths marked unlikely: the loop body with its in-line compactions is ~15 KB of code per copy, and the
+                // counting warps lost a sixth of their time to instruction fetch -- stall_no_inst + branch_resolving, profiles/r02)
+#pragma unroll 1
                 for (int k = 0; k < 2; ++k, ++c) {
                     const uint32_t buf = c % 3u, bu = c / 3u;
                     const uint32_t tS = tmem + w * 192 + buf * 64 + 32 * h + lane_base;
@@ -464,8 +466,8 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_free + 3 * w + buf); // this warp's part of the accumulator is in registers
                     if (p.dbg == 1 || p.dbg == 3) continue;
-                    if (wgt != cur_wgt) { compact(); cur_wgt = wgt; }
-                    if (has_diag) { // |x_i - x_i|^2 = 0 exactly (diagonal tiles only); folded: t = 0 - lo
+                    if (__builtin_expect(wgt != cur_wgt, 0)) { compact(); cur_wgt = wgt; }
+                    if (__builtin_expect(has_diag, 0)) { // |x_i - x_i|^2 = 0 exactly (diagonal tiles only); folded: t = 0 - lo
                         const uint32_t dz = FOLD ? __float_as_uint(-p.lo_f) : 0u;
 #pragma unroll
                         for (int q = 0; q < 32; ++q)
@@ -507,7 +509,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                                 m0 = fminf(fminf(m0, fabsf(__uint_as_float(r0[q]))), fabsf(__uint_as_float(r0[q + 1])));
                                 m1 = fminf(fminf(m1, fabsf(__uint_as_float(r0[q + 2]))), fabsf(__uint_as_float(r0[q + 3])));
                             }
-                            if (__any_sync(0xffffffffu, fminf(m0, m1) < __uint_as_float(wbits))) { // rare: collect with the exact test
+                            if (__builtin_expect(__any_sync(0xffffffffu, fminf(m0, m1) < __uint_as_float(wbits)), 0)) { // rare: collect with the exact test
 #pragma unroll
                                 for (int q = 0; q < 32; ++q)
                                     asm volatile("{\n\t.reg .pred pi;\n\t"
@@ -583,7 +585,7 @@ dist2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constan
                                          : "memory");
                     }
                     // the next chunk may add up to 32 entries per thread: compact when any thread could overflow
-                    if (__any_sync(0xffffffffu, paddr - priv_base > (uint32_t)(D2_PRIV - 32) * 128u)) compact();
+                    if (__builtin_expect(__any_sync(0xffffffffu, paddr - priv_base > (uint32_t)(D2_PRIV - 32) * 128u), 0)) compact();
                     below += (unsigned long long)(cnt4[0] + cnt4[1] + cnt4[2] + cnt4[3]) * wgt;
                 }
             }
