@@ -535,6 +535,17 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
             // first 16 of the 32 S columns it has just read (E_b = S_b columns [0,16) and [32,48)).  The S of the NEXT unit is
             // fetched while the E stores of this one drain, if it is already complete.
             const uint32_t nunits = 2u * (uint32_t)nt;
+            // The one unit of the segment (if any) whose 32 columns of this warp, [J + 64 q, +32), meet its 32 rows [r_lo, +32): it holds
+            // k(x_i, x_i); dq = this thread's diagonal column there (inside [0, 32) for the rows that have one).
+            int q_diag = -1, dq = -1;
+            {
+                const int64_t J = (int64_t)sg.jb * TC_TILE + 32 * h, r_lo = iw0 + (warp & 3) * 32;
+                const int64_t t = r_lo + 31 - J;
+                if (t >= 0 && t / 64 < (int64_t)nunits) {
+                    const int64_t j0 = J + 64 * (t / 64);
+                    if (j0 < r_lo + 32 && j0 + 32 > r_lo) { q_diag = (int)(t / 64); dq = (int)(i - j0); }
+                }
+            }
             uint32_t r0[32];
             {
                 if (tracer) TC_TRACE(1 + w, g, 1);
@@ -547,10 +558,7 @@ phi2_tc32_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant
                 const uint32_t gt = g + (q >> 1);
                 const int b = 2 * w + k;
                 const uint32_t tS = tmem + b * 64 + 32 * h + lane_base;
-                const int64_t j0 = (int64_t)(sg.jb + (int)(q >> 1)) * TC_TILE + 64 * k + 32 * h;
-                const int dq = (int)(i - j0); // column of k(x_i, x_i) among this warp's 32, if inside [0,32)
-                const int64_t r_lo = iw0 + (warp & 3) * 32;       // this warp's rows are [r_lo, r_lo + 32)
-                const bool has_diag = (j0 < r_lo + 32) && (j0 + 32 > r_lo); // warp-uniform
+                const bool has_diag = (int)q == q_diag; // warp-uniform
                 tmem_ld_wait();
                 if (tracer) TC_TRACE(1 + w, gt, 2 + 3 * k);
                 uint32_t pk[16];
