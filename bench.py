@@ -437,14 +437,15 @@ def main():
         line = {
             "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f16x2-split/f32-acc (tcgen05 kind::f16; fp16 kernel values; FP64 optimizer state)" if tc else "f64",
+            "dtype": "f16x2-split/f32-acc (tcgen05 kind::f16 + an e5m2 correction term; fp16 kernel values; FP64 optimizer state)" if tc else "f64",
             "data": "synthetic",
             "config": {"workload": w["name"] % n,
                        "n_particles": n, "dim": d, "parallelism": "rows sharded over %d GPU(s), NCCL all-gather of the operands per step" % world,
                        "l2": "working set (X, V, X_next, optimizer state) = %d MB > 126 MB L2; compute-bound, no flush" % (5 * nbytes // 2 ** 20),
                        "median_passes_per_step": median_passes / max(1, args.steps), "finite": finite,
                        "precision_mode": "F64: DMMA fp64 end to end" if not tc else
-                       "TC32: tcgen05 kind::f16 MMAs on split fp16 (pair kernel) / bf16 (median) particles and scaled-fp16 kernel values, "
+                       "TC32: tcgen05 kind::f16 MMAs on split fp16 (pair kernel; the row particle's second term as an e5m2 kind::f8f6f4 product at d >= 48) / "
+                       "fp16 two-product or bf16x3 (median) particles and scaled-fp16 kernel values, "
                        "fp32 accumulation in TMEM, fp32 ex2, FP64 optimizer state (error bound in DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_ms / args.steps,
