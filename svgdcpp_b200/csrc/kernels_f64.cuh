@@ -178,6 +178,44 @@ mvn_sum_grad_f64_kernel(const double *__restrict__ X, int64_t n_total, int d, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// The mixture gradient as library GEMMs (launch_grad_gemm in svgd_b200_api.cu): the two streaming kernels around each
+// Y = (X - mu_c) Sigma_c^-1.  Same online log-sum-exp as mvn_sum_grad_f64_kernel, state kept per particle in global memory.
+// ---------------------------------------------------------------------------------------------
+// D[t] = X[t] - mu[t mod d] over the rank's rows (X already offset to its first row)
+__global__ void __launch_bounds__(256)
+grad_diff_kernel(const double *__restrict__ X, int64_t cnt, int d, const double *__restrict__ mu, double *__restrict__ D)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (int64_t)gridDim.x * blockDim.x) D[t] = X[t] - mu[t % d];
+}
+
+// one warp per particle: q = D_i . Y_i, h = -q / 2, (m, s) <- online log-sum-exp, G_i <- G_i e^(m - m') - e^(h - m') Y_i; the last
+// component divides by s.  c = 0 initialises (G, m, s are not read).
+__global__ void __launch_bounds__(256)
+grad_accumulate_kernel(const double *__restrict__ D, const double *__restrict__ Y, int64_t rows, int d, int c, int last,
+                       double *__restrict__ mrun, double *__restrict__ srun, double *__restrict__ G)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= rows) return;
+    const double *Di = D + i * d, *Yi = Y + i * d;
+    double *Gi = G + i * d;
+    double q = 0.0;
+    for (int r = lane; r < d; r += 32) q = fma(Di[r], Yi[r], q);
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const double h = -0.5 * q;
+    const double m_old = c == 0 ? -INFINITY : mrun[i], s_old = c == 0 ? 0.0 : srun[i];
+    const double m_new = fmax(m_old, h);
+    const double sc = (m_old == -INFINITY) ? 0.0 : exp(m_old - m_new);
+    const double w = exp(h - m_new);
+    const double s_new = s_old * sc + w;
+    for (int r = lane; r < d; r += 32) {
+        const double g = (c == 0 ? 0.0 : Gi[r] * sc) - w * Yi[r];
+        Gi[r] = last ? g / s_new : g;
+    }
+    if (lane == 0 && !last) { mrun[i] = m_new; srun[i] = s_new; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Shared tile loader: rows [row_base, row_base+64) x cols [col_base, col_base+ncols) of a
 // particle-contiguous matrix into smem with leading dimension ld, zero-filled outside (n, d)
 // and up to ncols_pad columns.

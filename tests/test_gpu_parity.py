@@ -403,19 +403,56 @@ def test_mixture_gradient_log_sum_exp(sv, oracle):
     svgd.close()
 
 
+@pytest.mark.parametrize("n,d,C", [(333, 16, 5), (1000, 64, 3), (700, 5, 2), (2048, 256, 16), (513, 100, 1)])
+def test_mixture_gradient_through_library_gemm(sv, oracle, monkeypatch, n, d, C):
+    """The mixture gradient as C DGEMMs Y = (X - mu_c) Sigma_c^-1 + streaming log-sum-exp kernels (launch_grad_gemm; automatic for
+    mixtures at d >= 64 and n C >= 16,384, forced here): same values as the oracle and as the one-kernel form, incl. far components, a
+    dimension that is no multiple of anything, one component, and 10 steps of the whole path on top."""
+    from svgdcpp_b200 import synth
+
+    x0, means, covs = synth.gmm_problem(n, d, C)
+    X0 = np.array(x0.T, order="C", copy=True)
+    G_ref = oracle.mvn_sum_logp_grad(X0, means, covs, lse=True)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SVGDB_GRAD_GEMM", mode)
+        model = None
+        for k in range(C):
+            m = sv.MultivariateNormal(means[k], covs[k])
+            model = m if model is None else model + m
+        x = x0.copy(order="F")
+        svgd = sv.SVGD(d, 10, x, sv.GaussianRBFKernel(x, sv.ScaleMethod.Median, model), model, sv.AdaGrad(d, n, 0.1))
+        got[mode] = svgd.EvaluateLogModelGrad().T.copy()
+        if mode == "1" and n * d <= 64 * 1024:
+            svgd.Initialize()
+            svgd.Run()
+            ref = oracle.svgd_run(X0, 10, means, covs, opt_kind=oracle.OPT_ADAGRAD, lr=0.1, lse=True)
+            assert _rel(x.T, ref) < FINAL_RTOL
+        svgd.close()
+    print("n=%d d=%d C=%d: gemm form vs oracle %.3g, one-kernel form vs oracle %.3g, between them %.3g"
+          % (n, d, C, _rel(got["1"], G_ref), _rel(got["0"], G_ref), _rel(got["1"], got["0"])))
+    assert _rel(got["1"], G_ref) < 1e-12
+    assert _rel(got["1"], got["0"]) < 1e-12
+
+
 def test_mixture_finite_where_reference_underflows(sv):
     """Every exp(-q/2) underflows in double: the reference's log(sum exp) is NaN (SURVEY.md 3.3);
     the device path evaluates the same gradient through log-sum-exp and stays finite."""
     d = 4
     x0 = np.asfortranarray(np.full((d, 8), 60.0) + np.arange(8)[None, :])
-    model = sv.MultivariateNormal(np.zeros(d), np.eye(d)) + sv.MultivariateNormal(np.ones(d), np.eye(d))
-    kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
-    svgd = sv.SVGD(d, 1, x0, kernel, model, sv.AdaGrad(d, 8, 0.1))
-    G = svgd.EvaluateLogModelGrad()
-    assert np.all(np.isfinite(G))
-    # dominated by the nearer component (mean 1): grad ~ -(x - 1)
-    assert np.allclose(G, -(x0 - 1.0), rtol=1e-9)
-    svgd.close()
+    for mode in ("0", "1"):  # the one-kernel form and the library-GEMM form
+        os.environ["SVGDB_GRAD_GEMM"] = mode
+        try:
+            model = sv.MultivariateNormal(np.zeros(d), np.eye(d)) + sv.MultivariateNormal(np.ones(d), np.eye(d))
+            kernel = sv.GaussianRBFKernel(x0, sv.ScaleMethod.Median, model)
+            svgd = sv.SVGD(d, 1, x0, kernel, model, sv.AdaGrad(d, 8, 0.1))
+            G = svgd.EvaluateLogModelGrad()
+            assert np.all(np.isfinite(G))
+            # dominated by the nearer component (mean 1): grad ~ -(x - 1)
+            assert np.allclose(G, -(x0 - 1.0), rtol=1e-9)
+            svgd.close()
+        finally:
+            del os.environ["SVGDB_GRAD_GEMM"]
 
 
 @pytest.mark.parametrize("capacity", [64, 1000])
