@@ -235,7 +235,7 @@ struct svgdb_ctx {
     int phi_tcsum = 1;   // SVGDB_PHI_TCSUM: the e5m2 variant takes the row sums from the tensor core (four N = 16 MMAs per unit) instead of the exp warps
     int phi_no_vlo = -1; // SVGDB_PHI_NO_VLO: the e5m2 variant of the FAST pair kernel leaves E . v_lo out (v carries one fp16 term, like E and the
                          // column particle: 11 MMAs per unit).  -1 = automatic: from 32,768 particles (measured error)
-    int phi_poly = 1;    // SVGDB_PHI_POLY=k (0 ... 4): k of the 16 exponential pairs of a 32-column chunk on the FMA pipe (measured optimum 1)
+    int phi_poly = 1;    // SVGDB_PHI_POLY=k (0, 1, 2, 4): k of the 16 exponential pairs of a 32-column chunk on the FMA pipe (measured optimum 1)
     int phi_cluster = -1; // 2-CTA clusters with TMA multicast of the column tiles in the pair kernels.  Default (-1): on for the wide kernel (d > 64:
                           // -10 % at d = 256), off for d <= 64 (measured: no gain, 1.83 ms either way -- that kernel is not bound by L2 traffic);
                           // SVGDB_PHI_CLUSTER=0 / 1 forces it
@@ -1504,9 +1504,8 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
                 SVGDB_PHI2_CASE(0)
                 SVGDB_PHI2_CASE(1)
                 SVGDB_PHI2_CASE(2)
-                SVGDB_PHI2_CASE(3)
                 SVGDB_PHI2_CASE(4)
-            default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0 ... 4");
+            default: return fail(ctx, SVGDB_ERR_INVALID, "SVGDB_PHI_POLY must be 0, 1, 2 or 4");
             }
 #undef SVGDB_PHI2_CASE
 #undef SVGDB_P2_LAUNCH
@@ -1939,7 +1938,6 @@ int svgdb_create(svgdb_ctx **out, int device, int64_t n_total, int32_t d, int pr
         SVGDB_PHI2_ATTR(0)
         SVGDB_PHI2_ATTR(1)
         SVGDB_PHI2_ATTR(2)
-        SVGDB_PHI2_ATTR(3)
         SVGDB_PHI2_ATTR(4)
 #undef SVGDB_PHI2_ATTR
 #define SVGDB_D2_ATTR(M, G, F) \
