@@ -925,8 +925,9 @@ bool grad_use_gemm(const svgdb_ctx *ctx)
 {
     if (ctx->model_kind != MODEL_MVN_SUM) return false;
     if (ctx->grad_gemm >= 0) return ctx->grad_gemm != 0 && ctx->C >= 1;
-    // automatic: mixtures whose precision matrices no longer stay in L1 next to a 16-particle tile, at sizes where a GEMM is not all launch latency
-    return ctx->C >= 2 && ctx->d >= 64 && ctx->n_rows * (int64_t)ctx->C >= 16384;
+    // automatic: at sizes where a GEMM is not all launch latency.  Measured: config 4 (d = 256, C = 16) 37.7 against 83.8 ms, config 3 (d = 64,
+    // one Gaussian, N = 65,536) 0.072 against 0.136 ms -- 2.14 against 2.21 ms per step, the gradient shares the SMs with the distance pass
+    return ctx->d >= 32 && ctx->n_rows * (int64_t)ctx->C >= 16384;
 }
 
 int launch_grad(svgdb_ctx *ctx, cudaStream_t stream)

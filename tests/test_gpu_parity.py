@@ -405,8 +405,8 @@ def test_mixture_gradient_log_sum_exp(sv, oracle):
 
 @pytest.mark.parametrize("n,d,C", [(333, 16, 5), (1000, 64, 3), (700, 5, 2), (2048, 256, 16), (513, 100, 1)])
 def test_mixture_gradient_through_library_gemm(sv, oracle, monkeypatch, n, d, C):
-    """The mixture gradient as C DGEMMs Y = (X - mu_c) Sigma_c^-1 + streaming log-sum-exp kernels (launch_grad_gemm; automatic for
-    mixtures at d >= 64 and n C >= 16,384, forced here): same values as the oracle and as the one-kernel form, incl. far components, a
+    """The mixture gradient as C DGEMMs Y = (X - mu_c) Sigma_c^-1 + streaming log-sum-exp kernels (launch_grad_gemm; automatic at
+    d >= 32 and n C >= 16,384, forced here): same values as the oracle and as the one-kernel form, incl. far components, a
     dimension that is no multiple of anything, one component, and 10 steps of the whole path on top."""
     from svgdcpp_b200 import synth
 
