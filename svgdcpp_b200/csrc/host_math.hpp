@@ -117,5 +117,35 @@ inline void upload_chunk_ends(int n_ipairs, int ends[4])
     for (int ch = 0; ch < 4; ++ch) ends[ch] = ch == 3 ? n_ipairs : (n_ipairs * (ch + 1)) / 4;
 }
 
+// ---- which arithmetic / which kernels a context runs: the measured thresholds in one place (DESIGN.md sections 3 and 5) ------------
+// `forced` arguments: -1 = automatic, 0 = off, 1 = on (environment knobs); `variant`: 0 AUTO, 1 FAST, 2 PRECISE (svgdb_tc32_variant).
+
+// PRECISE unless FAST's zero-mean error terms average out by construction: one Gaussian target, >= 16,384 particles, d >= 8.
+inline bool rule_tc32_precise(int variant, bool one_gaussian_target, int64_t n, int d)
+{
+    if (variant == 1) return false;
+    if (variant == 2) return true;
+    return !(one_gaussian_target && n >= 16384 && d >= 8);
+}
+
+// lean FAST pair kernel (e5m2 `lo_i . y^_j`, row sums on the tensor core): d <= 64 kernels only; pays and keeps the error from d >= 48.
+inline bool rule_phi_lean(bool precise, bool wide, int forced, int64_t n, int d)
+{
+    if (precise || wide) return false;
+    if (forced >= 0) return forced != 0;
+    return d >= 48 && n >= 16384;
+}
+
+// ... and v = grad - 2 a x~ in one fp16 term (E . v_lo left out) once a row has enough neighbours to average the rounding of v_j.
+inline bool rule_phi_one_term_v(int forced, int64_t n) { return forced >= 0 ? forced != 0 : n >= 32768; }
+
+// grad log p through library DGEMMs + streaming kernels instead of the one-kernel form: where a GEMM is not all launch latency.
+inline bool rule_grad_gemm(bool gaussian_sum_model, int forced, int components, int d, int64_t rows)
+{
+    if (!gaussian_sum_model) return false;
+    if (forced >= 0) return forced != 0 && components >= 1;
+    return d >= 32 && rows * (int64_t)components >= 16384;
+}
+
 } // namespace host
 } // namespace svgdb

@@ -420,9 +420,7 @@ int make_u8_map_rows(svgdb_ctx *ctx, CUtensorMap *m, void *base, uint64_t rows, 
 bool tc32_precise(const svgdb_ctx *ctx);
 bool phi_use_f8(const svgdb_ctx *ctx)
 {
-    if (tc32_precise(ctx) || ctx->wide) return false;
-    if (ctx->phi_f8 >= 0) return ctx->phi_f8 != 0;
-    return ctx->d >= 48 && ctx->N >= 16384;
+    return svgdb::host::rule_phi_lean(tc32_precise(ctx), ctx->wide, ctx->phi_f8, ctx->N, ctx->d);
 }
 
 int alloc_tc32(svgdb_ctx *ctx)
@@ -921,13 +919,12 @@ int launch_grad_gemm(svgdb_ctx *ctx, cudaStream_t stream)
     return SVGDB_OK;
 }
 
+// Automatic (rule_grad_gemm, host_math.hpp) at sizes where a GEMM is not all launch latency.  Measured: config 4 (d = 256, C = 16) 37.7 against
+// 83.8 ms, config 3 (d = 64, one Gaussian, N = 65,536) 0.072 against 0.136 ms -- 2.14 against 2.21 ms per step, the gradient shares the SMs
+// with the distance pass.
 bool grad_use_gemm(const svgdb_ctx *ctx)
 {
-    if (ctx->model_kind != MODEL_MVN_SUM) return false;
-    if (ctx->grad_gemm >= 0) return ctx->grad_gemm != 0 && ctx->C >= 1;
-    // automatic: at sizes where a GEMM is not all launch latency.  Measured: config 4 (d = 256, C = 16) 37.7 against 83.8 ms, config 3 (d = 64,
-    // one Gaussian, N = 65,536) 0.072 against 0.136 ms -- 2.14 against 2.21 ms per step, the gradient shares the SMs with the distance pass
-    return ctx->d >= 32 && ctx->n_rows * (int64_t)ctx->C >= 16384;
+    return svgdb::host::rule_grad_gemm(ctx->model_kind == MODEL_MVN_SUM, ctx->grad_gemm, ctx->C, ctx->d, ctx->n_rows);
 }
 
 int launch_grad(svgdb_ctx *ctx, cudaStream_t stream)
@@ -1314,9 +1311,7 @@ int launch_dist_pass_tc32(svgdb_ctx *ctx, int mode, uint64_t lo, uint64_t hi, in
 // 3e-5 at d = 8); mixtures, user models behind the gradient hook, small particle sets and d < 8 get the precise variant (1.5x the MMAs).
 bool tc32_precise(const svgdb_ctx *ctx)
 {
-    if (ctx->tc32_variant == SVGDB_TC32_FAST) return false;
-    if (ctx->tc32_variant == SVGDB_TC32_PRECISE) return true;
-    return !(ctx->model_kind == MODEL_MVN_SUM && ctx->C == 1 && ctx->N >= 16384 && ctx->d >= 8);
+    return svgdb::host::rule_tc32_precise(ctx->tc32_variant, ctx->model_kind == MODEL_MVN_SUM && ctx->C == 1, ctx->N, ctx->d);
 }
 
 // The particle-side operands of the pair kernel (they need X and the bandwidth, not V) and the zeroed accumulator.
@@ -1465,7 +1460,7 @@ int launch_phi_tc32(svgdb_ctx *ctx, bool debug_phi, bool x_operands_done = false
         a.n_ipairs = (chunk_ipairs[ch] + cl - 1) / cl; // i-pair groups
         a.max_seg = ctx->phi_max_seg > 0 ? ctx->phi_max_seg : (tc32_precise(ctx) ? 32 : 128); // j-tiles (128 particles) per flush
         a.poly = ctx->phi_poly;
-        a.no_vlo = ctx->phi_no_vlo >= 0 ? ctx->phi_no_vlo : (ctx->N >= 32768 ? 1 : 0);
+        a.no_vlo = svgdb::host::rule_phi_one_term_v(ctx->phi_no_vlo, ctx->N) ? 1 : 0;
         a.dbg = ctx->phi_dbg_mode;
         a.err = ctx->tc_err;
         a.trace = ctx->tc_trace;

@@ -109,5 +109,37 @@ int main()
     }
 
     if (failures == 0) std::printf("host_math_test: all checks passed\n");
+    { // selection rules (thresholds of DESIGN.md sections 3 and 5)
+        // AUTO: FAST only for one Gaussian, >= 16,384 particles, d >= 8; explicit variants win
+        CHECK(rule_tc32_precise(0, true, 65536, 64) == false);
+        CHECK(rule_tc32_precise(0, true, 16384, 8) == false);
+        CHECK(rule_tc32_precise(0, true, 16383, 64) == true);
+        CHECK(rule_tc32_precise(0, true, 65536, 7) == true);
+        CHECK(rule_tc32_precise(0, false, 262144, 64) == true);
+        CHECK(rule_tc32_precise(1, false, 100, 2) == false);
+        CHECK(rule_tc32_precise(2, true, 65536, 64) == true);
+        // lean pair kernel: FAST, d <= 64 kernels, d >= 48, N >= 16,384; environment override; never with PRECISE or the wide kernels
+        CHECK(rule_phi_lean(false, false, -1, 65536, 64) == true);
+        CHECK(rule_phi_lean(false, false, -1, 16384, 48) == true);
+        CHECK(rule_phi_lean(false, false, -1, 65536, 47) == false);
+        CHECK(rule_phi_lean(false, false, -1, 16383, 64) == false);
+        CHECK(rule_phi_lean(false, false, 1, 128, 2) == true);
+        CHECK(rule_phi_lean(false, false, 0, 65536, 64) == false);
+        CHECK(rule_phi_lean(true, false, 1, 65536, 64) == false);
+        CHECK(rule_phi_lean(false, true, 1, 65536, 128) == false);
+        CHECK(rule_phi_one_term_v(-1, 32768) == true);
+        CHECK(rule_phi_one_term_v(-1, 32767) == false);
+        CHECK(rule_phi_one_term_v(0, 1 << 20) == false);
+        CHECK(rule_phi_one_term_v(1, 128) == true);
+        // gradient through library DGEMMs: Gaussian-sum models only; d >= 32 and rows x components >= 16,384
+        CHECK(rule_grad_gemm(true, -1, 1, 64, 65536) == true);
+        CHECK(rule_grad_gemm(true, -1, 16, 256, 1024) == true);
+        CHECK(rule_grad_gemm(true, -1, 16, 256, 1023) == false);
+        CHECK(rule_grad_gemm(true, -1, 1, 31, 1 << 20) == false);
+        CHECK(rule_grad_gemm(true, -1, 1, 64, 8192) == false);   // config 3 on 8 GPUs: 8192 rows per rank stay with the one-kernel form
+        CHECK(rule_grad_gemm(false, 1, 1, 64, 65536) == false);  // gradient hooks never
+        CHECK(rule_grad_gemm(true, 0, 16, 256, 262144) == false);
+        CHECK(rule_grad_gemm(true, 1, 2, 5, 10) == true);
+    }
     return failures == 0 ? 0 : 1;
 }
